@@ -1,0 +1,100 @@
+"""ctypes binding of libspn_b200.so (the C ABI declared in include/spn_b200.h).
+
+The library is the only compute backend of this package: there is no CPU path and no eager-PyTorch fallback.
+``lib()`` raises if the shared object has not been built (run ``python __graft_entry__.py`` or
+``python -m build_ext`` equivalent: ``build.py``), and every op wrapper raises if its tensors are not CUDA tensors.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libspn_b200.so")
+
+_c_int, _c_i64, _c_u64, _c_ptr = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_void_p
+
+# name -> argtypes, in the order of include/spn_b200.h
+_P, _I, _L, _U = _c_ptr, _c_int, _c_i64, _c_u64
+SIGNATURES = {
+    "spn_version": [ctypes.c_char_p, _I],
+    "spn_leaf_fwd": [_P, _L, _L, _L, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _L, _P],
+    "spn_leaf_bwd_params": [_P, _L, _L, _L, _L, _P, _L, _L, _L, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P,
+                            _P],
+    "spn_leaf_bwd_x": [_P, _L, _L, _L, _L, _P, _L, _L, _L, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L,
+                       _P],
+    "spn_sum_fwd": [_I, _P, _L, _L, _L, _L, _I, _I, _P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L,
+                    _L, _L, _P],
+    "spn_sum_bwd_w": [_I, _P, _L, _L, _L, _L, _I, _I, _P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P,
+                      _L, _L, _L, _L, _P, _L, _P],
+    "spn_sum_bwd_x": [_I, _P, _L, _L, _L, _L, _I, _I, _P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P,
+                      _L, _L, _L, _L, _P, _P],
+    "spn_xprod_fwd": [_P, _I, _I, _I, _I, _P, _P],
+    "spn_xprod_bwd": [_P, _I, _I, _I, _I, _P, _P],
+    "spn_sample_sum": [_P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _I, _P, _P, _L, _L, _L, _L,
+                       _I, _I, _I, _I, _I, _P, _I, _U, _U, _P, _P],
+    "spn_sample_leaf": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _P, _P, _I, _U, _U, _P, _P, _L, _L, _L,
+                        _I, _I, _P, _P, _P],
+}
+
+_lib = None
+LAUNCHES = 0  # number of kernel-launching ABI calls made by this process (bench.py reports it)
+
+
+class SpnAbiError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library once.  Fails loudly when it is missing (no fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SpnAbiError(
+                f"{LIB_PATH} is missing: build the CUDA library first (python __graft_entry__.py, or "
+                f"python conditional-ratspn-for-rl_b200/build.py). This package has no CPU / eager fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if a declared symbol is not exported
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_int
+        _lib = handle
+    return _lib
+
+
+def version() -> str:
+    buf = ctypes.create_string_buffer(128)
+    lib().spn_version(buf, 128)
+    return buf.value.decode()
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        if rc <= -1000:
+            raise SpnAbiError(f"{what}: CUDA error {-(rc + 1000)}")
+        raise SpnAbiError(f"{what}: status {rc} (invalid argument / unsupported shape)")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise SpnAbiError(
+                "ratspn_b200 runs on CUDA (sm_100a) only: got a tensor on "
+                f"{t.device}. Move the model and its inputs to a B200 ('cuda'); there is no CPU path.")
+
+
+def call(name, *args):
+    global LAUNCHES
+    LAUNCHES += 1
+    check(getattr(lib(), name)(*args), name)

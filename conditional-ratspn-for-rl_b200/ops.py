@@ -1,0 +1,225 @@
+"""Autograd wrappers around the C-ABI kernels (include/spn_b200.h).
+
+Each ``torch.autograd.Function`` here is a forward/backward kernel pair; PyTorch only provides device memory, the
+current stream and the autograd tape.  All tensors must live on a CUDA device -- there is no other backend.
+"""
+import math
+
+import torch
+
+from . import _abi
+from ._abi import call, ptr, require_cuda, stream_ptr
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _pow2_ceil(d: int) -> int:
+    return 1 << max(0, (d - 1).bit_length())
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Leaf: permutation gather + Gaussian log-density + tanh correction + NaN marginalisation + product over `card`
+# --------------------------------------------------------------------------------------------------------------
+class LeafFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mu, sigma, perm32, card, tanh_corr):
+        require_cuda(x, mu, sigma, perm32)
+        x, mu, sigma = _f32c(x), _f32c(mu), _f32c(sigma)
+        Wsets, F, I, R = mu.shape
+        *lead, w, Fx, oc, rr = x.shape
+        assert Fx == F and oc in (1, I) and rr in (1, R)
+        assert Wsets in (1, w), f"{Wsets} weight sets cannot be matched with {w} conditionals"
+        B = x.numel() // (F * oc * rr)
+        d0 = -(-F // card)
+        out = torch.empty(*lead, w, d0, I, R, device=x.device, dtype=torch.float32)
+        sx = (F * oc * rr, oc * rr, rr if oc > 1 else 0, 1 if rr > 1 else 0)
+        so = (d0 * I * R, I * R, R, 1)
+        call("spn_leaf_fwd", ptr(x), *sx, ptr(perm32), ptr(mu), ptr(sigma), Wsets, w, B, F, I, R, card, d0,
+             int(tanh_corr), ptr(out), *so, stream_ptr(x.device))
+        ctx.save_for_backward(x, mu, sigma, perm32 if perm32 is not None else torch.empty(0, device=x.device))
+        ctx.meta = (sx, so, Wsets, w, B, F, I, R, card, d0, int(tanh_corr), perm32 is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, mu, sigma, perm32 = ctx.saved_tensors
+        sx, so, Wsets, w, B, F, I, R, card, d0, tanh_corr, has_perm = ctx.meta
+        perm32 = perm32 if has_perm else None
+        g = _f32c(g)
+        dx = dmu = dsigma = None
+        st = stream_ptr(x.device)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dmu = torch.empty_like(mu)
+            dsigma = torch.empty_like(sigma)
+            call("spn_leaf_bwd_params", ptr(g), *so, ptr(x), *sx, ptr(perm32), ptr(mu), ptr(sigma), Wsets, w, B, F,
+                 I, R, card, d0, ptr(dmu), ptr(dsigma), st)
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            call("spn_leaf_bwd_x", ptr(g), *so, ptr(x), *sx, ptr(perm32), ptr(mu), ptr(sigma), Wsets, w, B, F, I, R,
+                 card, d0, tanh_corr, ptr(dx), dx.numel(), st)
+        return dx, dmu, dsigma, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Sum (optionally fused with the CrossProduct below it; optionally the root, which also reduces over repetitions)
+# --------------------------------------------------------------------------------------------------------------
+def _sum_geometry(x, lw, mode):
+    """Returns the integer / stride argument pack shared by spn_sum_fwd / _bwd_w / _bwd_x."""
+    *lead, w, dx_, cx, R = x.shape
+    Wsets = lw.shape[0]
+    assert Wsets in (1, w), f"{Wsets} weight sets cannot be matched with {w} conditionals"
+    B = x.numel() // (dx_ * cx * R)
+    sx = (dx_ * cx * R, cx * R, R, 1)
+    if mode == "sum":
+        _, d_out, ic, oc, Rw = lw.shape
+        assert (d_out, ic, Rw) == (dx_, cx, R), f"input {tuple(x.shape)} does not fit weights {tuple(lw.shape)}"
+        xprod, d_in, c, reduce_r = 0, d_out, 0, 0
+        sw = (d_out * ic * oc * R, ic * oc * R, oc * R, R, 1)
+        out_shape = (*lead, w, d_out, oc, R)
+        so = (d_out * oc * R, oc * R, R, 1)
+    elif mode == "xsum":
+        _, d_out, ic, oc, Rw = lw.shape
+        assert ic == cx * cx and Rw == R and _pow2_ceil(dx_) == 2 * d_out, \
+            f"input {tuple(x.shape)} does not fit weights {tuple(lw.shape)}"
+        xprod, d_in, c, reduce_r = 1, dx_, cx, 0
+        sw = (d_out * ic * oc * R, ic * oc * R, oc * R, R, 1)
+        out_shape = (*lead, w, d_out, oc, R)
+        so = (d_out * oc * R, oc * R, R, 1)
+    elif mode == "xroot":
+        _, one, KR, oc, one2 = lw.shape
+        ic = cx * cx
+        assert one == 1 and one2 == 1 and KR == R * ic and dx_ <= 2, \
+            f"input {tuple(x.shape)} does not fit root weights {tuple(lw.shape)}"
+        xprod, d_in, c, reduce_r, d_out = 1, dx_, cx, 1, 1
+        sw = (KR * oc, 0, oc, 1, ic * oc)
+        out_shape = (*lead, w, 1, oc, 1)
+        so = (oc, 0, 1, 0)
+    else:
+        raise ValueError(mode)
+    ints = (Wsets, w, B, d_out, ic, oc, R, reduce_r)
+    return xprod, sx, d_in, c, sw, ints, so, out_shape
+
+
+class SumFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, lw, mode):
+        require_cuda(x, lw)
+        x, lw = _f32c(x), _f32c(lw)
+        xprod, sx, d_in, c, sw, ints, so, out_shape = _sum_geometry(x, lw, mode)
+        out = torch.empty(out_shape, device=x.device, dtype=torch.float32)
+        call("spn_sum_fwd", xprod, ptr(x), *sx, d_in, c, ptr(lw), *sw, *ints, ptr(out), *so, stream_ptr(x.device))
+        ctx.save_for_backward(x, lw, out)
+        ctx.mode = mode
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, lw, out = ctx.saved_tensors
+        xprod, sx, d_in, c, sw, ints, so, _ = _sum_geometry(x, lw, ctx.mode)
+        g = _f32c(g)
+        st = stream_ptr(x.device)
+        dx = dlw = None
+        if ctx.needs_input_grad[1]:
+            dlw = torch.empty_like(lw)
+            call("spn_sum_bwd_w", xprod, ptr(x), *sx, d_in, c, ptr(lw), *sw, *ints, ptr(out), ptr(g), *so, ptr(dlw),
+                 dlw.numel(), st)
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            call("spn_sum_bwd_x", xprod, ptr(x), *sx, d_in, c, ptr(lw), *sw, *ints, ptr(out), ptr(g), *so, ptr(dx), st)
+        return dx, dlw, None
+
+
+class CrossProductFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        require_cuda(x)
+        x = _f32c(x)
+        *lead, w, d, c, R = x.shape
+        B = x.numel() // (d * c * R)
+        d_out = max(_pow2_ceil(d) // 2, 1)
+        out = torch.empty(*lead, w, d_out, c * c, R, device=x.device, dtype=torch.float32)
+        call("spn_xprod_fwd", ptr(x), B, d, c, R, ptr(out), stream_ptr(x.device))
+        ctx.shape = (tuple(x.shape), B, d, c, R)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, B, d, c, R = ctx.shape
+        g = _f32c(g)
+        dx = torch.empty(shape, device=g.device, dtype=torch.float32)
+        call("spn_xprod_bwd", ptr(g), B, d, c, R, ptr(dx), stream_ptr(g.device))
+        return dx
+
+
+def leaf_forward(x, mu, sigma, perm32, card, tanh_corr):
+    return LeafFn.apply(x, mu, sigma, perm32, card, tanh_corr)
+
+
+def sum_forward(x, lw, mode="sum"):
+    return SumFn.apply(x, lw, mode)
+
+
+def cross_product(x):
+    return CrossProductFn.apply(x)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Sampling kernels (no autograd: index mode)
+# --------------------------------------------------------------------------------------------------------------
+def _i32c(t):
+    return t.to(torch.int32).contiguous() if t is not None else None
+
+
+def sample_sum(lw, root, Q, d, Rs, pa, pa_strides, unravel, rep, xc, Qe, gumbel, mpe, seed=0, q_offset=0):
+    """One Sum layer of the top-down pass (include/spn_b200.h: spn_sample_sum).  Returns int32 [Q, d, Rs]."""
+    require_cuda(lw, pa, rep, xc, gumbel)
+    lw = _f32c(lw)
+    Wsets = lw.shape[0]
+    if root:
+        _, _, KR, oc, _ = lw.shape
+        ic = KR
+        sw = (KR * oc, 0, oc, 1, 0)  # the repetition offset is applied through ic_top inside the kernel
+    else:
+        _, dl, ic, oc, R = lw.shape
+        assert dl == d
+        sw = (dl * ic * oc * R, ic * oc * R, oc * R, R, 1)
+    w = Wsets if Wsets != 1 else 1
+    c, xc_din, sxc, ic_top = 0, 0, (0, 0, 0, 0), 0
+    if xc is not None:
+        xc = _f32c(xc)
+        xc_din, c, Rx = xc.shape[-3:]
+        sxc = (xc_din * c * Rx, c * Rx, Rx, 1)
+    if root:
+        Rr = root  # number of repetitions
+        ic_top = ic // Rr
+        sw = (KR * oc, 0, oc, 1, ic_top * oc)
+        if xc is None:
+            c = int(round(math.sqrt(ic_top)))
+    out = torch.empty(Q, d, Rs, device=lw.device, dtype=torch.int32)
+    call("spn_sample_sum", ptr(lw), *sw, Wsets, w, Q, d, ic, oc, Rs, ptr(pa), *pa_strides, int(unravel), ptr(rep),
+         ptr(xc), *sxc, xc_din, c, Qe, 1 if root else 0, ic_top, ptr(gumbel), int(mpe), seed, q_offset, ptr(out),
+         stream_ptr(lw.device))
+    return out
+
+
+def sample_leaf(mu, sigma, Q, card, Rs, pa, pa_strides, rep, eps, mpe, inv_perm32, evidence, ev_strides, Qe, squash,
+                want_channels=True, seed=0, q_offset=0):
+    """Leaf step + post-processing (include/spn_b200.h: spn_sample_leaf).  Returns (samples [Q,F,Rs], channels)."""
+    require_cuda(mu, sigma, pa, rep, eps, inv_perm32, evidence)
+    mu, sigma = _f32c(mu), _f32c(sigma)
+    Wsets, F, I, R = mu.shape
+    w = Wsets if Wsets != 1 else 1
+    out = torch.empty(Q, F, Rs, device=mu.device, dtype=torch.float32)
+    ch = torch.empty(Q, F, Rs, device=mu.device, dtype=torch.int32) if want_channels else None
+    call("spn_sample_leaf", ptr(mu), ptr(sigma), Wsets, w, Q, F, I, R, card, Rs, ptr(pa), *pa_strides, ptr(rep),
+         ptr(eps), int(mpe), seed, q_offset, ptr(inv_perm32), ptr(evidence), *ev_strides, Qe, int(squash), ptr(out),
+         ptr(ch), stream_ptr(mu.device))
+    return out, ch
+
+
+def launches() -> int:
+    return _abi.LAUNCHES

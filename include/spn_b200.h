@@ -1,0 +1,137 @@
+/*
+ * spn_b200.h -- C ABI of libspn_b200.so: hand-written sm_100a CUDA kernels for the RAT-SPN / CSPN log-space
+ * circuit evaluation (forward log-likelihood, backward, ancestral sampling, entropy building blocks).
+ *
+ * The reference (monoclecat/Conditional-RATSPN-for-RL) has no FFI: its "kernels" are eager ATen expressions inside
+ * Python modules.  Each entry point below replaces one such group of expressions; the reference file:line it
+ * replaces is cited per function.  The Python modules of this repo (rat_spn.py / cspn.py / layers.py /
+ * distributions.py mirrors) bind these symbols with ctypes (see INTEGRATION.md for the stub a reference
+ * maintainer would add).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise
+ *   - activations / parameters are fp32, indices int32, strides are in ELEMENTS (int64) and may be 0 (broadcast)
+ *   - `stream` is a cudaStream_t passed as void*; work is stream ordered; nothing synchronises, nothing allocates
+ *   - return value: 0 = ok, SPN_ERR_ARG = invalid argument, <= -1000 = -(1000 + cudaError_t)
+ *   - row index b runs over prod(batch dims) * w with the conditional w innermost; the weight set used by row b is
+ *     0 when Wsets == 1 (RatSpn: shared weights) and b % w when Wsets == w (CSPN: one set per conditional)
+ *   - weight tensors are addressed as lw[ws*sw_w + s*sw_d + i*sw_i + o*sw_o + r*sw_r]; an inner Sum layer
+ *     [W, d, ic, oc, R] and the root [W, 1, R*ic, C, 1] (channel = r*ic + i) are the same kernel with other strides
+ */
+#ifndef SPN_B200_H
+#define SPN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPN_OK 0
+#define SPN_ERR_ARG (-1)
+#define SPN_ERR_UNSUPPORTED (-2)
+
+/* Library / build identification.  Returns e.g. 100 for sm_100a and writes a version string (host pointer). */
+int spn_version(char* buf, int buflen);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Leaf layer: per-repetition feature permutation + Gaussian log-density + tanh change-of-variables correction +
+ * NaN marginalisation + product over `card` consecutive features, in one pass.
+ * Replaces rat_spn.py:155-170 (apply_permutation), distributions.py:199-246 (RatNormal.forward),
+ * distributions.py:366-382 (pad + IndependentMultivariate.forward) and layers.py:276-312 (Product.forward).
+ *   x     [B, F, 1|I, 1|R]  via strides (sx_i / sx_r = 0 when the dim is broadcast); pre-squash values
+ *   perm  int32 [F, R] or NULL (x_needs_permutation=False)
+ *   mu, sigma [Wsets, F, I, R] contiguous, already bounded (distributions.py:131-154)
+ *   out   [B, d0, I, R] via strides, d0 = ceil(F / card)
+ * ------------------------------------------------------------------------------------------------------------- */
+int spn_leaf_fwd(const float* x, int64_t sx_b, int64_t sx_f, int64_t sx_i, int64_t sx_r, const int32_t* perm,
+                 const float* mu, const float* sigma, int Wsets, int w, int B, int F, int I, int R, int card,
+                 int d0, int tanh_corr, float* out, int64_t so_b, int64_t so_d, int64_t so_c, int64_t so_r,
+                 void* stream);
+
+/* Backward of spn_leaf_fwd w.r.t. the bounded parameters (autograd of the expressions above).
+ *   g [B, d0, I, R] via strides; dmu, dsigma [Wsets, F, I, R] contiguous, fully overwritten. */
+int spn_leaf_bwd_params(const float* g, int64_t sg_b, int64_t sg_d, int64_t sg_c, int64_t sg_r, const float* x,
+                        int64_t sx_b, int64_t sx_f, int64_t sx_i, int64_t sx_r, const int32_t* perm,
+                        const float* mu, const float* sigma, int Wsets, int w, int B, int F, int I, int R,
+                        int card, int d0, float* dmu, float* dsigma, void* stream);
+
+/* Backward of spn_leaf_fwd w.r.t. x (needed for reparameterised samples in the entropy estimator).
+ *   dx has the shape/strides of x (broadcast dims are reduced); it is zeroed and accumulated into. */
+int spn_leaf_bwd_x(const float* g, int64_t sg_b, int64_t sg_d, int64_t sg_c, int64_t sg_r, const float* x,
+                   int64_t sx_b, int64_t sx_f, int64_t sx_i, int64_t sx_r, const int32_t* perm, const float* mu,
+                   const float* sigma, int Wsets, int w, int B, int F, int I, int R, int card, int d0,
+                   int tanh_corr, float* dx, int64_t dx_numel, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Sum layer, optionally fused with the CrossProduct layer below it (the c*c outer sum is never materialised).
+ * Replaces layers.py:419-440 + :545-563 (CrossProduct.forward / split_shuffled_scopes), layers.py:110-128
+ * (Sum.forward: broadcast add + logsumexp) and, with reduce_r = 1, rat_spn.py:230-236 (root merge over repetitions).
+ *   xprod = 1: x [B, d_in, c, R]; scope s of the sum pairs input scopes (2s, 2s+1); scopes >= d_in are zero padding;
+ *              in-channel i = l*c + r'.            xprod = 0: x [B, d_out, ic, R] is the sum input itself.
+ *   out [B, d_out, oc, R]  (reduce_r = 1: [B, d_out, oc], logsumexp additionally runs over r; so_r ignored)
+ * ------------------------------------------------------------------------------------------------------------- */
+int spn_sum_fwd(int xprod, const float* x, int64_t sx_b, int64_t sx_d, int64_t sx_c, int64_t sx_r, int d_in, int c,
+                const float* lw, int64_t sw_w, int64_t sw_d, int64_t sw_i, int64_t sw_o, int64_t sw_r, int Wsets,
+                int w, int B, int d_out, int ic, int oc, int R, int reduce_r, float* out, int64_t so_b,
+                int64_t so_d, int64_t so_o, int64_t so_r, void* stream);
+
+/* Backward of spn_sum_fwd w.r.t. the log-weights: dlw[ws, s, i, o, r] = sum_b g * exp(x_i + lw - out)
+ * (per conditional when Wsets == w).  dlw uses the strides of lw and is fully overwritten. */
+int spn_sum_bwd_w(int xprod, const float* x, int64_t sx_b, int64_t sx_d, int64_t sx_c, int64_t sx_r, int d_in,
+                  int c, const float* lw, int64_t sw_w, int64_t sw_d, int64_t sw_i, int64_t sw_o, int64_t sw_r,
+                  int Wsets, int w, int B, int d_out, int ic, int oc, int R, int reduce_r, const float* out,
+                  const float* g, int64_t so_b, int64_t so_d, int64_t so_o, int64_t so_r, float* dlw,
+                  int64_t dlw_numel, void* stream);
+
+/* Backward of spn_sum_fwd w.r.t. x.  dx is contiguous [B, d_in, c, R] (xprod) or [B, d_out, ic, R]. */
+int spn_sum_bwd_x(int xprod, const float* x, int64_t sx_b, int64_t sx_d, int64_t sx_c, int64_t sx_r, int d_in,
+                  int c, const float* lw, int64_t sw_w, int64_t sw_d, int64_t sw_i, int64_t sw_o, int64_t sw_r,
+                  int Wsets, int w, int B, int d_out, int ic, int oc, int R, int reduce_r, const float* out,
+                  const float* g, int64_t so_b, int64_t so_d, int64_t so_o, int64_t so_r, float* dx, void* stream);
+
+/* Stand-alone CrossProduct (materialising) and its backward: layers.py:419-440.  x [B, d_in, c, R] contiguous,
+ * out [B, ceil_pow2(d_in)/2, c*c, R] contiguous; dx [B, d_in, c, R] contiguous. */
+int spn_xprod_fwd(const float* x, int B, int d_in, int c, int R, float* out, void* stream);
+int spn_xprod_bwd(const float* g, int B, int d_in, int c, int R, float* dx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Top-down ancestral sampling, one Sum layer per call (the CrossProduct index un-ravelling above it is fused).
+ * Replaces layers.py:130-237 (Sum.sample: weight gather, evidence re-weighting, Gumbel-max / MPE argmax) and
+ * layers.py:442-511 (CrossProduct.sample).  Items are (q, s, rs): q in [0, Q) = (node, *n, w) flattened with w
+ * innermost, s a scope of this layer, rs in [0, Rs) (Rs = 1 once a repetition is selected, else R).
+ *   pa      int32 parent choice via strides (sp_q, sp_s, sp_r): unravel = 0 -> out-channel o = pa[q, s, rs];
+ *           unravel = 1 -> pa holds the channel chosen over oc*oc pairs for scope s/2, o = pa / oc or pa % oc
+ *   rep     int32 [Q] selected repetition or NULL (then r = rs)
+ *   xc      NULL, or activations of the layer below from a forward pass on the evidence [Qe, xc_din, c, R] via
+ *           strides; the posterior logit offset is xc[qe, 2s, l, r] + xc[qe, 2s+1, r', r], qe = q % Qe
+ *   root    1: this is the root Sum over R*ic_top channels (d = 1, Rs = 1); the repetition is i / ic_top
+ *   gumbel  [Q, d, ic, Rs] contiguous noise, or NULL with mpe = 1 (argmax) or mpe = 0 (in-kernel Philox, keyed by
+ *           seed and the global element index q_offset-shifted so results do not depend on the GPU count)
+ *   out     int32 [Q, d, Rs] chosen in-channel (first maximal index)
+ * ------------------------------------------------------------------------------------------------------------- */
+int spn_sample_sum(const float* lw, int64_t sw_w, int64_t sw_d, int64_t sw_i, int64_t sw_o, int64_t sw_r, int Wsets,
+                   int w, int Q, int d, int ic, int oc, int Rs, const int32_t* pa, int64_t sp_q, int64_t sp_s,
+                   int64_t sp_r, int unravel, const int32_t* rep, const float* xc, int64_t sxc_b, int64_t sxc_d,
+                   int64_t sxc_c, int64_t sxc_r, int xc_din, int c, int Qe, int root, int ic_top,
+                   const float* gumbel, int mpe, uint64_t seed, uint64_t q_offset, int32_t* out, void* stream);
+
+/* Leaf step of sampling fused with the post-processing: channel fan-out to features, (mu, sigma) gather, Gaussian
+ * draw, inverse permutation of the selected repetition, evidence fill-in, clamp+tanh.
+ * Replaces layers.py:343-362, distributions.py:248-302 + :384-393 and rat_spn.py:538-580.
+ *   pa int32 via strides: channel chosen over I*I pairs for leaf scope s/2 (un-ravelled here)
+ *   eps [Q, F, Rs] contiguous standard-normal noise indexed by *slot* (pre inverse permutation), NULL with mpe=1,
+ *       or NULL with mpe=0 for in-kernel Philox + Box-Muller
+ *   inv_perm int32 [F, R] or NULL (no inverse permutation); evidence via strides or NULL (NaN = sample it)
+ *   out [Q, F, Rs] contiguous; ch_out int32 [Q, F, Rs] (leaf channel per slot) or NULL
+ * ------------------------------------------------------------------------------------------------------------- */
+int spn_sample_leaf(const float* mu, const float* sigma, int Wsets, int w, int Q, int F, int I, int R, int card,
+                    int Rs, const int32_t* pa, int64_t sp_q, int64_t sp_s, int64_t sp_r, const int32_t* rep,
+                    const float* eps, int mpe, uint64_t seed, uint64_t q_offset, const int32_t* inv_perm,
+                    const float* evidence, int64_t se_q, int64_t se_f, int64_t se_r, int Qe, int squash,
+                    float* out, int32_t* ch_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPN_B200_H */
