@@ -223,3 +223,42 @@ def sample_leaf(mu, sigma, Q, card, Rs, pa, pa_strides, rep, eps, mpe, inv_perm3
 
 def launches() -> int:
     return _abi.LAUNCHES
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Tensor-core path (shared weights, internal activation layout [scope][repetition][batch][channel])
+# --------------------------------------------------------------------------------------------------------------
+def tc_supported(c: int, oc: int, R: int) -> bool:
+    return bool(_abi.lib().spn_sum_tc_supported(int(c), int(oc), int(R)))
+
+
+def tc_prepare(lw: torch.Tensor) -> torch.Tensor:
+    """fp32 log-weights [1, d, c*c, oc, R] -> bf16 exp() operand image for spn_sum_tc_fwd (uint8 buffer)."""
+    require_cuda(lw)
+    lw = _f32c(lw)
+    _, d, ic, oc, R = lw.shape
+    c = int(round(math.sqrt(ic)))
+    assert c * c == ic
+    npad = (oc + 15) // 16 * 16
+    wimg = torch.empty(d * R * ic * npad * 2, device=lw.device, dtype=torch.uint8)
+    call("spn_sum_tc_prepare", ptr(lw), d, c, oc, R, ptr(wimg), stream_ptr(lw.device))
+    return wimg
+
+
+def tc_sum_forward(x: torch.Tensor, wimg: torch.Tensor, lw: torch.Tensor) -> torch.Tensor:
+    """x [d_in, R, B, c] -> out [d_out, R, B, oc] (fused CrossProduct + Sum on tcgen05)."""
+    require_cuda(x, wimg, lw)
+    x, lw = _f32c(x), _f32c(lw)
+    d_in, R, B, c = x.shape
+    _, d_out, ic, oc, Rw = lw.shape
+    assert ic == c * c and Rw == R and _pow2_ceil(d_in) == 2 * d_out
+    out = torch.empty(d_out, R, B, oc, device=x.device, dtype=torch.float32)
+    call("spn_sum_tc_fwd", ptr(x), ptr(wimg), ptr(lw), B, d_in, d_out, c, oc, R, ptr(out), stream_ptr(x.device))
+    return out
+
+
+def tc_aborts() -> int:
+    import ctypes
+    v = ctypes.c_int(0)
+    _abi.check(_abi.lib().spn_debug_tc_aborts(ctypes.byref(v)), "spn_debug_tc_aborts")
+    return v.value

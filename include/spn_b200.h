@@ -131,6 +131,22 @@ int spn_sample_leaf(const float* mu, const float* sigma, int Wsets, int w, int Q
                     const float* evidence, int64_t se_q, int64_t se_f, int64_t se_r, int Qe, int squash,
                     float* out, int32_t* ch_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Tensor-core path (tcgen05 + TMEM) for SHARED-weight layers: fused CrossProduct + Sum forward as a bf16 GEMM with
+ * fp32 accumulation; replaces the same reference lines as spn_sum_fwd(xprod = 1) for RatSpn models whose channel
+ * counts are supported (spn_sum_tc_supported).  Activations use the internal layout [scope][repetition][batch][channel]:
+ *   x [d_in, R, B, c] contiguous, out [d_out, R, B, oc] contiguous.
+ * spn_sum_tc_prepare turns fp32 log-weights lw [1, d_out, c*c, oc, R] into the bf16 operand image
+ * (d_out * R * c*c * ceil16(oc) * 2 bytes, caller-allocated) that spn_sum_tc_fwd streams through shared memory.
+ * Outputs whose linear-domain sum underflows are recomputed exactly in fp32 from lw (logsumexp semantics are kept).
+ * ------------------------------------------------------------------------------------------------------------- */
+int spn_sum_tc_supported(int c, int oc, int R);
+int spn_sum_tc_prepare(const float* lw, int d_out, int c, int oc, int R, void* wimg, void* stream);
+int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw, int B, int d_in, int d_out, int c, int oc, int R,
+                   float* out, void* stream);
+/* Debug aid (synchronises): number of CTAs that gave up on an mbarrier wait since the library was loaded. */
+int spn_debug_tc_aborts(int* out_host);
+
 #ifdef __cplusplus
 }
 #endif
