@@ -16,6 +16,8 @@
 // Activations use the internal layout [scope][repetition][batch][channel] so that one thread reads / writes one
 // contiguous row.  Outputs whose linear-domain sum underflows are recomputed exactly in fp32 (same rescue rule as
 // the general kernel in sum.cu), so results keep th.logsumexp semantics.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -29,6 +31,7 @@ struct TcFwdArgs {
     float* out;            // [d_out][R][B][OC]
     int B, d_in, d_out, R, OC;
     int ntiles, nsplit;    // batch tiles of 128 rows; splits of the tile range per (s, r)
+    int debug;             // profiling aid: 1 = skip MMA issue, 2 = skip A generation (results invalid)
 };
 
 // exact fp32 log-sum-exp for one output (rare rescue path)
@@ -50,17 +53,18 @@ __device__ __noinline__ float tc_exact_lse(const float* xl, const float* xr, con
     return m + logf(acc);
 }
 
-template <int C, int OC, int NPAD, int NST>
-__global__ void __launch_bounds__(288, 1) sum_tc_fwd_kernel(TcFwdArgs a) {
+template <int C, int OC, int NPAD, int NST, int LPS>
+__global__ void __launch_bounds__(320, 1) sum_tc_fwd_kernel(TcFwdArgs a) {
     constexpr int NG = NPAD / 8;
     constexpr int K = C * C;
     constexpr int W_BYTES = K * NPAD * 2;
-    constexpr int STEPS = C / 2;              // pipeline stages per tile: two l's (2*C k-values) each
-    constexpr int MMAS_PER_STAGE = 2 * C / 16;
+    constexpr int STEPS = C / LPS;            // pipeline stages per tile: LPS l's (LPS*C k-values) each
+    constexpr int MMAS_PER_STAGE = LPS * C / 16;
     constexpr int ACC_COLS = 64;              // accumulator slot per warpgroup (NPAD <= 64)
-    constexpr int A_COLS = C;                 // 2*C bf16 = C 32-bit columns per stage
+    constexpr int A_COLS = LPS * C / 2;       // LPS*C bf16 = LPS*C/2 32-bit columns per stage
     constexpr int A_BASE = 2 * ACC_COLS;
-    static_assert(C % 8 == 0 && NPAD % 16 == 0 && NPAD <= 64 && OC <= NPAD && OC % 4 == 0, "unsupported shape");
+    static_assert(C % 8 == 0 && NPAD % 16 == 0 && NPAD <= 64 && OC <= NPAD && OC % 4 == 0 && LPS % 2 == 0 && C % LPS == 0,
+                  "unsupported shape");
     static_assert(A_BASE + 2 * NST * A_COLS <= 512, "TMEM budget exceeded");
     constexpr uint32_t IDESC = instr_desc_bf16(128, NPAD, 0, 1);
 
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(288, 1) sum_tc_fwd_kernel(TcFwdArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2 * NST; ++i) {
-            mbar_init(bar_full + i, 128);
+            mbar_init(bar_full + i, 4);  // one arrival per producer warp
             mbar_init(bar_empty + i, 1);
         }
         mbar_init(bar_acc + 0, 1);
@@ -89,7 +93,11 @@ __global__ void __launch_bounds__(288, 1) sum_tc_fwd_kernel(TcFwdArgs a) {
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
+    // The whole TMEM (512 columns) of this SM is ours, so the allocation starts at lane 0 / column 0.  Using the
+    // constant keeps every MMA operand warp-uniform for ptxas; anything else is reported through the abort flag.
+    if (threadIdx.x == 0 && *tmem_slot != 0) *abort_flag = 1;
+    constexpr uint32_t tmem_base = 0;
+    __syncthreads();
 
     const int nitems = a.d_out * a.R * a.nsplit;
     const int tiles_per_split = (a.ntiles + a.nsplit - 1) / a.nsplit;
@@ -106,42 +114,39 @@ __global__ void __launch_bounds__(288, 1) sum_tc_fwd_kernel(TcFwdArgs a) {
         const int tile_end = min(a.ntiles, tile_begin + tiles_per_split);
         __syncthreads();  // every MMA of the previous item has completed (all epilogues waited on bar_acc)
         if (*abort_flag) break;  // uniform: the flag is only written before the barrier above
-        if (warp == 8) {
-            // ===================================== W loader + MMA issuer =====================================
-            if (lane == 0) {
+        if (warp >= 8) {
+            // ============================ MMA issuers (warp 8 -> warpgroup 0, warp 9 -> warpgroup 1) ============================
+            const int wg = warp - 8;
+            if (wg == 0 && lane == 0) {  // warp 8 also streams the weight image into shared memory (TMA bulk copy)
                 mbar_arrive_expect_tx(bar_w, W_BYTES);
                 const uint8_t* src = a.wimg + (size_t)sr * W_BYTES;
                 constexpr int CH = 16384;
                 for (int off = 0; off < W_BYTES; off += CH)
                     bulk_g2s(wsm + off, src + off, min(CH, W_BYTES - off), bar_w);
             }
+            __syncwarp();
             bool ok = mbar_wait(bar_w, items_done & 1, abort_flag);
             fence_after_sync();
             const uint32_t wsm_addr = smem_u32(wsm);
-            for (int t0 = tile_begin; t0 < tile_end && ok; t0 += 2) {
-                for (int step = 0; step < STEPS && ok; ++step) {
+            const uint32_t acc = tmem_base + wg * ACC_COLS;
+            for (int tile = tile_begin + wg; tile < tile_end && ok; tile += 2) {
+                for (int step = 0; step < STEPS; ++step) {
+                    const uint32_t st = mma_stage[0] % NST, par = (mma_stage[0] / NST) & 1;
+                    ok = mbar_wait(bar_full + wg * NST + st, par, abort_flag);
+                    if (!ok) break;
+                    fence_after_sync();
+                    const uint32_t abase = tmem_base + A_BASE + (wg * NST + st) * A_COLS;
+                    const int kg0 = step * (LPS * C / 8);  // first 8-row K group of this stage
+                    if (a.debug != 1) {
 #pragma unroll
-                    for (int wg = 0; wg < 2; ++wg) {
-                        if (t0 + wg >= tile_end) continue;
-                        const uint32_t st = mma_stage[wg] % NST, par = (mma_stage[wg] / NST) & 1;
-                        ok = ok && mbar_wait(bar_full + wg * NST + st, par, abort_flag);
-                        fence_after_sync();
-                        if (lane == 0 && ok) {
-                            const uint32_t acc = tmem_base + wg * ACC_COLS;
-                            const uint32_t abase = tmem_base + A_BASE + (wg * NST + st) * A_COLS;
-                            const int kg0 = step * (2 * C / 8);  // first 8-row K group of this stage
-#pragma unroll
-                            for (int kk = 0; kk < MMAS_PER_STAGE; ++kk) {
-                                const uint64_t bdesc =
-                                    smem_desc(wsm_addr + (uint32_t)(kg0 + 2 * kk) * (NG * 128), NG * 128, 128);
-                                mma_ts(acc, abase + kk * 8, bdesc, IDESC, (step | kk) ? 1u : 0u);
-                            }
-                            mma_commit(bar_empty + wg * NST + st);
-                            if (step == STEPS - 1) mma_commit(bar_acc + wg);
+                        for (int kk = 0; kk < MMAS_PER_STAGE; ++kk) {
+                            const uint64_t bdesc = smem_desc(wsm_addr + (uint32_t)(kg0 + 2 * kk) * (NG * 128), NG * 128, 128);
+                            mma_ts_uniform(acc, abase + kk * 8, bdesc, IDESC, (step | kk) ? 1u : 0u);
                         }
-                        __syncwarp();
-                        ++mma_stage[wg];
                     }
+                    mma_commit_uniform(bar_empty + wg * NST + st);
+                    if (step == STEPS - 1) mma_commit_uniform(bar_acc + wg);
+                    ++mma_stage[0];
                 }
             }
         } else {
@@ -159,29 +164,34 @@ __global__ void __launch_bounds__(288, 1) sum_tc_fwd_kernel(TcFwdArgs a) {
                 uint32_t eL[C / 2], eR[C / 2];
                 float mL = 0.f, mR = 0.f;
                 {
-                    float v[C];
+                    float vl[C], vr[C];  // both rows are requested before either is consumed (one exposed latency)
 #pragma unroll
                     for (int q = 0; q < C / 4; ++q) {
-                        float4 t = (valid && has_l) ? reinterpret_cast<const float4*>(xl)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                        const float4 t = (valid && has_l) ? reinterpret_cast<const float4*>(xl)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        vl[4 * q] = t.x; vl[4 * q + 1] = t.y; vl[4 * q + 2] = t.z; vl[4 * q + 3] = t.w;
                     }
-                    float m = v[0];
 #pragma unroll
-                    for (int q = 1; q < C; ++q) m = fmaxf(m, v[q]);
+                    for (int q = 0; q < C / 4; ++q) {
+                        const float4 t = (valid && has_r) ? reinterpret_cast<const float4*>(xr)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        vr[4 * q] = t.x; vr[4 * q + 1] = t.y; vr[4 * q + 2] = t.z; vr[4 * q + 3] = t.w;
+                    }
+                    // pull the rows of this warpgroup's next tile towards L2 while this tile is being processed
+                    if (tile + 2 < tile_end && b + 256 < a.B) {
+                        const char* nl = reinterpret_cast<const char*>(xl + (int64_t)256 * C);
+                        const char* nr = reinterpret_cast<const char*>(xr + (int64_t)256 * C);
+                        if (has_l) { prefetch_l2(nl); prefetch_l2(nl + C * 4 - 4); }
+                        if (has_r) { prefetch_l2(nr); prefetch_l2(nr + C * 4 - 4); }
+                    }
+                    float m = vl[0], m2 = vr[0];
+#pragma unroll
+                    for (int q = 1; q < C; ++q) { m = fmaxf(m, vl[q]); m2 = fmaxf(m2, vr[q]); }
                     mL = (m == -CUDART_INF_F) ? 0.f : m;
+                    mR = (m2 == -CUDART_INF_F) ? 0.f : m2;
 #pragma unroll
-                    for (int q = 0; q < C / 2; ++q) eL[q] = pack_bf16(__expf(v[2 * q] - mL), __expf(v[2 * q + 1] - mL));
-#pragma unroll
-                    for (int q = 0; q < C / 4; ++q) {
-                        float4 t = (valid && has_r) ? reinterpret_cast<const float4*>(xr)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                    for (int q = 0; q < C / 2; ++q) {
+                        eL[q] = pack_bf16(__expf(vl[2 * q] - mL), __expf(vl[2 * q + 1] - mL));
+                        eR[q] = pack_bf16(__expf(vr[2 * q] - mR), __expf(vr[2 * q + 1] - mR));
                     }
-                    m = v[0];
-#pragma unroll
-                    for (int q = 1; q < C; ++q) m = fmaxf(m, v[q]);
-                    mR = (m == -CUDART_INF_F) ? 0.f : m;
-#pragma unroll
-                    for (int q = 0; q < C / 2; ++q) eR[q] = pack_bf16(__expf(v[2 * q] - mR), __expf(v[2 * q + 1] - mR));
                 }
 #pragma unroll
                 for (int step = 0; step < STEPS; ++step) {
@@ -189,18 +199,24 @@ __global__ void __launch_bounds__(288, 1) sum_tc_fwd_kernel(TcFwdArgs a) {
                     ok = ok && mbar_wait(bar_empty + wg * NST + st, par ^ 1, abort_flag);
                     if (!ok) break;
                     fence_after_sync();
-                    uint32_t p[C];
-                    // two l's per stage: l = 2*step (low half of eL[step]) and 2*step + 1 (high half)
-                    const uint32_t l0 = bcast_lo(eL[step]), l1 = bcast_hi(eL[step]);
+                    const uint32_t stage_addr = tmem_base + lane_base + A_BASE + (wg * NST + st) * A_COLS;
 #pragma unroll
-                    for (int q = 0; q < C / 2; ++q) {
-                        p[q] = hmul2_bf16(l0, eR[q]);
-                        p[C / 2 + q] = hmul2_bf16(l1, eR[q]);
+                    for (int h = 0; h < LPS / 2; ++h) {
+                        // two l's per store batch: l = 2*j (low half of eL[j]) and 2*j + 1 (high half), j = step*LPS/2 + h
+                        uint32_t p[C];
+                        const uint32_t e = eL[step * (LPS / 2) + h];
+                        const uint32_t l0 = bcast_lo(e), l1 = bcast_hi(e);
+#pragma unroll
+                        for (int q = 0; q < C / 2; ++q) {
+                            p[q] = hmul2_bf16(l0, eR[q]);
+                            p[C / 2 + q] = hmul2_bf16(l1, eR[q]);
+                        }
+                        if (a.debug != 2) tmem_store_cols<C>(stage_addr + h * C, p);
                     }
-                    tmem_store_cols<C>(tmem_base + lane_base + A_BASE + (wg * NST + st) * A_COLS, p);
                     tmem_wait_st();
                     fence_before_sync();
-                    mbar_arrive(bar_full + wg * NST + st);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_full + wg * NST + st);
                     ++g_stage;
                 }
                 if (!ok) break;
@@ -222,7 +238,7 @@ __global__ void __launch_bounds__(288, 1) sum_tc_fwd_kernel(TcFwdArgs a) {
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const float sum = __uint_as_float(acc[o4 + u]);
-                            if (sum >= 1e-30f) {
+                            if (sum >= 1e-30f || a.debug) {
                                 res[u] = shift + __logf(sum);
                             } else {
                                 const float* lwp = a.lw + ((int64_t)s * K * OC + (o4 + u)) * a.R + r;
@@ -268,13 +284,13 @@ __global__ void __launch_bounds__(256) tc_wimage_kernel(const float* __restrict_
     }
 }
 
-template <int C, int OC, int NPAD, int NST>
+template <int C, int OC, int NPAD, int NST, int LPS>
 static int launch_tc_fwd(const TcFwdArgs& a, cudaStream_t st) {
     constexpr int W_BYTES = C * C * NPAD * 2;
     constexpr int SMEM = W_BYTES + (4 * NST + 3) * 8 + 16;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(sum_tc_fwd_kernel<C, OC, NPAD, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaError_t e = cudaFuncSetAttribute(sum_tc_fwd_kernel<C, OC, NPAD, NST, LPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return spn_cuda_status(e);
         configured = true;
     }
@@ -283,7 +299,7 @@ static int launch_tc_fwd(const TcFwdArgs& a, cudaStream_t st) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int nitems = a.d_out * a.R * a.nsplit;
     const int grid = nitems < sms ? nitems : sms;
-    sum_tc_fwd_kernel<C, OC, NPAD, NST><<<grid, 288, SMEM, st>>>(a);
+    sum_tc_fwd_kernel<C, OC, NPAD, NST, LPS><<<grid, 320, SMEM, st>>>(a);
     return spn_launch_status();
 }
 
@@ -316,10 +332,14 @@ extern "C" int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw,
     if (nsplit > a.ntiles / 4) nsplit = a.ntiles / 4;
     if (nsplit < 1) nsplit = 1;
     a.nsplit = nsplit;
+    {
+        const char* dbg = getenv("SPN_TC_DEBUG");
+        a.debug = dbg ? atoi(dbg) : 0;
+    }
     cudaStream_t st = (cudaStream_t)stream;
-    if (c == 40) return launch_tc_fwd<40, 40, 48, 4>(a, st);
-    if (c == 32) return launch_tc_fwd<32, 32, 32, 4>(a, st);
-    if (c == 16) return launch_tc_fwd<16, 16, 16, 4>(a, st);
+    if (c == 40) return launch_tc_fwd<40, 40, 48, 2, 4>(a, st);
+    if (c == 32) return launch_tc_fwd<32, 32, 32, 2, 4>(a, st);
+    if (c == 16) return launch_tc_fwd<16, 16, 16, 2, 4>(a, st);
     return SPN_ERR_UNSUPPORTED;
 }
 
