@@ -9,7 +9,7 @@ struct SumArgs {
     const float* lw; int64_t sw_w, sw_d, sw_i, sw_o, sw_r;
     int Wsets, w, B, d_out, ic, oc, R, reduce_r;
     float* out; const float* outc; const float* g; int64_t so_b, so_d, so_o, so_r;
-    float* dlw; float* dx; int nsplit;
+    float* dlw; float* dx; int64_t sdx_b, sdx_d, sdx_c, sdx_r; int nsplit;
 };
 
 // value of in-channel i of sum scope s for row b, repetition r
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256) sum_bwd_x_kernel(SumArgs a) {
             acc += gp[(int64_t)o * a.so_o] * __expf(xi + lwi[(int64_t)o * a.sw_o] - ov);
         }
     }
-    a.dx[tid] = acc;
+    a.dx[b * a.sdx_b + (int64_t)sc * a.sdx_d + (int64_t)ch * a.sdx_c + (int64_t)r * a.sdx_r] = acc;
 }
 
 // Stand-alone CrossProduct (materialising), contiguous in/out.
@@ -300,13 +300,14 @@ extern "C" int spn_sum_bwd_x(int xprod, const float* x, int64_t sx_b, int64_t sx
                              int d_in, int c, const float* lw, int64_t sw_w, int64_t sw_d, int64_t sw_i, int64_t sw_o,
                              int64_t sw_r, int Wsets, int w, int B, int d_out, int ic, int oc, int R, int reduce_r,
                              const float* out, const float* g, int64_t so_b, int64_t so_d, int64_t so_o, int64_t so_r,
-                             float* dx, void* stream) {
+                             float* dx, int64_t sdx_b, int64_t sdx_d, int64_t sdx_c, int64_t sdx_r, void* stream) {
     SumArgs a{};
     int rc = fill_args(a, xprod, x, sx_b, sx_d, sx_c, sx_r, d_in, c, lw, sw_w, sw_d, sw_i, sw_o, sw_r, Wsets, w, B,
                        d_out, ic, oc, R, reduce_r, so_b, so_d, so_o, so_r);
     if (rc != SPN_OK || !out || !g || !dx) return SPN_ERR_ARG;
     if (B == 0) return SPN_OK;
     a.outc = out; a.g = g; a.dx = dx;
+    a.sdx_b = sdx_b; a.sdx_d = sdx_d; a.sdx_c = sdx_c; a.sdx_r = sdx_r;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total = (int64_t)B * (xprod ? d_in * c : d_out * ic) * R;
     if (xprod) sum_bwd_x_kernel<true><<<spn_blocks(total, 256), 256, 0, st>>>(a);

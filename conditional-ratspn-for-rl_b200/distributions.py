@@ -202,7 +202,8 @@ class IndependentMultivariate(Leaf):
             x = F.pad(x, pad=[0, 0, 0, 0, 0, self._pad], mode="constant", value=0.0)
         return x
 
-    def forward(self, x: th.Tensor, reduction='sum', detach_params: bool = False, perm32: th.Tensor = None):
+    def forward(self, x: th.Tensor, reduction='sum', detach_params: bool = False, perm32: th.Tensor = None,
+                layout: str = "ref"):
         """x [*batch, w, F, 1|I, 1|R] -> [*batch, w, ceil(F/card), I, R].  ``perm32`` (int32 [F, R]) applies the
         model's per-repetition feature permutation inside the kernel."""
         base = self.base_leaf
@@ -211,7 +212,7 @@ class IndependentMultivariate(Leaf):
                 raise NotImplementedError("permutation fusion requires the default (sum) reduction")
             return self.prod(self.pad_input(base(x, detach_params=detach_params)), reduction=reduction)
         mu, sigma = base._params_for(detach_params)
-        return ops.leaf_forward(x, mu, sigma, perm32, self.cardinality, base.tanh_correction_enabled)
+        return ops.leaf_forward(x, mu, sigma, perm32, self.cardinality, base.tanh_correction_enabled, layout)
 
     def sample(self, mode: str = None, ctx: Sample = None):
         if not ctx.is_root:

@@ -26,7 +26,7 @@ def _pow2_ceil(d: int) -> int:
 # --------------------------------------------------------------------------------------------------------------
 class LeafFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, mu, sigma, perm32, card, tanh_corr):
+    def forward(ctx, x, mu, sigma, perm32, card, tanh_corr, layout="ref"):
         require_cuda(x, mu, sigma, perm32)
         x, mu, sigma = _f32c(x), _f32c(mu), _f32c(sigma)
         Wsets, F, I, R = mu.shape
@@ -35,9 +35,13 @@ class LeafFn(torch.autograd.Function):
         assert Wsets in (1, w), f"{Wsets} weight sets cannot be matched with {w} conditionals"
         B = x.numel() // (F * oc * rr)
         d0 = -(-F // card)
-        out = torch.empty(*lead, w, d0, I, R, device=x.device, dtype=torch.float32)
         sx = (F * oc * rr, oc * rr, rr if oc > 1 else 0, 1 if rr > 1 else 0)
-        so = (d0 * I * R, I * R, R, 1)
+        if layout == "ref":      # [*batch, w, d0, I, R]
+            out = torch.empty(*lead, w, d0, I, R, device=x.device, dtype=torch.float32)
+            so = (d0 * I * R, I * R, R, 1)
+        else:                    # internal layout of the tensor-core path: [d0, R, B, I]
+            out = torch.empty(d0, R, B, I, device=x.device, dtype=torch.float32)
+            so = (I, R * B * I, 1, B * I)
         call("spn_leaf_fwd", ptr(x), *sx, ptr(perm32), ptr(mu), ptr(sigma), Wsets, w, B, F, I, R, card, d0,
              int(tanh_corr), ptr(out), *so, stream_ptr(x.device))
         ctx.save_for_backward(x, mu, sigma, perm32 if perm32 is not None else torch.empty(0, device=x.device))
@@ -61,19 +65,27 @@ class LeafFn(torch.autograd.Function):
             dx = torch.empty_like(x)
             call("spn_leaf_bwd_x", ptr(g), *so, ptr(x), *sx, ptr(perm32), ptr(mu), ptr(sigma), Wsets, w, B, F, I, R,
                  card, d0, tanh_corr, ptr(dx), dx.numel(), st)
-        return dx, dmu, dsigma, None, None, None
+        return dx, dmu, dsigma, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------------------------------
 # Sum (optionally fused with the CrossProduct below it; optionally the root, which also reduces over repetitions)
 # --------------------------------------------------------------------------------------------------------------
-def _sum_geometry(x, lw, mode):
-    """Returns the integer / stride argument pack shared by spn_sum_fwd / _bwd_w / _bwd_x."""
-    *lead, w, dx_, cx, R = x.shape
+def _sum_geometry(x, lw, mode, layout="ref"):
+    """Returns the integer / stride argument pack shared by spn_sum_fwd / _bwd_w / _bwd_x.
+
+    layout 'ref': x [*batch, w, d, c, R] (reference layout); 'drbc': x [d, R, B, c] (internal, shared weights only)."""
     Wsets = lw.shape[0]
+    if layout == "ref":
+        *lead, w, dx_, cx, R = x.shape
+        B = x.numel() // (dx_ * cx * R)
+        sx = (dx_ * cx * R, cx * R, R, 1)
+    else:
+        dx_, R, B, cx = x.shape
+        lead, w = (B,), 1
+        sx = (cx, R * B * cx, 1, B * cx)
+        assert Wsets == 1, "the internal layout is only used with shared weights"
     assert Wsets in (1, w), f"{Wsets} weight sets cannot be matched with {w} conditionals"
-    B = x.numel() // (dx_ * cx * R)
-    sx = (dx_ * cx * R, cx * R, R, 1)
     if mode == "sum":
         _, d_out, ic, oc, Rw = lw.shape
         assert (d_out, ic, Rw) == (dx_, cx, R), f"input {tuple(x.shape)} does not fit weights {tuple(lw.shape)}"
@@ -89,6 +101,9 @@ def _sum_geometry(x, lw, mode):
         sw = (d_out * ic * oc * R, ic * oc * R, oc * R, R, 1)
         out_shape = (*lead, w, d_out, oc, R)
         so = (d_out * oc * R, oc * R, R, 1)
+        if layout != "ref":
+            out_shape = (d_out, R, B, oc)
+            so = (oc, R * B * oc, 1, B * oc)
     elif mode == "xroot":
         _, one, KR, oc, one2 = lw.shape
         ic = cx * cx
@@ -100,37 +115,61 @@ def _sum_geometry(x, lw, mode):
         so = (oc, 0, 1, 0)
     else:
         raise ValueError(mode)
+    assert layout == "ref" or mode in ("xsum", "xroot")
     ints = (Wsets, w, B, d_out, ic, oc, R, reduce_r)
     return xprod, sx, d_in, c, sw, ints, so, out_shape
 
 
+def _sum_backward(x, lw, out, g, mode, layout, need_dx, need_dlw):
+    """Exact fp32 backward kernels (general path)."""
+    xprod, sx, d_in, c, sw, ints, so, _ = _sum_geometry(x, lw, mode, layout)
+    g = _f32c(g)
+    st = stream_ptr(x.device)
+    dx = dlw = None
+    if need_dlw:
+        dlw = torch.empty_like(lw)
+        call("spn_sum_bwd_w", xprod, ptr(x), *sx, d_in, c, ptr(lw), *sw, *ints, ptr(out), ptr(g), *so, ptr(dlw),
+             dlw.numel(), st)
+    if need_dx:
+        dx = torch.empty_like(x)
+        call("spn_sum_bwd_x", xprod, ptr(x), *sx, d_in, c, ptr(lw), *sw, *ints, ptr(out), ptr(g), *so, ptr(dx), *sx, st)
+    return dx, dlw
+
+
 class SumFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, lw, mode):
+    def forward(ctx, x, lw, mode, layout="ref"):
         require_cuda(x, lw)
         x, lw = _f32c(x), _f32c(lw)
-        xprod, sx, d_in, c, sw, ints, so, out_shape = _sum_geometry(x, lw, mode)
+        xprod, sx, d_in, c, sw, ints, so, out_shape = _sum_geometry(x, lw, mode, layout)
         out = torch.empty(out_shape, device=x.device, dtype=torch.float32)
         call("spn_sum_fwd", xprod, ptr(x), *sx, d_in, c, ptr(lw), *sw, *ints, ptr(out), *so, stream_ptr(x.device))
         ctx.save_for_backward(x, lw, out)
-        ctx.mode = mode
+        ctx.mode, ctx.layout = mode, layout
         return out
 
     @staticmethod
     def backward(ctx, g):
         x, lw, out = ctx.saved_tensors
-        xprod, sx, d_in, c, sw, ints, so, _ = _sum_geometry(x, lw, ctx.mode)
-        g = _f32c(g)
-        st = stream_ptr(x.device)
-        dx = dlw = None
-        if ctx.needs_input_grad[1]:
-            dlw = torch.empty_like(lw)
-            call("spn_sum_bwd_w", xprod, ptr(x), *sx, d_in, c, ptr(lw), *sw, *ints, ptr(out), ptr(g), *so, ptr(dlw),
-                 dlw.numel(), st)
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            call("spn_sum_bwd_x", xprod, ptr(x), *sx, d_in, c, ptr(lw), *sw, *ints, ptr(out), ptr(g), *so, ptr(dx), st)
-        return dx, dlw, None
+        dx, dlw = _sum_backward(x, lw, out, g, ctx.mode, ctx.layout, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return dx, dlw, None, None
+
+
+class SumTcFn(torch.autograd.Function):
+    """Shared-weight fused CrossProduct + Sum on the tensor cores; activations in the internal [d, R, B, c] layout."""
+
+    @staticmethod
+    def forward(ctx, x, lw):
+        wimg = tc_prepare(lw)
+        out = tc_sum_forward(x, wimg, lw)
+        ctx.save_for_backward(x, lw, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, lw, out = ctx.saved_tensors
+        dx, dlw = _sum_backward(x, lw, out, g, "xsum", "drbc", ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return dx, dlw
 
 
 class CrossProductFn(torch.autograd.Function):
@@ -155,12 +194,16 @@ class CrossProductFn(torch.autograd.Function):
         return dx
 
 
-def leaf_forward(x, mu, sigma, perm32, card, tanh_corr):
-    return LeafFn.apply(x, mu, sigma, perm32, card, tanh_corr)
+def leaf_forward(x, mu, sigma, perm32, card, tanh_corr, layout="ref"):
+    return LeafFn.apply(x, mu, sigma, perm32, card, tanh_corr, layout)
 
 
-def sum_forward(x, lw, mode="sum"):
-    return SumFn.apply(x, lw, mode)
+def sum_forward(x, lw, mode="sum", layout="ref"):
+    return SumFn.apply(x, lw, mode, layout)
+
+
+def sum_forward_tc(x, lw):
+    return SumTcFn.apply(x.contiguous(), lw.contiguous())
 
 
 def cross_product(x):

@@ -223,8 +223,10 @@ class RatSpn(nn.Module):
         if self.training and cfg.dropout > 0.0:
             return self._forward_layerwise(x, layer_index, x_needs_permutation, detach_params)
 
-        h = self._leaf(x, detach_params=detach_params, perm32=perm32)
         caching = self.root._is_input_cache_enabled
+        if self._tensor_core_path_ok(x, caching):
+            return self._forward_tensor_core(x, layer_index, perm32, detach_params)
+        h = self._leaf(x, detach_params=detach_params, perm32=perm32)
         for li in range(1, min(layer_index, self.max_layer_index - 1) + 1):
             layer = self._inner_layers[li - 1]
             if li % 2 == 1:
@@ -238,6 +240,37 @@ class RatSpn(nn.Module):
             if caching:
                 self.root._input_cache_fused = h.detach()
             h = ops.sum_forward(h, self.root._weights_for(detach_params), "xroot")
+        return h
+
+    # rows below which the exact fp32 kernels are used even when the tensor-core path is available (tiles are 128 rows)
+    tensor_core_min_rows = 256
+    use_tensor_cores = True
+
+    def _tensor_core_path_ok(self, x: th.Tensor, caching: bool) -> bool:
+        """Shared weights (RatSpn), supported channel counts, enough rows to fill 128-row tiles, no evidence cache."""
+        cfg = self.config
+        if not (self.use_tensor_cores and cfg.is_ratspn) or caching or cfg.D < 2:
+            return False
+        rows = x.numel() // (x.shape[-3] * x.shape[-2] * x.shape[-1])
+        if rows < self.tensor_core_min_rows:
+            return False
+        if cfg.D > 2 and cfg.I != cfg.S:
+            pass  # S_1 pairs leaf channels (c = I), the layers above pair sum channels (c = S); both must be supported
+        return ops.tc_supported(cfg.I, cfg.S, cfg.R) and (cfg.D == 2 or ops.tc_supported(cfg.S, cfg.S, cfg.R))
+
+    def _forward_tensor_core(self, x, layer_index, perm32, detach_params):
+        """Same evaluation with activations in the internal [scope, repetition, row, channel] layout and every inner
+        Sum layer on the tcgen05 kernel; the root (N = C outputs, GEMV-shaped) stays on the exact fp32 kernel."""
+        batch_shape = x.shape[:-3]  # (*batch_dims, w)
+        h = self._leaf(x, detach_params=detach_params, perm32=perm32, layout="drbc")
+        for li in range(2, min(layer_index, self.max_layer_index - 1) + 1, 2):
+            h = ops.sum_forward_tc(h, self._inner_layers[li - 1]._weights_for(detach_params))
+        if layer_index == self.max_layer_index:
+            out = ops.sum_forward(h, self.root._weights_for(detach_params), "xroot", "drbc")  # [B, 1, 1, C, 1]
+            return out.reshape(*batch_shape, 1, self.config.C, 1)
+        h = h.permute(2, 0, 3, 1).reshape(*batch_shape, h.shape[0], h.shape[3], h.shape[1])  # -> [*batch, w, d, c, R]
+        if layer_index % 2 == 1:
+            h = self._inner_layers[layer_index - 1](h)
         return h
 
     def _forward_layerwise(self, x, layer_index, x_needs_permutation, detach_params):

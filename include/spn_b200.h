@@ -84,11 +84,13 @@ int spn_sum_bwd_w(int xprod, const float* x, int64_t sx_b, int64_t sx_d, int64_t
                   const float* g, int64_t so_b, int64_t so_d, int64_t so_o, int64_t so_r, float* dlw,
                   int64_t dlw_numel, void* stream);
 
-/* Backward of spn_sum_fwd w.r.t. x.  dx is contiguous [B, d_in, c, R] (xprod) or [B, d_out, ic, R]. */
+/* Backward of spn_sum_fwd w.r.t. x.  dx [B, d_in, c, R] (xprod) or [B, d_out, ic, R], addressed through its own
+ * strides (sdx_*); every element is written exactly once. */
 int spn_sum_bwd_x(int xprod, const float* x, int64_t sx_b, int64_t sx_d, int64_t sx_c, int64_t sx_r, int d_in,
                   int c, const float* lw, int64_t sw_w, int64_t sw_d, int64_t sw_i, int64_t sw_o, int64_t sw_r,
                   int Wsets, int w, int B, int d_out, int ic, int oc, int R, int reduce_r, const float* out,
-                  const float* g, int64_t so_b, int64_t so_d, int64_t so_o, int64_t so_r, float* dx, void* stream);
+                  const float* g, int64_t so_b, int64_t so_d, int64_t so_o, int64_t so_r, float* dx, int64_t sdx_b,
+                  int64_t sdx_d, int64_t sdx_c, int64_t sdx_r, void* stream);
 
 /* Stand-alone CrossProduct (materialising) and its backward: layers.py:419-440.  x [B, d_in, c, R] contiguous,
  * out [B, ceil_pow2(d_in)/2, c*c, R] contiguous; dx [B, d_in, c, R] contiguous. */

@@ -50,3 +50,50 @@ def test_tc_forward_keeps_logsumexp_semantics_on_underflow_and_minus_inf():
     assert not torch.isnan(out).any()
     assert (out[:, :, 1:] - ref[:, :, 1:]).abs().max().item() < 2e-2
     assert ops.tc_aborts() == 0
+
+
+def test_model_forward_backward_on_tensor_core_path_vs_oracle():
+    """Whole-model check of the tensor-core path (internal layout, tcgen05 Sum layers, exact root) against the CPU
+    oracle: |d LL| <= 1e-4 relative (BASELINE.json tolerance), parameter gradients within 2% of the tensor's max."""
+    import numpy as np
+    import ratspn_b200 as rb
+    from oracle import spn_oracle as O
+    torch.manual_seed(5)
+    np.random.seed(5)
+    F, D, R, S, I, C = 64, 3, 3, 16, 16, 2
+    cfg = rb.RatSpnConfig()
+    cfg.F, cfg.D, cfg.R, cfg.S, cfg.I, cfg.C = F, D, R, S, I, C
+    cfg.dropout, cfg.leaf_base_class, cfg.leaf_base_kwargs, cfg.tanh_squash = 0.0, rb.RatNormal, {}, False
+    m = rb.RatSpn(cfg)
+    arch = O.Arch(F=F, D=D, R=R, S=S, I=I, C=C)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    raw = {}
+    for k in list(sd):
+        if k.split(".")[-1] in ("weight_param", "mean_param", "std_param") and not k.startswith("_sampling_root"):
+            sd[k] = sd[k].requires_grad_(True)
+            raw[k] = sd[k]
+    B = 300
+    x = torch.randn(B, 1, F, 1, 1)
+    x[7, 0, ::5] = float("nan")
+    ref = O.forward(O.params_from_ratspn_state(sd, arch), arch, x)
+    (-ref.mean()).backward()
+    m = m.to(DEV)
+    assert m._tensor_core_path_ok(x.to(DEV), False)
+    out = m(x.to(DEV))
+    rel = ((out.cpu() - ref).abs() / ref.abs().clamp_min(1.0)).max().item()
+    assert rel < 1e-4, f"relative LL error {rel}"
+    (-out.mean()).backward()
+    for k, p in m.named_parameters():
+        if p.requires_grad:
+            g, r = p.grad.cpu(), raw[k].grad
+            assert (g - r).abs().max().item() <= 2e-2 * r.abs().max().item() + 1e-9, k
+    # partial forwards through the internal layout agree with the exact path
+    m.use_tensor_cores = False
+    exact2 = m(x.to(DEV), layer_index=2)
+    exact3 = m(x.to(DEV), layer_index=3)
+    m.use_tensor_cores = True
+    assert (m(x.to(DEV), layer_index=2) - exact2).abs().max().item() < 2e-2
+    assert (m(x.to(DEV), layer_index=3) - exact3).abs().max().item() < 4e-2
+    assert torch.equal(m(x.to(DEV), layer_index=0), m._leaf(x.to(DEV), perm32=m._perm32()[0]))
+    from ratspn_b200 import ops
+    assert ops.tc_aborts() == 0
