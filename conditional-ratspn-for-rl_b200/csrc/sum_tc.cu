@@ -344,10 +344,14 @@ extern "C" int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw,
 }
 
 // debug: number of CTAs that hit the bounded-wait timeout since the library was loaded (synchronises)
+int tc_bwd_aborts_host(int* out);
+
 extern "C" int spn_debug_tc_aborts(int* out_host) {
-    int v = 0;
+    int v = 0, w = 0;
     cudaError_t e = cudaMemcpyFromSymbol(&v, g_tc_aborts, sizeof(int));
     if (e != cudaSuccess) return spn_cuda_status(e);
-    if (out_host) *out_host = v;
+    int rc = tc_bwd_aborts_host(&w);
+    if (rc != SPN_OK) return rc;
+    if (out_host) *out_host = v + w;
     return SPN_OK;
 }

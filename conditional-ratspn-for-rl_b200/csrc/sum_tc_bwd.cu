@@ -1,0 +1,565 @@
+// Backward of the shared-weight CrossProduct+Sum layer on the tensor cores (tcgen05 + TMEM); see sum_tc.cu for the
+// forward formulation.  With E[b,k] = eL[b,l] eR[b,r'] (k = l*c + r'), W = exp(log-weights) and
+// G[b,o] = g[b,o] * exp(mL + mR - out[b,o])  (= g / linear-domain sum), SURVEY A.5 becomes two GEMMs:
+//
+//   dX:  dE[b,k] = sum_o G[b,o] W[k,o]            (M = 128 rows, N = k-chunk, K = o)      -> spn_sum_tc_bwd_x
+//        dxL[b,l] = eL[b,l] * sum_r' eR[b,r'] dE[b,l,r'],  dxR[b,r'] = eR[b,r'] * sum_l eL[b,l] dE[b,l,r']
+//   dW:  dWlin[k,o] = sum_b E[b,k] G[b,o]         (M = k-chunk of 128, N = o, K = rows)   -> spn_sum_tc_bwd_w
+//        d(log w)[k,o] = W[k,o] * dWlin[k,o]      (applied by the layout-restoring epilogue kernel)
+//
+// dX reuses the forward's weight image as a K-major B operand (same bytes, other descriptor); its A operand (G) is
+// written to TMEM once per tile and the 128 x N fp32 product is consumed straight out of TMEM by the CUDA cores.
+// dW contracts over the batch, so both operands are generated per row into shared memory (MN-major core matrices:
+// one 16-byte store per 8 elements, conflict free) and the accumulators for up to 7 k-chunks stay resident in TMEM
+// while the CTA walks over every batch tile.
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+using namespace tc;
+
+__device__ int g_tc_bwd_aborts = 0;
+
+struct TcBwdArgs {
+    const float* x;       // [d_in][R][B][C]
+    const float* out;     // [d_out][R][B][OC]
+    const float* g;       // [d_out][R][B][OC]
+    const uint8_t* wimg;  // forward weight image (dX only)
+    float* dx;            // [d_in][R][B][C]                (dX)
+    float* dwt;           // [d_out][R][K][OC] linear-domain weight gradient (dW)
+    int B, d_in, d_out, R;
+    int ntiles, nsplit;
+};
+
+// Recompute the forward's per-row quantities: packed bf16 eL / eR, and G = g * exp(mL + mR - out) packed bf16.
+template <int C, int OC, int NPAD>
+__device__ __forceinline__ void tc_bwd_prologue(const TcBwdArgs& a, int s, int r, int64_t b, bool valid, uint32_t* eL,
+                                                uint32_t* eR, uint32_t* Gp) {
+    const bool has_l = 2 * s < a.d_in, has_r = 2 * s + 1 < a.d_in;
+    const float* xl = a.x + (((int64_t)(2 * s) * a.R + r) * a.B + (valid ? b : 0)) * C;
+    const float* xr = a.x + (((int64_t)(2 * s + 1) * a.R + r) * a.B + (valid ? b : 0)) * C;
+    const float* op = a.out + (((int64_t)s * a.R + r) * a.B + (valid ? b : 0)) * OC;
+    const float* gp = a.g + (((int64_t)s * a.R + r) * a.B + (valid ? b : 0)) * OC;
+    float vl[C], vr[C];
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q) {
+        const float4 t = (valid && has_l) ? reinterpret_cast<const float4*>(xl)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        vl[4 * q] = t.x; vl[4 * q + 1] = t.y; vl[4 * q + 2] = t.z; vl[4 * q + 3] = t.w;
+    }
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q) {
+        const float4 t = (valid && has_r) ? reinterpret_cast<const float4*>(xr)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        vr[4 * q] = t.x; vr[4 * q + 1] = t.y; vr[4 * q + 2] = t.z; vr[4 * q + 3] = t.w;
+    }
+    float m = vl[0], m2 = vr[0];
+#pragma unroll
+    for (int q = 1; q < C; ++q) { m = fmaxf(m, vl[q]); m2 = fmaxf(m2, vr[q]); }
+    const float mL = (m == -CUDART_INF_F) ? 0.f : m;
+    const float mR = (m2 == -CUDART_INF_F) ? 0.f : m2;
+#pragma unroll
+    for (int q = 0; q < C / 2; ++q) {
+        eL[q] = pack_bf16(__expf(vl[2 * q] - mL), __expf(vl[2 * q + 1] - mL));
+        eR[q] = pack_bf16(__expf(vr[2 * q] - mR), __expf(vr[2 * q + 1] - mR));
+    }
+    const float shift = mL + mR;
+    float G[NPAD];
+#pragma unroll
+    for (int q = 0; q < OC / 4; ++q) {
+        const float4 o4 = valid ? reinterpret_cast<const float4*>(op)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 g4 = valid ? reinterpret_cast<const float4*>(gp)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        // out = -inf (impossible row): no gradient.  exp argument <= ~0 whenever out is finite.
+        // G = g / (linear-domain sum) = g * exp(shift - out) >= g.  out = -inf (impossible row): no gradient.  The
+        // exponent is capped so that rows whose sum underflowed in the forward (rescue path) stay finite.
+        G[4 * q] = o4.x == -CUDART_INF_F ? 0.f : g4.x * __expf(fminf(shift - o4.x, 80.f));
+        G[4 * q + 1] = o4.y == -CUDART_INF_F ? 0.f : g4.y * __expf(fminf(shift - o4.y, 80.f));
+        G[4 * q + 2] = o4.z == -CUDART_INF_F ? 0.f : g4.z * __expf(fminf(shift - o4.z, 80.f));
+        G[4 * q + 3] = o4.w == -CUDART_INF_F ? 0.f : g4.w * __expf(fminf(shift - o4.w, 80.f));
+    }
+#pragma unroll
+    for (int q = OC; q < NPAD; ++q) G[q] = 0.f;
+#pragma unroll
+    for (int q = 0; q < NPAD / 2; ++q) Gp[q] = pack_bf16(G[2 * q], G[2 * q + 1]);
+}
+
+// ================================================================================================================
+// dX
+// ================================================================================================================
+// Roles as in the forward: warps 0-3 / 4-7 = two row-tile warpgroups (prologue + TMEM epilogue), warp 8 / 9 = their MMA
+// issuers (warp 8 also streams the weight image).  Per tile the k axis is processed in chunks of LPS*C columns
+// through NBUF TMEM buffers per warpgroup.
+template <int C, int OC, int NPAD, int LPS, int NBUF>
+__global__ void __launch_bounds__(320, 1) sum_tc_bwd_x_kernel(TcBwdArgs a) {
+    constexpr int NG = NPAD / 8;
+    constexpr int K = C * C;
+    constexpr int W_BYTES = K * NPAD * 2;
+    constexpr int NCH = LPS * C;               // dE columns per chunk
+    constexpr int CHUNKS = C / LPS;
+    constexpr int G_COLS = 32;                 // NPAD/2 <= 32 packed-bf16 columns for the A operand
+    constexpr int WG_COLS = G_COLS + NBUF * NCH;
+    static_assert(NPAD <= 64 && NCH % 16 == 0 && NCH <= 256 && 2 * WG_COLS <= 512, "unsupported shape");
+    constexpr uint32_t IDESC = instr_desc_bf16(128, NCH, 0, 0);
+    constexpr int STAGE_F = 128 * (C + 1);     // per-warpgroup dxL staging (row-major, +1 float padding)
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* wsm = smem;
+    float* stage = reinterpret_cast<float*>(smem + W_BYTES);              // [2][128][C+1]
+    uint64_t* bar_a = reinterpret_cast<uint64_t*>(stage + 2 * STAGE_F);   // [2]       G operand written (4 warp arrivals)
+    uint64_t* bar_dfull = bar_a + 2;                                      // [2][NBUF] chunk product ready (commit)
+    uint64_t* bar_dfree = bar_dfull + 2 * NBUF;                           // [2][NBUF] chunk consumed (4 warp arrivals)
+    uint64_t* bar_w = bar_dfree + 2 * NBUF;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 1);
+    volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a + 0, 4);
+        mbar_init(bar_a + 1, 4);
+        for (int i = 0; i < 2 * NBUF; ++i) {
+            mbar_init(bar_dfull + i, 1);
+            mbar_init(bar_dfree + i, 4);
+        }
+        mbar_init(bar_w, 1);
+        *abort_flag = 0;
+        mbar_fence_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (threadIdx.x == 0 && *tmem_slot != 0) *abort_flag = 1;
+    constexpr uint32_t tmem_base = 0;
+    __syncthreads();
+
+    const int nitems = a.d_out * a.R * a.nsplit;
+    const int tiles_per_split = (a.ntiles + a.nsplit - 1) / a.nsplit;
+    uint32_t n_tiles_done = 0;   // per role: tiles processed by this warpgroup (bar_a phase)
+    uint32_t n_chunks = 0;       // per role: chunks processed by this warpgroup (buffer ring position)
+    uint32_t items_done = 0;
+
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++items_done) {
+        const int split = item % a.nsplit;
+        const int sr = item / a.nsplit;
+        const int r = sr % a.R, s = sr / a.R;
+        const int tile_begin = split * tiles_per_split;
+        const int tile_end = min(a.ntiles, tile_begin + tiles_per_split);
+        __syncthreads();
+        if (*abort_flag) break;
+        if (warp >= 8) {
+            const int wg = warp - 8;
+            if (wg == 0 && lane == 0) {
+                mbar_arrive_expect_tx(bar_w, W_BYTES);
+                const uint8_t* src = a.wimg + (size_t)sr * W_BYTES;
+                constexpr int CH = 16384;
+                for (int off = 0; off < W_BYTES; off += CH) bulk_g2s(wsm + off, src + off, min(CH, W_BYTES - off), bar_w);
+            }
+            __syncwarp();
+            bool ok = mbar_wait(bar_w, items_done & 1, abort_flag);
+            fence_after_sync();
+            const uint32_t wsm_addr = smem_u32(wsm);
+            const uint32_t wg_base = tmem_base + wg * WG_COLS;
+            for (int tile = tile_begin + wg; tile < tile_end && ok; tile += 2) {
+                ok = mbar_wait(bar_a + wg, n_tiles_done & 1, abort_flag);
+                ++n_tiles_done;
+                if (!ok) break;
+                fence_after_sync();
+                for (int ch = 0; ch < CHUNKS; ++ch) {
+                    const uint32_t buf = n_chunks % NBUF, par = (n_chunks / NBUF) & 1;
+                    ok = mbar_wait(bar_dfree + wg * NBUF + buf, par ^ 1, abort_flag);
+                    if (!ok) break;
+                    fence_after_sync();
+                    const uint32_t dcol = wg_base + G_COLS + buf * NCH;
+                    const int kg0 = ch * (NCH / 8);
+#pragma unroll
+                    for (int kk = 0; kk < NPAD / 16; ++kk) {
+                        // B[N = k, K = o] K-major: 8-row groups along N are NG*128 bytes apart, the two K halves 128 bytes
+                        const uint64_t bdesc = smem_desc(wsm_addr + (uint32_t)(kg0 * NG + 2 * kk) * 128, 128, NG * 128);
+                        mma_ts_uniform(dcol, wg_base + kk * 8, bdesc, IDESC, kk ? 1u : 0u);
+                    }
+                    mma_commit_uniform(bar_dfull + wg * NBUF + buf);
+                    ++n_chunks;
+                }
+            }
+        } else {
+            const int wg = warp >> 2;
+            const int row = threadIdx.x & 127;
+            const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+            const uint32_t wg_base = tmem_base + lane_base + wg * WG_COLS;
+            float* my_stage = stage + wg * STAGE_F + row * (C + 1);
+            bool ok = true;
+            for (int tile = tile_begin + wg; tile < tile_end && ok; tile += 2) {
+                const int64_t b = (int64_t)tile * 128 + row;
+                const bool valid = b < a.B;
+                uint32_t eL[C / 2], eRp[C / 2], Gp[NPAD / 2];
+                tc_bwd_prologue<C, OC, NPAD>(a, s, r, b, valid, eL, eRp, Gp);
+                // the previous tile's MMAs (which read the G columns) completed before its last chunk was consumed
+                {
+                    uint32_t gz[G_COLS];
+#pragma unroll
+                    for (int q = 0; q < G_COLS; ++q) gz[q] = q < NPAD / 2 ? Gp[q] : 0u;
+                    tmem_store_cols<G_COLS>(wg_base, gz);
+                }
+                tmem_wait_st();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_a + wg);
+                float eR[C], tR[C];
+#pragma unroll
+                for (int q = 0; q < C / 2; ++q) {
+                    eR[2 * q] = bf16_lo(eRp[q]);
+                    eR[2 * q + 1] = bf16_hi(eRp[q]);
+                    tR[2 * q] = 0.f;
+                    tR[2 * q + 1] = 0.f;
+                }
+#pragma unroll
+                for (int ch = 0; ch < CHUNKS; ++ch) {
+                    const uint32_t buf = n_chunks % NBUF, par = (n_chunks / NBUF) & 1;
+                    ok = ok && mbar_wait(bar_dfull + wg * NBUF + buf, par, abort_flag);
+                    if (!ok) break;
+                    fence_after_sync();
+#pragma unroll
+                    for (int h = 0; h < LPS; ++h) {
+                        const int l = ch * LPS + h;
+                        uint32_t v[C];
+#pragma unroll
+                        for (int q = 0; q < C / 8; ++q) tmem_ld8(wg_base + G_COLS + buf * NCH + h * C + q * 8, v + q * 8);
+                        tmem_wait_ld();
+                        const float el = (l & 1) ? bf16_hi(eL[l / 2]) : bf16_lo(eL[l / 2]);
+                        float tl = 0.f;
+#pragma unroll
+                        for (int q = 0; q < C; ++q) {
+                            const float d = __uint_as_float(v[q]);
+                            tl = fmaf(eR[q], d, tl);
+                            tR[q] = fmaf(el, d, tR[q]);
+                        }
+                        my_stage[l] = el * tl;
+                    }
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_dfree + wg * NBUF + buf);
+                    ++n_chunks;
+                }
+                if (!ok) break;
+                if (valid) {
+                    if (2 * s < a.d_in) {
+                        float* dl = a.dx + (((int64_t)(2 * s) * a.R + r) * a.B + b) * C;
+#pragma unroll
+                        for (int q = 0; q < C / 4; ++q)
+                            reinterpret_cast<float4*>(dl)[q] =
+                                make_float4(my_stage[4 * q], my_stage[4 * q + 1], my_stage[4 * q + 2], my_stage[4 * q + 3]);
+                    }
+                    if (2 * s + 1 < a.d_in) {
+                        float* dr = a.dx + (((int64_t)(2 * s + 1) * a.R + r) * a.B + b) * C;
+#pragma unroll
+                        for (int q = 0; q < C / 4; ++q)
+                            reinterpret_cast<float4*>(dr)[q] =
+                                make_float4(eR[4 * q] * tR[4 * q], eR[4 * q + 1] * tR[4 * q + 1],
+                                            eR[4 * q + 2] * tR[4 * q + 2], eR[4 * q + 3] * tR[4 * q + 3]);
+                    }
+                }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (threadIdx.x == 0 && *abort_flag) atomicAdd(&g_tc_bwd_aborts, 1);
+    if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+// ================================================================================================================
+// dW
+// ================================================================================================================
+// The k axis (c*c products) is split into 8x8 blocks (8 left channels x 8 right channels); a chunk is two blocks =
+// 128 k-values = the M extent of one MMA.  chunk -> k mapping (also used by tc_dw_finish_kernel):
+//   block = 2*chunk + m/64, l = 8*(block / (C/8)) + (m%64)/8, r' = 8*(block % (C/8)) + m%8, k = l*C + r'.
+// One work item = (scope, repetition, group of <= GC chunks); it walks over all row tiles and keeps its accumulators
+// in TMEM.  Warps 0-3 / 4-7 produce the operands of alternating tiles into shared memory, warp 8 issues every MMA.
+template <int C, int OC, int NPAD, int GC>
+__global__ void __launch_bounds__(288, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int ngroups) {
+    constexpr int NG = NPAD / 8;
+    constexpr int K = C * C;
+    constexpr int NBLK = (C / 8) * (C / 8);
+    constexpr int NCHUNK = (NBLK + 1) / 2;
+    constexpr int A_BYTES = 128 * 128 * 2;     // [16 row-groups][16 m-groups][8][8] bf16
+    constexpr int G_BYTES = 128 * NPAD * 2;    // [16 row-groups][NG][8][8] bf16
+    constexpr int NSTA = 2;                    // A stages per warpgroup
+    static_assert(GC * NPAD <= 512, "TMEM budget exceeded");
+    constexpr uint32_t IDESC = instr_desc_bf16(128, NPAD, 1, 1);
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* abuf = smem;                                   // [2 wg][NSTA][A_BYTES]
+    uint8_t* gbuf = smem + 2 * NSTA * A_BYTES;              // [2 wg][G_BYTES]
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(gbuf + 2 * G_BYTES);  // [2][NSTA]
+    uint64_t* bar_empty = bar_full + 2 * NSTA;                              // [2][NSTA]
+    uint64_t* bar_gfree = bar_empty + 2 * NSTA;                             // [2] G tile no longer read
+    uint64_t* bar_done = bar_gfree + 2;                                     // [1] all MMAs of the item complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 1);
+    volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2 * NSTA; ++i) {
+            mbar_init(bar_full + i, 4);
+            mbar_init(bar_empty + i, 1);
+        }
+        mbar_init(bar_gfree + 0, 1);
+        mbar_init(bar_gfree + 1, 1);
+        mbar_init(bar_done, 1);
+        *abort_flag = 0;
+        mbar_fence_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (threadIdx.x == 0 && *tmem_slot != 0) *abort_flag = 1;
+    constexpr uint32_t tmem_base = 0;
+    __syncthreads();
+
+    const int nitems = a.d_out * a.R * ngroups;
+    uint32_t n_stage[2] = {0, 0};   // producer: own counter in [0]; MMA warp: one per warpgroup
+    uint32_t n_gtile[2] = {0, 0};
+    uint32_t items_done = 0;
+
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++items_done) {
+        const int grp = item % ngroups;
+        const int sr = item / ngroups;
+        const int r = sr % a.R, s = sr / a.R;
+        const int chunk_begin = grp * GC;
+        const int chunk_end = min(NCHUNK, chunk_begin + GC);
+        __syncthreads();
+        if (*abort_flag) break;
+        if (warp == 8) {
+            // ---------------------------------------- MMA issuer ----------------------------------------
+            bool ok = true;
+            const uint32_t abuf_addr = smem_u32(abuf), gbuf_addr = smem_u32(gbuf);
+            for (int t0 = 0; t0 < a.ntiles && ok; t0 += 2) {
+#pragma unroll
+                for (int wg = 0; wg < 2; ++wg) {
+                    const int tile = t0 + wg;
+                    if (tile >= a.ntiles) continue;
+                    for (int ch = chunk_begin; ch < chunk_end; ++ch) {
+                        const uint32_t st = n_stage[wg] % NSTA, par = (n_stage[wg] / NSTA) & 1;
+                        ok = ok && mbar_wait(bar_full + wg * NSTA + st, par, abort_flag);
+                        if (!ok) break;
+                        fence_after_sync();
+                        const uint32_t aaddr = abuf_addr + (wg * NSTA + st) * A_BYTES;
+                        const uint32_t gaddr = gbuf_addr + wg * G_BYTES;
+                        const uint32_t dcol = tmem_base + (ch - chunk_begin) * NPAD;
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            // A[M = k, K = row] MN-major: 8-element groups along M are 128 B apart, 8-row groups along K 2048 B
+                            const uint64_t adesc = smem_desc(aaddr + (uint32_t)(2 * t) * 2048, 2048, 128);
+                            // B[K = row, N = o] MN-major: 8-element groups along N 128 B apart, 8-row groups NG*128 B
+                            const uint64_t bdesc = smem_desc(gaddr + (uint32_t)(2 * t) * (NG * 128), NG * 128, 128);
+                            mma_ss_uniform(dcol, adesc, bdesc, IDESC, (tile | t) ? 1u : 0u);
+                        }
+                        mma_commit_uniform(bar_empty + wg * NSTA + st);
+                        ++n_stage[wg];
+                    }
+                    if (!ok) break;
+                    mma_commit_uniform(bar_gfree + wg);
+                }
+            }
+            if (ok) mma_commit_uniform(bar_done);
+        } else {
+            // ---------------------------------------- operand producers ----------------------------------------
+            const int wg = warp >> 2;
+            const int row = threadIdx.x & 127;
+            bool ok = true;
+            uint8_t* my_g = gbuf + wg * G_BYTES + ((row >> 3) * NG) * 128 + (row & 7) * 16;
+            for (int tile = wg; tile < a.ntiles && ok; tile += 2) {
+                const int64_t b = (int64_t)tile * 128 + row;
+                const bool valid = b < a.B;
+                uint32_t eL[C / 2], eR[C / 2], Gp[NPAD / 2];
+                tc_bwd_prologue<C, OC, NPAD>(a, s, r, b, valid, eL, eR, Gp);
+                if (!valid) {
+#pragma unroll
+                    for (int q = 0; q < NPAD / 2; ++q) Gp[q] = 0u;  // rows past the batch contribute nothing
+                }
+                // G tile of the previous tile of this warpgroup must have been consumed
+                ok = mbar_wait(bar_gfree + wg, (n_gtile[0] & 1) ^ 1, abort_flag);
+                ++n_gtile[0];
+                if (!ok) break;
+#pragma unroll
+                for (int og = 0; og < NG; ++og)
+                    *reinterpret_cast<uint4*>(my_g + og * 128) = make_uint4(Gp[4 * og], Gp[4 * og + 1], Gp[4 * og + 2], Gp[4 * og + 3]);
+#pragma unroll 1
+                for (int ch = chunk_begin; ch < chunk_end; ++ch) {
+                    const uint32_t st = n_stage[0] % NSTA, par = (n_stage[0] / NSTA) & 1;
+                    ok = mbar_wait(bar_empty + wg * NSTA + st, par ^ 1, abort_flag);
+                    if (!ok) break;
+                    uint8_t* my_a = abuf + (wg * NSTA + st) * A_BYTES + ((row >> 3) * 16) * 128 + (row & 7) * 16;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int blk = 2 * ch + half;
+                        const int lb = blk / (C / 8), rb = blk % (C / 8);
+                        // eR for r' in [8 rb, 8 rb + 8): 4 packed registers, selected without dynamic register indexing
+                        uint32_t er[4], el4[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { er[q] = 0u; el4[q] = 0u; }
+#pragma unroll
+                        for (int j = 0; j < C / 8; ++j) {
+                            if (j == rb && blk < NBLK) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) er[q] = eR[4 * j + q];
+                            }
+                            if (j == lb && blk < NBLK) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) el4[q] = eL[4 * j + q];
+                            }
+                        }
+#pragma unroll
+                        for (int li = 0; li < 8; ++li) {
+                            const uint32_t e = el4[li >> 1];
+                            const uint32_t l2 = (li & 1) ? bcast_hi(e) : bcast_lo(e);
+                            *reinterpret_cast<uint4*>(my_a + (half * 8 + li) * 128) =
+                                make_uint4(hmul2_bf16(l2, er[0]), hmul2_bf16(l2, er[1]), hmul2_bf16(l2, er[2]), hmul2_bf16(l2, er[3]));
+                        }
+                    }
+                    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_full + wg * NSTA + st);
+                    ++n_stage[0];
+                }
+            }
+            // ---------------------------------------- epilogue: TMEM -> dwt ----------------------------------------
+            ok = ok && mbar_wait(bar_done, items_done & 1, abort_flag);
+            if (ok) {
+                fence_after_sync();
+                const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+                for (int ch = chunk_begin + wg; ch < chunk_end; ch += 2) {
+                    uint32_t v[NPAD];
+#pragma unroll
+                    for (int q = 0; q < NPAD / 8; ++q) tmem_ld8(tmem_base + lane_base + (ch - chunk_begin) * NPAD + q * 8, v + q * 8);
+                    tmem_wait_ld();
+                    const int blk = 2 * ch + (row >> 6);
+                    if (blk < NBLK) {
+                        const int l = 8 * (blk / (C / 8)) + ((row & 63) >> 3);
+                        const int rp = 8 * (blk % (C / 8)) + (row & 7);
+                        float* dst = a.dwt + (((int64_t)s * a.R + r) * K + (l * C + rp)) * OC;
+#pragma unroll
+                        for (int q = 0; q < OC / 4; ++q)
+                            reinterpret_cast<float4*>(dst)[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                                            __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                    }
+                }
+                fence_before_sync();
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (threadIdx.x == 0 && *abort_flag) atomicAdd(&g_tc_bwd_aborts, 1);
+    if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+// dlw[0][s][k][o][r] = exp(lw[0][s][k][o][r]) * dwt[s][r][k][o]: restores the parameter layout (R innermost) and applies
+// d exp / d log w.  One block per (s, tile of 32 k); tiles go through shared memory so both sides stay coalesced.
+__global__ void __launch_bounds__(256) tc_dw_finish_kernel(const float* __restrict__ lw, const float* __restrict__ dwt,
+                                                          float* __restrict__ dlw, int d, int K, int OC, int R) {
+    extern __shared__ float tile[];  // [R][KT*OC + 1]
+    constexpr int KT = 4;
+    const int kt = blockIdx.x % (K / KT);
+    const int s = blockIdx.x / (K / KT);
+    const int n = KT * OC;
+    for (int i = threadIdx.x; i < R * n; i += blockDim.x) {
+        const int r = i / n, e = i % n;
+        tile[r * (n + 1) + e] = dwt[(((int64_t)s * R + r) * K + (int64_t)kt * KT) * OC + e];
+    }
+    __syncthreads();
+    const int64_t base = ((int64_t)s * K + (int64_t)kt * KT) * OC * R;
+    for (int i = threadIdx.x; i < n * R; i += blockDim.x) {
+        const int e = i / R, r = i % R;
+        dlw[base + i] = __expf(lw[base + i]) * tile[r * (n + 1) + e];
+    }
+}
+
+extern "C" int spn_sum_tc_supported(int c, int oc, int R);
+
+template <int C, int OC, int NPAD, int LPS, int NBUF>
+static int launch_bwd_x(const TcBwdArgs& a, cudaStream_t st) {
+    constexpr int SMEM = C * C * NPAD * 2 + 2 * 128 * (C + 1) * 4 + (3 + 4 * NBUF) * 8 + 16;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(sum_tc_bwd_x_kernel<C, OC, NPAD, LPS, NBUF>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return spn_cuda_status(e);
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int nitems = a.d_out * a.R * a.nsplit;
+    sum_tc_bwd_x_kernel<C, OC, NPAD, LPS, NBUF><<<nitems < sms ? nitems : sms, 320, SMEM, st>>>(a);
+    return spn_launch_status();
+}
+
+template <int C, int OC, int NPAD, int GC>
+static int launch_bwd_w(const TcBwdArgs& a, cudaStream_t st) {
+    constexpr int NCHUNK = ((C / 8) * (C / 8) + 1) / 2;
+    constexpr int NGROUPS = (NCHUNK + GC - 1) / GC;
+    constexpr int SMEM = 2 * 2 * 128 * 128 * 2 + 2 * 128 * NPAD * 2 + (4 * 2 + 3) * 8 + 16;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(sum_tc_bwd_w_kernel<C, OC, NPAD, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return spn_cuda_status(e);
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int nitems = a.d_out * a.R * NGROUPS;
+    sum_tc_bwd_w_kernel<C, OC, NPAD, GC><<<nitems < sms ? nitems : sms, 288, SMEM, st>>>(a, NGROUPS);
+    return spn_launch_status();
+}
+
+extern "C" int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g, const void* wimg, int B, int d_in,
+                                int d_out, int c, int oc, int R, float* dx, void* stream) {
+    if (!x || !out || !g || !wimg || !dx || B <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
+    if (!spn_sum_tc_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
+    TcBwdArgs a{};
+    a.x = x; a.out = out; a.g = g; a.wimg = (const uint8_t*)wimg; a.dx = dx;
+    a.B = B; a.d_in = d_in; a.d_out = d_out; a.R = R;
+    a.ntiles = (B + 127) / 128;
+    int nsplit = (4 * 148 + d_out * R - 1) / (d_out * R);
+    if (nsplit > a.ntiles / 4) nsplit = a.ntiles / 4;
+    if (nsplit < 1) nsplit = 1;
+    a.nsplit = nsplit;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c == 40) return launch_bwd_x<40, 40, 48, 2, 2>(a, st);
+    if (c == 32) return launch_bwd_x<32, 32, 32, 2, 2>(a, st);
+    if (c == 16) return launch_bwd_x<16, 16, 16, 2, 2>(a, st);
+    return SPN_ERR_UNSUPPORTED;
+}
+
+extern "C" int spn_sum_tc_bwd_w(const float* x, const float* out, const float* g, const float* lw, int B, int d_in,
+                                int d_out, int c, int oc, int R, float* dwt_workspace, float* dlw, void* stream) {
+    if (!x || !out || !g || !lw || !dwt_workspace || !dlw || B <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
+    if (!spn_sum_tc_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
+    TcBwdArgs a{};
+    a.x = x; a.out = out; a.g = g; a.dwt = dwt_workspace;
+    a.B = B; a.d_in = d_in; a.d_out = d_out; a.R = R;
+    a.ntiles = (B + 127) / 128;
+    a.nsplit = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (c == 40) rc = launch_bwd_w<40, 40, 48, 7>(a, st);
+    else if (c == 32) rc = launch_bwd_w<32, 32, 32, 8>(a, st);
+    else if (c == 16) rc = launch_bwd_w<16, 16, 16, 2>(a, st);
+    else return SPN_ERR_UNSUPPORTED;
+    if (rc != SPN_OK) return rc;
+    const int K = c * c;
+    const size_t smem = (size_t)R * (4 * oc + 1) * sizeof(float);
+    tc_dw_finish_kernel<<<d_out * (K / 4), 256, smem, st>>>(lw, dwt_workspace, dlw, d_out, K, oc, R);
+    return spn_launch_status();
+}
+
+int tc_bwd_aborts_host(int* out) {
+    int v = 0;
+    cudaError_t e = cudaMemcpyFromSymbol(&v, g_tc_bwd_aborts, sizeof(int));
+    if (e != cudaSuccess) return spn_cuda_status(e);
+    *out = v;
+    return SPN_OK;
+}

@@ -162,13 +162,14 @@ class SumTcFn(torch.autograd.Function):
     def forward(ctx, x, lw):
         wimg = tc_prepare(lw)
         out = tc_sum_forward(x, wimg, lw)
-        ctx.save_for_backward(x, lw, out)
+        ctx.save_for_backward(x, lw, out, wimg)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x, lw, out = ctx.saved_tensors
-        dx, dlw = _sum_backward(x, lw, out, g, "xsum", "drbc", ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        x, lw, out, wimg = ctx.saved_tensors
+        dx = tc_sum_backward_x(x, out, g, wimg, lw) if ctx.needs_input_grad[0] else None
+        dlw = tc_sum_backward_w(x, out, g, lw) if ctx.needs_input_grad[1] else None
         return dx, dlw
 
 
@@ -298,6 +299,30 @@ def tc_sum_forward(x: torch.Tensor, wimg: torch.Tensor, lw: torch.Tensor) -> tor
     out = torch.empty(d_out, R, B, oc, device=x.device, dtype=torch.float32)
     call("spn_sum_tc_fwd", ptr(x), ptr(wimg), ptr(lw), B, d_in, d_out, c, oc, R, ptr(out), stream_ptr(x.device))
     return out
+
+
+def tc_sum_backward_x(x, out, g, wimg, lw):
+    """dL/dx of tc_sum_forward, [d_in, R, B, c] (tensor-core GEMM dE = G W^T + in-register reduction)."""
+    require_cuda(x, out, g, wimg)
+    x, out, g = _f32c(x), _f32c(out), _f32c(g)
+    d_in, R, B, c = x.shape
+    d_out, oc = out.shape[0], out.shape[3]
+    dx = torch.empty_like(x)
+    call("spn_sum_tc_bwd_x", ptr(x), ptr(out), ptr(g), ptr(wimg), B, d_in, d_out, c, oc, R, ptr(dx), stream_ptr(x.device))
+    return dx
+
+
+def tc_sum_backward_w(x, out, g, lw):
+    """dL/d(log-weights) of tc_sum_forward, [1, d_out, c*c, oc, R] (tensor-core GEMM over the batch)."""
+    require_cuda(x, out, g, lw)
+    x, out, g, lw = _f32c(x), _f32c(out), _f32c(g), _f32c(lw)
+    d_in, R, B, c = x.shape
+    d_out, oc = out.shape[0], out.shape[3]
+    work = torch.empty(d_out * R * c * c * oc, device=x.device, dtype=torch.float32)
+    dlw = torch.empty_like(lw)
+    call("spn_sum_tc_bwd_w", ptr(x), ptr(out), ptr(g), ptr(lw), B, d_in, d_out, c, oc, R, ptr(work), ptr(dlw),
+         stream_ptr(x.device))
+    return dlw
 
 
 def tc_aborts() -> int:

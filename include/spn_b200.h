@@ -146,6 +146,14 @@ int spn_sum_tc_supported(int c, int oc, int R);
 int spn_sum_tc_prepare(const float* lw, int d_out, int c, int oc, int R, void* wimg, void* stream);
 int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw, int B, int d_in, int d_out, int c, int oc, int R,
                    float* out, void* stream);
+/* Backward of spn_sum_tc_fwd (SURVEY A.5 as two tensor-core GEMMs; layouts as in the forward).
+ *   spn_sum_tc_bwd_x: dx [d_in, R, B, c] fully overwritten.
+ *   spn_sum_tc_bwd_w: dlw [1, d_out, c*c, oc, R] = gradient w.r.t. the log-weights lw, fully overwritten;
+ *                     dwt_workspace: caller-provided scratch of d_out * R * c*c * oc floats. */
+int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g, const void* wimg, int B, int d_in, int d_out,
+                     int c, int oc, int R, float* dx, void* stream);
+int spn_sum_tc_bwd_w(const float* x, const float* out, const float* g, const float* lw, int B, int d_in, int d_out,
+                     int c, int oc, int R, float* dwt_workspace, float* dlw, void* stream);
 /* Debug aid (synchronises): number of CTAs that gave up on an mbarrier wait since the library was loaded. */
 int spn_debug_tc_aborts(int* out_host);
 

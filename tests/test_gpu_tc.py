@@ -97,3 +97,35 @@ def test_model_forward_backward_on_tensor_core_path_vs_oracle():
     assert torch.equal(m(x.to(DEV), layer_index=0), m._leaf(x.to(DEV), perm32=m._perm32()[0]))
     from ratspn_b200 import ops
     assert ops.tc_aborts() == 0
+
+
+@pytest.mark.parametrize("c,d_in,R,B", [(16, 4, 3, 300), (16, 3, 2, 128), (32, 2, 2, 257), (40, 4, 3, 300), (40, 7, 2, 1024)])
+def test_tc_backward_matches_exact_kernels(c, d_in, R, B):
+    """dX and dW tensor-core kernels against the exact fp32 backward kernels on the same inputs."""
+    from ratspn_b200 import ops
+    g = torch.Generator().manual_seed(c * 77 + B)
+    x = (torch.randn(d_in, R, B, c, generator=g) * 4.0 - 30.0).to(DEV)
+    d_out = max(1, (1 << (d_in - 1).bit_length()) // 2)
+    lw = torch.log_softmax(torch.randn(1, d_out, c * c, c, R, generator=g), dim=2).to(DEV)
+    go = torch.randn(d_out, R, B, c, generator=g).to(DEV)
+    # exact: general kernels through autograd on the internal layout
+    xe = x.clone().requires_grad_(True)
+    lwe = lw.clone().requires_grad_(True)
+    oe = ops.sum_forward(xe, lwe, "xsum", "drbc")
+    (oe * go).sum().backward()
+    # tensor cores
+    xt = x.clone().requires_grad_(True)
+    lwt = lw.clone().requires_grad_(True)
+    ot = ops.sum_forward_tc(xt, lwt)
+    (ot * go).sum().backward()
+    torch.cuda.synchronize()
+    assert ops.tc_aborts() == 0
+    assert (ot - oe).abs().max().item() < 2e-2
+    sx = xe.grad.abs().max().item()
+    sw = lwe.grad.abs().max().item()
+    ex = (xt.grad - xe.grad).abs().max().item()
+    ew = (lwt.grad - lwe.grad).abs().max().item()
+    assert ex <= 2e-2 * sx, f"dx: max err {ex} vs scale {sx}"
+    assert ew <= 2e-2 * sw, f"dlw: max err {ew} vs scale {sw}"
+    assert (xt.grad - xe.grad).abs().mean().item() <= 2e-3 * sx
+    assert (lwt.grad - lwe.grad).abs().mean().item() <= 2e-3 * sw
