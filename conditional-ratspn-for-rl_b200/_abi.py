@@ -23,6 +23,10 @@ SIGNATURES = {
                             _P],
     "spn_leaf_bwd_x": [_P, _L, _L, _L, _L, _P, _L, _L, _L, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L,
                        _P],
+    "spn_leaf_shared_fwd": [_P, _L, _L, _L, _L, _P, _P, _P, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _L,
+                            _P],
+    "spn_leaf_shared_bwd_params": [_P, _L, _L, _L, _L, _P, _L, _L, _L, _L, _P, _P, _P, _L, _L, _L, _I, _I, _I, _I, _I,
+                                   _I, _I, _P, _P, _P],
     "spn_sum_fwd": [_I, _P, _L, _L, _L, _L, _I, _I, _P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L,
                     _L, _L, _P],
     "spn_sum_bwd_w": [_I, _P, _L, _L, _L, _L, _I, _I, _P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P,

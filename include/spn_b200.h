@@ -63,6 +63,19 @@ int spn_leaf_bwd_x(const float* g, int64_t sg_b, int64_t sg_d, int64_t sg_c, int
                    const float* sigma, int Wsets, int w, int B, int F, int I, int R, int card, int d0,
                    int tanh_corr, float* dx, int64_t dx_numel, void* stream);
 
+/* Shared-parameter (RatSpn, one weight set) variants of spn_leaf_fwd / spn_leaf_bwd_params with layout-aware thread
+ * mapping.  mu / sigma / dmu / dsigma are addressed as p[f*sp_f + i*sp_i + r*sp_r] (F*I*R elements); i_fast = 1 decodes
+ * the thread index with the leaf channel fastest (pass it with the internal [scope][rep][row][channel] activation layout
+ * and parameters stored [F][R][I]); i_fast = 0 is the reference order (r fastest, parameters [F][I][R]). */
+int spn_leaf_shared_fwd(const float* x, int64_t sx_b, int64_t sx_f, int64_t sx_i, int64_t sx_r, const int32_t* perm,
+                        const float* mu, const float* sigma, int64_t sp_f, int64_t sp_i, int64_t sp_r, int i_fast, int B,
+                        int F, int I, int R, int card, int d0, int tanh_corr, float* out, int64_t so_b, int64_t so_d,
+                        int64_t so_c, int64_t so_r, void* stream);
+int spn_leaf_shared_bwd_params(const float* g, int64_t sg_b, int64_t sg_d, int64_t sg_c, int64_t sg_r, const float* x,
+                               int64_t sx_b, int64_t sx_f, int64_t sx_i, int64_t sx_r, const int32_t* perm,
+                               const float* mu, const float* sigma, int64_t sp_f, int64_t sp_i, int64_t sp_r, int i_fast,
+                               int B, int F, int I, int R, int card, int d0, float* dmu, float* dsigma, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Sum layer, optionally fused with the CrossProduct layer below it (the c*c outer sum is never materialised).
  * Replaces layers.py:419-440 + :545-563 (CrossProduct.forward / split_shuffled_scopes), layers.py:110-128
