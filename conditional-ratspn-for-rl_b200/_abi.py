@@ -38,11 +38,14 @@ SIGNATURES = {
     "spn_sample_sum": [_P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _I, _P, _P, _L, _L, _L, _L,
                        _I, _I, _I, _I, _I, _P, _I, _U, _U, _P, _P],
     "spn_sum_tc_supported": [_I, _I, _I],
-    "spn_sum_tc_prepare": [_P, _I, _I, _I, _I, _P, _P],
-    "spn_sum_tc_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "spn_sum_tc_prepare": [_P, _I, _I, _I, _I, _P, _P, _P],
+    "spn_sum_tc_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "spn_sum_tc_bwd_x": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
-    "spn_sum_tc_bwd_w": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "spn_sum_tc_bwd_w": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "spn_debug_tc_aborts": [_P],
+    "spn_root_shared_supported": [_I, _I, _I],
+    "spn_root_shared_fwd": [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P],
+    "spn_root_shared_bwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "spn_sample_leaf": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _P, _P, _I, _U, _U, _P, _P, _L, _L, _L,
                         _I, _I, _P, _P, _P],
 }

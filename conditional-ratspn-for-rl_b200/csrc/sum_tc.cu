@@ -28,6 +28,7 @@ struct TcFwdArgs {
     const float* x;        // [d_in][R][B][C]
     const uint8_t* wimg;   // [d_out][R][K/8][NPAD/8][8][8] bf16
     const float* lw;       // fp32 log-weights [1][d_out][K][OC][R] (exact rescue path)
+    const float* logz;     // NULL, or [d_out][OC][R]: lw is unnormalised and the log-weights are lw - logz
     float* out;            // [d_out][R][B][OC]
     int B, d_in, d_out, R, OC;
     int ntiles, nsplit;    // batch tiles of 128 rows; splits of the tile range per (s, r)
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(320, 1) sum_tc_fwd_kernel(TcFwdArgs a) {
                             } else {
                                 const float* lwp = a.lw + ((int64_t)s * K * OC + (o4 + u)) * a.R + r;
                                 res[u] = tc_exact_lse<C>(has_l ? xl : nullptr, has_r ? xr : nullptr, lwp, (int64_t)OC * a.R);
+                                if (a.logz) res[u] -= a.logz[((int64_t)s * OC + (o4 + u)) * a.R + r];
                             }
                         }
                         *reinterpret_cast<float4*>(op + o4) = make_float4(res[0], res[1], res[2], res[3]);
@@ -263,14 +265,16 @@ __global__ void __launch_bounds__(320, 1) sum_tc_fwd_kernel(TcFwdArgs a) {
 // Weight operand preparation: fp32 log-weights [1][d][K][OC][R]  ->  bf16 exp() core-matrix image
 // [d][R][K/8][NPAD/8][8 (k)][8 (o)], zero padded for o >= OC.  One block per (scope, group of 8 k-values).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tc_wimage_kernel(const float* __restrict__ lw, uint8_t* __restrict__ wimg, int d,
-                                                       int K, int OC, int R, int NPAD) {
+__global__ void __launch_bounds__(256) tc_wimage_kernel(const float* __restrict__ lw, const float* __restrict__ logz,
+                                                       uint8_t* __restrict__ wimg, int d, int K, int OC, int R, int NPAD) {
     extern __shared__ float tile[];  // [8][OC][R]
     const int kg = blockIdx.x % (K / 8);
     const int s = blockIdx.x / (K / 8);
     const int n = 8 * OC * R;
     const float* src = lw + ((int64_t)s * K + (int64_t)kg * 8) * OC * R;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) tile[i] = __expf(src[i]);
+    const int ocr = OC * R;
+    const float* zp = logz ? logz + (int64_t)s * ocr : nullptr;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) tile[i] = __expf(src[i] - (zp ? zp[i % ocr] : 0.f));
     __syncthreads();
     const int NG = NPAD / 8;
     const int per_r = NG * 64;  // bf16 elements per (r, kg)
@@ -281,6 +285,51 @@ __global__ void __launch_bounds__(256) tc_wimage_kernel(const float* __restrict_
         const int o = og * 8 + oo;
         const float v = o < OC ? tile[(kk * OC + o) * R + r] : 0.f;
         dst[(((int64_t)s * R + r) * (K / 8) + kg) * per_r + e] = __float2bfloat16(v);
+    }
+}
+
+// Log-normaliser of the unnormalised weights: logz[s][o][r] = logsumexp_k param[s][k][o][r]  (F.log_softmax(dim=2) of
+// layers.py:85 is then lw = param - logz, applied by the consumers).  Block = 64 consecutive (o, r) columns x 4 k-phases;
+// every warp load is one 128-byte line; online max/sum so the parameters are read once.
+__global__ void __launch_bounds__(256) tc_logz_kernel(const float* __restrict__ param, float* __restrict__ logz, int K,
+                                                     int ocr, int tiles_per_s) {
+    __shared__ float sm_m[4][64], sm_s[4][64];
+    const int s = blockIdx.x / tiles_per_s;
+    const int col = (blockIdx.x % tiles_per_s) * 64 + (threadIdx.x & 63);
+    const int ph = threadIdx.x >> 6;
+    float m = -CUDART_INF_F, acc = 0.f;
+    if (col < ocr) {
+        const float* p = param + (int64_t)s * K * ocr + col;
+        int k = ph;
+        for (; k + 12 < K; k += 16) {  // four independent loads in flight per thread
+            const float v0 = p[(int64_t)k * ocr], v1 = p[(int64_t)(k + 4) * ocr], v2 = p[(int64_t)(k + 8) * ocr],
+                        v3 = p[(int64_t)(k + 12) * ocr];
+            const float mn = fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), m);
+            if (mn != -CUDART_INF_F) {
+                acc = acc * __expf(m - mn) + __expf(v0 - mn) + __expf(v1 - mn) + __expf(v2 - mn) + __expf(v3 - mn);
+                m = mn;
+            }
+        }
+        for (; k < K; k += 4) {
+            const float v = p[(int64_t)k * ocr];
+            const float mn = fmaxf(m, v);
+            if (mn != -CUDART_INF_F) {
+                acc = acc * __expf(m - mn) + __expf(v - mn);
+                m = mn;
+            }
+        }
+    }
+    sm_m[ph][threadIdx.x & 63] = m;
+    sm_s[ph][threadIdx.x & 63] = acc;
+    __syncthreads();
+    if (ph == 0 && col < ocr) {
+        float mm = fmaxf(fmaxf(sm_m[0][threadIdx.x], sm_m[1][threadIdx.x]), fmaxf(sm_m[2][threadIdx.x], sm_m[3][threadIdx.x]));
+        float tot = 0.f;
+        if (mm != -CUDART_INF_F) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tot += sm_s[q][threadIdx.x] * __expf(sm_m[q][threadIdx.x] - mm);
+        }
+        logz[(int64_t)s * ocr + col] = mm == -CUDART_INF_F ? -CUDART_INF_F : mm + logf(tot);
     }
 }
 
@@ -308,24 +357,30 @@ extern "C" int spn_sum_tc_supported(int c, int oc, int R) {
     return (c == 40 && oc == 40) || (c == 32 && oc == 32) || (c == 16 && oc == 16) ? 1 : 0;
 }
 
-extern "C" int spn_sum_tc_prepare(const float* lw, int d_out, int c, int oc, int R, void* wimg, void* stream) {
+extern "C" int spn_sum_tc_prepare(const float* lw, int d_out, int c, int oc, int R, float* logz, void* wimg, void* stream) {
     if (!lw || !wimg || !spn_sum_tc_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
     const int K = c * c, npad = (oc + 15) / 16 * 16;
+    if (logz) {
+        const int ocr = oc * R, tiles = (ocr + 63) / 64;
+        tc_logz_kernel<<<d_out * tiles, 256, 0, (cudaStream_t)stream>>>(lw, logz, K, ocr, tiles);
+        int rc = spn_launch_status();
+        if (rc != SPN_OK) return rc;
+    }
     const size_t smem = (size_t)8 * oc * R * sizeof(float);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(tc_wimage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return spn_cuda_status(e);
     }
-    tc_wimage_kernel<<<d_out * (K / 8), 256, smem, (cudaStream_t)stream>>>(lw, (uint8_t*)wimg, d_out, K, oc, R, npad);
+    tc_wimage_kernel<<<d_out * (K / 8), 256, smem, (cudaStream_t)stream>>>(lw, logz, (uint8_t*)wimg, d_out, K, oc, R, npad);
     return spn_launch_status();
 }
 
-extern "C" int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw, int B, int d_in, int d_out, int c,
-                              int oc, int R, float* out, void* stream) {
+extern "C" int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw, const float* logz, int B, int d_in,
+                              int d_out, int c, int oc, int R, float* out, void* stream) {
     if (!x || !wimg || !lw || !out || B <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
     if (!spn_sum_tc_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
     TcFwdArgs a{};
-    a.x = x; a.wimg = (const uint8_t*)wimg; a.lw = lw; a.out = out;
+    a.x = x; a.wimg = (const uint8_t*)wimg; a.lw = lw; a.logz = logz; a.out = out;
     a.B = B; a.d_in = d_in; a.d_out = d_out; a.R = R; a.OC = oc;
     a.ntiles = (B + 127) / 128;
     int nsplit = (4 * 148 + d_out * R - 1) / (d_out * R);

@@ -455,9 +455,55 @@ __global__ void __launch_bounds__(288, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
     if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
-// dlw[0][s][k][o][r] = exp(lw[0][s][k][o][r]) * dwt[s][r][k][o]: restores the parameter layout (R innermost) and applies
-// d exp / d log w.  One block per (s, tile of 32 k); tiles go through shared memory so both sides stay coalesced.
-__global__ void __launch_bounds__(256) tc_dw_finish_kernel(const float* __restrict__ lw, const float* __restrict__ dwt,
+// csum[s][o][r] = sum over rows b with out > -inf of g[s][r][b][o].  For normalised weights lw = param - logz the
+// softmax backward needs sum_k d(lw)[k,o] = sum_b g[b,o] * sum_k pi[b,k,o] = sum_b g[b,o]  (pi sums to one over k), so this
+// column sum of the upstream gradient replaces a second pass over the weight gradient.
+__global__ void __launch_bounds__(256) tc_gsum_kernel(const float* __restrict__ out, const float* __restrict__ g,
+                                                     float* __restrict__ csum, int B, int OC, int R, int rows_per_block) {
+    __shared__ float4 part[256];
+    const int sr = blockIdx.x;  // s * R + r
+    const int quads = OC / 4;                   // float4 per row (OC % 4 == 0 on the tensor-core path)
+    const int rpi = 256 / quads;                // rows per iteration
+    const int q = threadIdx.x % quads, slot = threadIdx.x / quads;
+    const int64_t b0 = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t b1 = min((int64_t)B, b0 + rows_per_block);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (slot < rpi) {
+        const float4* op = reinterpret_cast<const float4*>(out + (int64_t)sr * B * OC) + q;
+        const float4* gp = reinterpret_cast<const float4*>(g + (int64_t)sr * B * OC) + q;
+#pragma unroll 4
+        for (int64_t b = b0 + slot; b < b1; b += rpi) {
+            const float4 ov = __ldg(op + b * quads), gv = __ldg(gp + b * quads);
+            acc.x += ov.x == -CUDART_INF_F ? 0.f : gv.x;
+            acc.y += ov.y == -CUDART_INF_F ? 0.f : gv.y;
+            acc.z += ov.z == -CUDART_INF_F ? 0.f : gv.z;
+            acc.w += ov.w == -CUDART_INF_F ? 0.f : gv.w;
+        }
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < quads) {
+        float4 t = part[threadIdx.x];
+        for (int j = 1; j < rpi; ++j) {
+            const float4 u = part[j * quads + threadIdx.x];
+            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        const int s = sr / R, r = sr % R;
+        float* dst = csum + ((int64_t)s * OC + 4 * threadIdx.x) * R + r;
+        atomicAdd(dst, t.x);
+        atomicAdd(dst + R, t.y);
+        atomicAdd(dst + 2 * R, t.z);
+        atomicAdd(dst + 3 * R, t.w);
+    }
+}
+
+// Layout-restoring epilogue of dW: dwt[s][r][k][o] (linear-domain gradient) -> gradient w.r.t. the stored tensor, in the
+// parameter layout [1][s][k][o][r]:
+//   logz == NULL: lw holds log-weights;           dlw[k,o]    = exp(lw) * dwt
+//   logz != NULL: lw holds unnormalised params p; dparam[k,o] = softmax(p)[k,o] * (dwt[k,o] - csum[o])   (layers.py:85)
+// One block per (s, tile of KT k); tiles go through shared memory so both sides stay coalesced.
+__global__ void __launch_bounds__(256) tc_dw_finish_kernel(const float* __restrict__ lw, const float* __restrict__ logz,
+                                                          const float* __restrict__ csum, const float* __restrict__ dwt,
                                                           float* __restrict__ dlw, int d, int K, int OC, int R) {
     extern __shared__ float tile[];  // [R][KT*OC + 1]
     constexpr int KT = 4;
@@ -470,9 +516,16 @@ __global__ void __launch_bounds__(256) tc_dw_finish_kernel(const float* __restri
     }
     __syncthreads();
     const int64_t base = ((int64_t)s * K + (int64_t)kt * KT) * OC * R;
+    const int ocr = OC * R;
     for (int i = threadIdx.x; i < n * R; i += blockDim.x) {
         const int e = i / R, r = i % R;
-        dlw[base + i] = __expf(lw[base + i]) * tile[r * (n + 1) + e];
+        float w = lw[base + i], dv = tile[r * (n + 1) + e];
+        if (logz) {
+            const int zc = s * ocr + i % ocr;
+            w -= logz[zc];
+            dv -= csum[zc];
+        }
+        dlw[base + i] = __expf(w) * dv;
     }
 }
 
@@ -534,8 +587,9 @@ extern "C" int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g
     return SPN_ERR_UNSUPPORTED;
 }
 
-extern "C" int spn_sum_tc_bwd_w(const float* x, const float* out, const float* g, const float* lw, int B, int d_in,
-                                int d_out, int c, int oc, int R, float* dwt_workspace, float* dlw, void* stream) {
+extern "C" int spn_sum_tc_bwd_w(const float* x, const float* out, const float* g, const float* lw, const float* logz,
+                                int B, int d_in, int d_out, int c, int oc, int R, float* dwt_workspace, float* dlw,
+                                void* stream) {
     if (!x || !out || !g || !lw || !dwt_workspace || !dlw || B <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
     if (!spn_sum_tc_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
     TcBwdArgs a{};
@@ -551,8 +605,20 @@ extern "C" int spn_sum_tc_bwd_w(const float* x, const float* out, const float* g
     else return SPN_ERR_UNSUPPORTED;
     if (rc != SPN_OK) return rc;
     const int K = c * c;
+    float* csum = nullptr;
+    if (logz) {
+        // the column sums live behind the linear-domain gradient in the caller's workspace
+        csum = dwt_workspace + (size_t)d_out * R * K * oc;
+        cudaError_t e = cudaMemsetAsync(csum, 0, (size_t)d_out * oc * R * sizeof(float), st);
+        if (e != cudaSuccess) return spn_cuda_status(e);
+        const int rows_per_block = 512;
+        dim3 grid(d_out * R, (B + rows_per_block - 1) / rows_per_block);
+        tc_gsum_kernel<<<grid, 256, 0, st>>>(out, g, csum, B, oc, R, rows_per_block);
+        rc = spn_launch_status();
+        if (rc != SPN_OK) return rc;
+    }
     const size_t smem = (size_t)R * (4 * oc + 1) * sizeof(float);
-    tc_dw_finish_kernel<<<d_out * (K / 4), 256, smem, st>>>(lw, dwt_workspace, dlw, d_out, K, oc, R);
+    tc_dw_finish_kernel<<<d_out * (K / 4), 256, smem, st>>>(lw, logz, csum, dwt_workspace, dlw, d_out, K, oc, R);
     return spn_launch_status();
 }
 

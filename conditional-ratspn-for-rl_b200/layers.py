@@ -48,6 +48,17 @@ class Sum(AbstractLayer):
         self._input_cache = None        # stand-alone forward: the layer input itself (layers.py:102-103)
         self._input_cache_fused = None  # fused forward: the *CrossProduct input* this layer's input derives from
         self.consolidated_weights = None
+        self._tc_cache = {}             # bf16 operand image + log-normaliser of weight_param (tensor-core path)
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_tc_cache"] = {}  # derived device buffers are not part of a checkpoint
+        return state
+
+    def invalidate_weight_cache(self):
+        """Drop the cached operand image (needed only after writing to ``weight_param.data`` behind autograd's back;
+        in-place updates of the Parameter itself are detected through its version counter)."""
+        self._tc_cache.clear()
 
     def _enable_input_cache(self):
         self._is_input_cache_enabled = True

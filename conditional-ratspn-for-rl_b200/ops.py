@@ -174,21 +174,66 @@ class SumFn(torch.autograd.Function):
 
 
 class SumTcFn(torch.autograd.Function):
-    """Shared-weight fused CrossProduct + Sum on the tensor cores; activations in the internal [d, R, B, c] layout."""
+    """Shared-weight fused CrossProduct + Sum on the tensor cores; activations in the internal [d, R, B, c] layout.
+
+    ``raw = False``: ``w`` holds log-weights.  ``raw = True``: ``w`` is the unnormalised parameter tensor and the
+    ``F.log_softmax(dim=2)`` of layers.py:85 (forward and backward) is fused into the operand-image / dW-epilogue
+    kernels.  ``cache`` (a dict owned by the layer) keeps the bf16 operand image while the parameter is unchanged."""
 
     @staticmethod
-    def forward(ctx, x, lw):
-        wimg = tc_prepare(lw)
-        out = tc_sum_forward(x, wimg, lw)
-        ctx.save_for_backward(x, lw, out, wimg)
+    def forward(ctx, x, w, raw=False, cache=None):
+        wimg, logz = tc_prepare_cached(w, raw, cache)
+        out = tc_sum_forward(x, wimg, w, logz)
+        ctx.save_for_backward(x, w, out, wimg, logz if raw else torch.empty(0, device=x.device))
+        ctx.raw = raw
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x, lw, out, wimg = ctx.saved_tensors
-        dx = tc_sum_backward_x(x, out, g, wimg, lw) if ctx.needs_input_grad[0] else None
-        dlw = tc_sum_backward_w(x, out, g, lw) if ctx.needs_input_grad[1] else None
+        x, w, out, wimg, logz = ctx.saved_tensors
+        logz = logz if ctx.raw else None
+        g = _f32c(g)
+        dx = tc_sum_backward_x(x, out, g, wimg, w) if ctx.needs_input_grad[0] else None
+        dw = tc_sum_backward_w(x, out, g, w, logz) if ctx.needs_input_grad[1] else None
+        return dx, dw, None, None
+
+
+class RootSharedFn(torch.autograd.Function):
+    """Root Sum (shared weights) fused with the last CrossProduct on the internal layout:
+    x [d_in, R, B, c], lw [1, 1, R*c*c, C, 1] (normalised log-weights) -> out [B, C]."""
+
+    @staticmethod
+    def forward(ctx, x, lw):
+        require_cuda(x, lw)
+        x, lw = _f32c(x), _f32c(lw)
+        d_in, R, B, c = x.shape
+        C = lw.shape[3]
+        assert lw.shape[2] == R * c * c, f"root weights {tuple(lw.shape)} do not fit the input {tuple(x.shape)}"
+        part = torch.empty(R, B, C, device=x.device, dtype=torch.float32)
+        out = torch.empty(B, C, device=x.device, dtype=torch.float32)
+        call("spn_root_shared_fwd", ptr(x), d_in, ptr(lw), B, c, C, R, ptr(part), ptr(out), stream_ptr(x.device))
+        ctx.save_for_backward(x, lw, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, lw, out = ctx.saved_tensors
+        d_in, R, B, c = x.shape
+        C = lw.shape[3]
+        g = _f32c(g)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dlw = torch.empty_like(lw) if ctx.needs_input_grad[1] else None
+        call("spn_root_shared_bwd", ptr(x), d_in, ptr(lw), ptr(out), ptr(g), B, c, C, R, ptr(dx), ptr(dlw),
+             stream_ptr(x.device))
         return dx, dlw
+
+
+def root_shared_supported(c: int, C: int, R: int) -> bool:
+    return bool(_abi.lib().spn_root_shared_supported(int(c), int(C), int(R)))
+
+
+def root_forward_shared(x, lw):
+    return RootSharedFn.apply(x.contiguous(), lw.contiguous())
 
 
 class CrossProductFn(torch.autograd.Function):
@@ -221,8 +266,8 @@ def sum_forward(x, lw, mode="sum", layout="ref"):
     return SumFn.apply(x, lw, mode, layout)
 
 
-def sum_forward_tc(x, lw):
-    return SumTcFn.apply(x.contiguous(), lw.contiguous())
+def sum_forward_tc(x, w, raw=False, cache=None):
+    return SumTcFn.apply(x.contiguous(), w.contiguous(), raw, cache)
 
 
 def cross_product(x):
@@ -294,28 +339,44 @@ def tc_supported(c: int, oc: int, R: int) -> bool:
     return bool(_abi.lib().spn_sum_tc_supported(int(c), int(oc), int(R)))
 
 
-def tc_prepare(lw: torch.Tensor) -> torch.Tensor:
-    """fp32 log-weights [1, d, c*c, oc, R] -> bf16 exp() operand image for spn_sum_tc_fwd (uint8 buffer)."""
-    require_cuda(lw)
-    lw = _f32c(lw)
-    _, d, ic, oc, R = lw.shape
+def tc_prepare(w: torch.Tensor, raw: bool = False):
+    """fp32 weights [1, d, c*c, oc, R] -> bf16 exp() operand image for spn_sum_tc_fwd (uint8 buffer).
+    raw = False: ``w`` are log-weights, returns the image.  raw = True: ``w`` are unnormalised parameters, returns
+    (image of softmax(w), logz [d, oc, R])."""
+    require_cuda(w)
+    w = _f32c(w)
+    _, d, ic, oc, R = w.shape
     c = int(round(math.sqrt(ic)))
     assert c * c == ic
     npad = (oc + 15) // 16 * 16
-    wimg = torch.empty(d * R * ic * npad * 2, device=lw.device, dtype=torch.uint8)
-    call("spn_sum_tc_prepare", ptr(lw), d, c, oc, R, ptr(wimg), stream_ptr(lw.device))
-    return wimg
+    wimg = torch.empty(d * R * ic * npad * 2, device=w.device, dtype=torch.uint8)
+    logz = torch.empty(d, oc, R, device=w.device, dtype=torch.float32) if raw else None
+    call("spn_sum_tc_prepare", ptr(w), d, c, oc, R, ptr(logz), ptr(wimg), stream_ptr(w.device))
+    return (wimg, logz) if raw else wimg
 
 
-def tc_sum_forward(x: torch.Tensor, wimg: torch.Tensor, lw: torch.Tensor) -> torch.Tensor:
+def tc_prepare_cached(w: torch.Tensor, raw: bool, cache):
+    """(wimg, logz) for ``w``; re-used from ``cache`` while the tensor (storage, version) is unchanged."""
+    key = (w.data_ptr(), w._version, tuple(w.shape), bool(raw))
+    if cache is not None and cache.get("key") == key:
+        return cache["wimg"], cache["logz"]
+    res = tc_prepare(w, raw)
+    wimg, logz = res if raw else (res, None)
+    if cache is not None:
+        cache.update(key=key, wimg=wimg, logz=logz)
+    return wimg, logz
+
+
+def tc_sum_forward(x: torch.Tensor, wimg: torch.Tensor, lw: torch.Tensor, logz: torch.Tensor = None) -> torch.Tensor:
     """x [d_in, R, B, c] -> out [d_out, R, B, oc] (fused CrossProduct + Sum on tcgen05)."""
-    require_cuda(x, wimg, lw)
+    require_cuda(x, wimg, lw, logz)
     x, lw = _f32c(x), _f32c(lw)
     d_in, R, B, c = x.shape
     _, d_out, ic, oc, Rw = lw.shape
     assert ic == c * c and Rw == R and _pow2_ceil(d_in) == 2 * d_out
     out = torch.empty(d_out, R, B, oc, device=x.device, dtype=torch.float32)
-    call("spn_sum_tc_fwd", ptr(x), ptr(wimg), ptr(lw), B, d_in, d_out, c, oc, R, ptr(out), stream_ptr(x.device))
+    call("spn_sum_tc_fwd", ptr(x), ptr(wimg), ptr(lw), ptr(logz), B, d_in, d_out, c, oc, R, ptr(out),
+         stream_ptr(x.device))
     return out
 
 
@@ -330,15 +391,16 @@ def tc_sum_backward_x(x, out, g, wimg, lw):
     return dx
 
 
-def tc_sum_backward_w(x, out, g, lw):
-    """dL/d(log-weights) of tc_sum_forward, [1, d_out, c*c, oc, R] (tensor-core GEMM over the batch)."""
-    require_cuda(x, out, g, lw)
+def tc_sum_backward_w(x, out, g, lw, logz=None):
+    """Gradient of tc_sum_forward w.r.t. the weight tensor it was given, [1, d_out, c*c, oc, R] (tensor-core GEMM over
+    the batch); with ``logz`` the tensor is the unnormalised parameter and the softmax backward is fused."""
+    require_cuda(x, out, g, lw, logz)
     x, out, g, lw = _f32c(x), _f32c(out), _f32c(g), _f32c(lw)
     d_in, R, B, c = x.shape
     d_out, oc = out.shape[0], out.shape[3]
-    work = torch.empty(d_out * R * c * c * oc, device=x.device, dtype=torch.float32)
+    work = torch.empty(d_out * R * (c * c + 1) * oc, device=x.device, dtype=torch.float32)
     dlw = torch.empty_like(lw)
-    call("spn_sum_tc_bwd_w", ptr(x), ptr(out), ptr(g), ptr(lw), B, d_in, d_out, c, oc, R, ptr(work), ptr(dlw),
+    call("spn_sum_tc_bwd_w", ptr(x), ptr(out), ptr(g), ptr(lw), ptr(logz), B, d_in, d_out, c, oc, R, ptr(work), ptr(dlw),
          stream_ptr(x.device))
     return dlw
 

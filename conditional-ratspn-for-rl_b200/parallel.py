@@ -70,3 +70,6 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0):
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src)
+    for m in module.modules():  # .data writes bypass the version counter the operand-image cache is keyed on
+        if hasattr(m, "invalidate_weight_cache"):
+            m.invalidate_weight_cache()

@@ -264,9 +264,16 @@ class RatSpn(nn.Module):
         batch_shape = x.shape[:-3]  # (*batch_dims, w)
         h = self._leaf(x, detach_params=detach_params, perm32=perm32, layout="drbc")
         for li in range(2, min(layer_index, self.max_layer_index - 1) + 1, 2):
-            h = ops.sum_forward_tc(h, self._inner_layers[li - 1]._weights_for(detach_params))
+            layer = self._inner_layers[li - 1]
+            # the unnormalised parameter goes in; log_softmax over the in-channels is fused into the kernels
+            w = layer.weight_param.detach() if detach_params else layer.weight_param
+            h = ops.sum_forward_tc(h, w, True, layer._tc_cache)
         if layer_index == self.max_layer_index:
-            out = ops.sum_forward(h, self.root._weights_for(detach_params), "xroot", "drbc")  # [B, 1, 1, C, 1]
+            lw_root = self.root._weights_for(detach_params)
+            if ops.root_shared_supported(h.shape[3], self.config.C, self.config.R):
+                out = ops.root_forward_shared(h, lw_root)  # [B, C]
+            else:
+                out = ops.sum_forward(h, lw_root, "xroot", "drbc")  # [B, 1, 1, C, 1]
             return out.reshape(*batch_shape, 1, self.config.C, 1)
         h = h.permute(2, 0, 3, 1).reshape(*batch_shape, h.shape[0], h.shape[3], h.shape[1])  # -> [*batch, w, d, c, R]
         if layer_index % 2 == 1:

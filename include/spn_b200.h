@@ -153,20 +153,39 @@ int spn_sample_leaf(const float* mu, const float* sigma, int Wsets, int w, int Q
  *   x [d_in, R, B, c] contiguous, out [d_out, R, B, oc] contiguous.
  * spn_sum_tc_prepare turns fp32 log-weights lw [1, d_out, c*c, oc, R] into the bf16 operand image
  * (d_out * R * c*c * ceil16(oc) * 2 bytes, caller-allocated) that spn_sum_tc_fwd streams through shared memory.
+ * Weight normalisation (layers.py:85, F.log_softmax over the in-channels on every read) is fused: when `logz`
+ * ([d_out, oc, R], caller-allocated) is non-NULL, `lw` is the UNNORMALISED parameter tensor, spn_sum_tc_prepare writes
+ * logz = logsumexp_k lw and every consumer uses lw - logz; with logz == NULL, lw must already be normalised.
  * Outputs whose linear-domain sum underflows are recomputed exactly in fp32 from lw (logsumexp semantics are kept).
  * ------------------------------------------------------------------------------------------------------------- */
 int spn_sum_tc_supported(int c, int oc, int R);
-int spn_sum_tc_prepare(const float* lw, int d_out, int c, int oc, int R, void* wimg, void* stream);
-int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw, int B, int d_in, int d_out, int c, int oc, int R,
-                   float* out, void* stream);
+int spn_sum_tc_prepare(const float* lw, int d_out, int c, int oc, int R, float* logz, void* wimg, void* stream);
+int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw, const float* logz, int B, int d_in, int d_out,
+                   int c, int oc, int R, float* out, void* stream);
 /* Backward of spn_sum_tc_fwd (SURVEY A.5 as two tensor-core GEMMs; layouts as in the forward).
  *   spn_sum_tc_bwd_x: dx [d_in, R, B, c] fully overwritten.
- *   spn_sum_tc_bwd_w: dlw [1, d_out, c*c, oc, R] = gradient w.r.t. the log-weights lw, fully overwritten;
- *                     dwt_workspace: caller-provided scratch of d_out * R * c*c * oc floats. */
+ *   spn_sum_tc_bwd_w: dlw [1, d_out, c*c, oc, R] = gradient w.r.t. the tensor passed as lw, fully overwritten: the
+ *                     log-weights (logz == NULL) or the unnormalised parameters (logz from spn_sum_tc_prepare; the
+ *                     softmax backward is fused); dwt_workspace: caller-provided scratch of
+ *                     d_out * R * (c*c + 1) * oc floats. */
 int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g, const void* wimg, int B, int d_in, int d_out,
                      int c, int oc, int R, float* dx, void* stream);
-int spn_sum_tc_bwd_w(const float* x, const float* out, const float* g, const float* lw, int B, int d_in, int d_out,
-                     int c, int oc, int R, float* dwt_workspace, float* dlw, void* stream);
+int spn_sum_tc_bwd_w(const float* x, const float* out, const float* g, const float* lw, const float* logz, int B,
+                     int d_in, int d_out, int c, int oc, int R, float* dwt_workspace, float* dlw, void* stream);
+/* ---------------------------------------------------------------------------------------------------------------
+ * Root sum layer for SHARED weights on the internal layout: merges the repetitions into the channel axis and sums over
+ * all of them, fused with the last CrossProduct.  Replaces rat_spn.py:230-236 + layers.py:110-128 for a RatSpn.
+ *   x    [d_in (1 or 2), R, B, c] contiguous (output of the last spn_sum_tc_fwd)
+ *   lw   root log-weights [1, 1, R*c*c, C, 1] contiguous (channel = r*c*c + l*c + r'), normalised over dim 2
+ *   part caller workspace of R * B * C floats; out [B, C]
+ * spn_root_shared_bwd: g = dL/dout [B, C]; dx [d_in, R, B, c] and / or dlw [R*c*c*C] (either may be NULL), overwritten.
+ * ------------------------------------------------------------------------------------------------------------- */
+int spn_root_shared_supported(int c, int C, int R);
+int spn_root_shared_fwd(const float* x, int d_in, const float* lw, int B, int c, int C, int R, float* part, float* out,
+                        void* stream);
+int spn_root_shared_bwd(const float* x, int d_in, const float* lw, const float* out, const float* g, int B, int c, int C,
+                        int R, float* dx, float* dlw, void* stream);
+
 /* Debug aid (synchronises): number of CTAs that gave up on an mbarrier wait since the library was loaded. */
 int spn_debug_tc_aborts(int* out_host);
 

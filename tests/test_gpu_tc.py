@@ -129,3 +129,40 @@ def test_tc_backward_matches_exact_kernels(c, d_in, R, B):
     assert ew <= 2e-2 * sw, f"dlw: max err {ew} vs scale {sw}"
     assert (xt.grad - xe.grad).abs().mean().item() <= 2e-3 * sx
     assert (lwt.grad - lwe.grad).abs().mean().item() <= 2e-3 * sw
+
+
+@pytest.mark.parametrize("c,d_in,R,B", [(16, 4, 3, 300), (40, 4, 3, 300), (40, 3, 40, 640)])
+def test_tc_fused_weight_normalisation_forward_and_backward(c, d_in, R, B):
+    """raw = True: the kernels take the unnormalised parameter and fuse F.log_softmax(dim=2) (layers.py:85) and its
+    backward; compared with autograd through torch's log_softmax + the exact fp32 kernels."""
+    from ratspn_b200 import ops
+    g = torch.Generator().manual_seed(c * 13 + B)
+    x = (torch.randn(d_in, R, B, c, generator=g) * 4.0 - 30.0).to(DEV)
+    d_out = max(1, (1 << (d_in - 1).bit_length()) // 2)
+    raw = (torch.randn(1, d_out, c * c, c, R, generator=g) * 1.5 + 0.7).to(DEV)
+    go = torch.randn(d_out, R, B, c, generator=g).to(DEV)
+    pe = raw.clone().requires_grad_(True)
+    oe = ops.sum_forward(x, torch.log_softmax(pe, dim=2), "xsum", "drbc")
+    (oe * go).sum().backward()
+    pt = raw.clone().requires_grad_(True)
+    cache = {}
+    ot = ops.sum_forward_tc(x, pt, True, cache)
+    (ot * go).sum().backward()
+    torch.cuda.synchronize()
+    assert ops.tc_aborts() == 0
+    logz = torch.logsumexp(raw, dim=2).squeeze(0)  # [d, oc, R]
+    assert (cache["logz"] - logz).abs().max().item() < 1e-5
+    assert (ot - oe).abs().max().item() < 2e-2
+    sw = pe.grad.abs().max().item()
+    assert (pt.grad - pe.grad).abs().max().item() <= 2e-2 * sw
+    assert (pt.grad - pe.grad).abs().mean().item() <= 2e-3 * sw
+    # the image is re-used while the parameter is unchanged and rebuilt after an in-place update
+    img = cache["wimg"]
+    ops.sum_forward_tc(x, pt, True, cache)
+    assert cache["wimg"] is img
+    with torch.no_grad():
+        pt.add_(0.5 * torch.randn(pt.shape, device=DEV))
+    o2 = ops.sum_forward_tc(x, pt, True, cache)
+    assert cache["wimg"] is not img
+    ref2 = ops.sum_forward(x, torch.log_softmax(pt.detach(), dim=2), "xsum", "drbc")
+    assert (o2 - ref2).abs().max().item() < 2e-2
