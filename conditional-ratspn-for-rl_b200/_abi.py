@@ -27,6 +27,10 @@ SIGNATURES = {
                             _P],
     "spn_leaf_shared_bwd_params": [_P, _L, _L, _L, _L, _P, _L, _L, _L, _L, _P, _P, _P, _L, _L, _L, _I, _I, _I, _I, _I,
                                    _I, _I, _P, _P, _P],
+    "spn_leaf_transpose": [_P, _L, _L, _I, _I, _P, _P],
+    "spn_leaf_tiled_supported": [_I, _I, _I],
+    "spn_leaf_tiled_fwd": [_P, _P, _P, _P, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _L, _P],
+    "spn_leaf_tiled_bwd_params": [_P, _P, _L, _L, _L, _L, _P, _P, _P, _L, _L, _L, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "spn_sum_fwd": [_I, _P, _L, _L, _L, _L, _I, _I, _P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L,
                     _L, _L, _P],
     "spn_sum_bwd_w": [_I, _P, _L, _L, _L, _L, _I, _I, _P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P,

@@ -1,0 +1,411 @@
+// Register-tiled leaf kernels for SHARED parameters (RatSpn) and plain inputs x [B, F] (no channel / repetition dims).
+//
+// The leaf layer evaluates N*F*I*R Gaussian log-densities (cfg 2: 5.1e9) from only N*F inputs and 2*F*I*R parameters,
+// so it is bound by the fp32 pipes, not by HBM -- provided operands are re-used from shared memory / registers:
+//   * x is first transposed to feature-major xT [F][B] (spn_leaf_transpose), so that the per-repetition feature
+//     permutation x[b, perm[f, r]] becomes a gather of whole contiguous 512-byte row segments instead of one 32-byte
+//     sector per value;
+//   * forward: block = (128 rows, scope s, repetition r); the features of the scope are staged in chunks of 32 as
+//     xs[feature][row] together with mu and 1/(2 sigma^2) per (feature, channel); each thread owns a 4-row x 4-channel
+//     register tile: 3 shared-memory vector loads feed 16 evaluations (sub, mul, fma) per feature;
+//   * backward (parameters): block = (scope s, repetition r, feature chunk); each thread owns a 4-feature x 4-channel
+//     tile of (sum g*d, sum g*d*d) accumulators and walks the rows in tiles of 64 staged in shared memory; row sub-groups
+//     of the block are combined through shared memory, so every gradient element is written once (no atomics unless the
+//     grid has to be split over rows to fill the machine).
+// NaN inputs (marginalised features, distributions.py:58-61, :243) take a block-uniform slow path with a validity mask.
+// Reference semantics: rat_spn.py:155-170, distributions.py:199-246, :366-382, layers.py:276-312.
+#include "common.cuh"
+
+namespace {
+
+constexpr int FC = 32;      // features per staged chunk
+constexpr int FROWS = 128;  // rows per forward block
+constexpr int BROWS = 64;   // rows per staged backward tile
+
+struct LeafTiledArgs {
+    const float* xT;  // [F][B]
+    const int32_t* perm;
+    const float* mu; const float* sigma; int64_t sp_f, sp_i, sp_r;
+    int B, F, I, R, card, d0, tanh_corr;
+    float* out; const float* g; int64_t so_b, so_d, so_c, so_r;
+    float* dmu; float* dsigma;
+    int nsplit, nchunk, fchunk;
+};
+
+__global__ void __launch_bounds__(256) leaf_transpose_kernel(const float* __restrict__ x, int64_t sx_b, int64_t sx_f, int B,
+                                                            int F, float* __restrict__ xT) {
+    __shared__ float tile[32][33];
+    const int b0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const int b = b0 + j, f = f0 + tx;
+        tile[j][tx] = (b < B && f < F) ? x[(int64_t)b * sx_b + (int64_t)f * sx_f] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int f = f0 + j, b = b0 + tx;
+        if (f < F && b < B) xT[(int64_t)f * B + b] = tile[tx][j];
+    }
+}
+
+// grid (ceil(B / FROWS), R, d0); block 32 * ceil(I / 4) threads: lane = row group (4 rows), warp = channel group (4 ch).
+__global__ void __launch_bounds__(1024) leaf_tiled_fwd_kernel(LeafTiledArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int I4 = (int)(blockDim.x >> 5) * 4;
+    float* xs = sm;                       // [FC][FROWS]            (re-used as the output staging tile [FROWS][I4])
+    float* pm = sm + max(FC * FROWS, FROWS * I4);  // [FC][I4] mu
+    float* pa = pm + FC * I4;             // [FC][I4] 1 / (2 sigma^2)
+    float* pk = pa + FC * I4;             // [FC][I4] log sigma + log sqrt(2 pi)
+    float* ks = pk + FC * I4;             // [I4]     sum of pk over the chunk
+    __shared__ int src_f[FC];
+    const int s = blockIdx.z, r = blockIdx.y;
+    const int64_t b0 = (int64_t)blockIdx.x * FROWS;
+    const int rg = threadIdx.x & 31, cg = threadIdx.x >> 5;
+    const int f_begin = s * a.card, f_end = min(a.F, f_begin + a.card);
+
+    float acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+
+    for (int fc0 = f_begin; fc0 < f_end; fc0 += FC) {
+        const int cnt = min(FC, f_end - fc0);
+        __syncthreads();  // previous chunk fully consumed
+        if (threadIdx.x < cnt) {
+            const int f = fc0 + threadIdx.x;
+            src_f[threadIdx.x] = a.perm ? a.perm[(int64_t)f * a.R + r] : f;
+        }
+        for (int e = threadIdx.x; e < cnt * I4; e += blockDim.x) {
+            const int j = e / I4, i = e % I4;
+            float m = 0.f, av = 0.f, kv = 0.f;
+            if (i < a.I) {
+                const int64_t p = (int64_t)(fc0 + j) * a.sp_f + (int64_t)i * a.sp_i + (int64_t)r * a.sp_r;
+                m = a.mu[p];
+                const float sg = a.sigma[p];
+                av = 1.f / (2.f * sg * sg);
+                kv = logf(sg) + SPN_LOG_SQRT_2PI;
+            }
+            pm[e] = m; pa[e] = av; pk[e] = kv;
+        }
+        __syncthreads();
+        int has_nan = 0;
+        for (int e = threadIdx.x; e < cnt * FROWS; e += blockDim.x) {
+            const int j = e / FROWS, row = e % FROWS;
+            const int64_t b = b0 + row;
+            float v = b < a.B ? __ldg(a.xT + (int64_t)src_f[j] * a.B + b) : 0.f;
+            if (isnan(v)) has_nan = 1;
+            xs[e] = v;
+        }
+        if (threadIdx.x < I4) {
+            float t = 0.f;
+            for (int j = 0; j < cnt; ++j) t += pk[j * I4 + threadIdx.x];
+            ks[threadIdx.x] = t;
+        }
+        has_nan = __syncthreads_or(has_nan);
+        if (!has_nan && !a.tanh_corr) {
+#pragma unroll 2
+            for (int j = 0; j < cnt; ++j) {
+                const float4 x4 = *reinterpret_cast<const float4*>(xs + j * FROWS + 4 * rg);
+                const float4 m4 = *reinterpret_cast<const float4*>(pm + j * I4 + 4 * cg);
+                const float4 a4 = *reinterpret_cast<const float4*>(pa + j * I4 + 4 * cg);
+                const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+                const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
+                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float d = xv[u] - mv[v];
+                        acc[u][v] = fmaf(-(d * av[v]), d, acc[u][v]);
+                    }
+            }
+            const float4 k4 = *reinterpret_cast<const float4*>(ks + 4 * cg);
+            const float kv[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] -= kv[v];
+        } else {
+            // slow path: NaN -> contributes nothing; tanh change-of-variables correction per (row, feature)
+            for (int j = 0; j < cnt; ++j) {
+                const float4 x4 = *reinterpret_cast<const float4*>(xs + j * FROWS + 4 * rg);
+                const float4 m4 = *reinterpret_cast<const float4*>(pm + j * I4 + 4 * cg);
+                const float4 a4 = *reinterpret_cast<const float4*>(pa + j * I4 + 4 * cg);
+                const float4 k4 = *reinterpret_cast<const float4*>(pk + j * I4 + 4 * cg);
+                const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+                const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
+                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+                const float kv[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (isnan(xv[u])) continue;
+                    const float corr = a.tanh_corr ? spn_tanh_correction(xv[u]) : 0.f;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float d = xv[u] - mv[v];
+                        acc[u][v] += -(d * d) * av[v] - kv[v] - corr;
+                    }
+                }
+            }
+        }
+    }
+    // stage the [FROWS][I4] tile and write it with the channel index fastest
+    __syncthreads();
+    float* os = sm;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        *reinterpret_cast<float4*>(os + (4 * rg + u) * I4 + 4 * cg) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+    __syncthreads();
+    const int nrow = (int)min((int64_t)FROWS, a.B - b0);
+    float* obase = a.out + (int64_t)s * a.so_d + (int64_t)r * a.so_r;
+    for (int e = threadIdx.x; e < nrow * a.I; e += blockDim.x) {
+        const int row = e / a.I, i = e % a.I;
+        obase[(b0 + row) * a.so_b + (int64_t)i * a.so_c] = os[row * I4 + i];
+    }
+}
+
+// grid (R * d0, nchunk, nsplit); block = ngroups * nfg * nig threads, nfg = ceil(fchunk / 4), nig = ceil(I / 4).
+__global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int nig = (a.I + 3) / 4, I4 = nig * 4;
+    const int nfg = (a.fchunk + 3) / 4, F4 = nfg * 4;
+    const int ntile = nfg * nig;
+    const int ngroups = blockDim.x / ntile;
+    float* gs = sm;                    // [BROWS][I4]
+    float* xs = gs + BROWS * I4;       // [F4][BROWS]
+    __shared__ int src_f[FC];
+    const int s = blockIdx.x / a.R, r = blockIdx.x % a.R;
+    const int f_begin = s * a.card + blockIdx.y * a.fchunk;
+    const int f_end = min(min(a.F, (s + 1) * a.card), f_begin + a.fchunk);
+    const int cnt = f_end - f_begin;
+    if (cnt <= 0) return;
+    const int tile = threadIdx.x % ntile, grp = threadIdx.x / ntile;
+    const bool worker = grp < ngroups;
+    const int ig = tile % nig, fg = tile / nig;
+
+    if (threadIdx.x < F4) {
+        const int f = f_begin + min((int)threadIdx.x, cnt - 1);
+        src_f[threadIdx.x] = a.perm ? a.perm[(int64_t)f * a.R + r] : f;
+    }
+    float mv[4][4];  // mu of (feature u, channel v)
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int f = f_begin + min(4 * fg + u, cnt - 1), i = min(4 * ig + v, a.I - 1);
+            mv[u][v] = a.mu[(int64_t)f * a.sp_f + (int64_t)i * a.sp_i + (int64_t)r * a.sp_r];
+        }
+    float a1[4][4], a2[4][4], cr[4][4], a0[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        a0[u] = 0.f;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { a1[u][v] = 0.f; a2[u][v] = 0.f; cr[u][v] = 0.f; }
+    }
+    const int64_t rows_per = (((int64_t)a.B + a.nsplit - 1) / a.nsplit + BROWS - 1) / BROWS * BROWS;
+    const int64_t row_begin = (int64_t)blockIdx.z * rows_per;
+    const int64_t row_end = min((int64_t)a.B, row_begin + rows_per);
+    const float* gbase = a.g + (int64_t)s * a.so_d + (int64_t)r * a.so_r;
+    __syncthreads();
+
+    for (int64_t b0 = row_begin; b0 < row_end; b0 += BROWS) {
+        const int nrow = (int)min((int64_t)BROWS, row_end - b0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < BROWS * I4; e += blockDim.x) {
+            const int row = e / I4, i = e % I4;
+            gs[e] = (row < nrow && i < a.I) ? __ldg(gbase + (b0 + row) * a.so_b + (int64_t)i * a.so_c) : 0.f;
+        }
+        int has_nan = 0;
+        for (int e = threadIdx.x; e < F4 * BROWS; e += blockDim.x) {
+            const int j = e / BROWS, row = e % BROWS;
+            float v = 0.f;
+            if (row < nrow && j < cnt) v = __ldg(a.xT + (int64_t)src_f[j] * a.B + b0 + row);
+            if (isnan(v)) has_nan = 1;
+            xs[e] = v;
+        }
+        has_nan = __syncthreads_or(has_nan);
+        if (!worker) continue;
+        if (!has_nan) {
+#pragma unroll 2
+            for (int row = grp; row < nrow; row += ngroups) {
+                const float4 g4 = *reinterpret_cast<const float4*>(gs + row * I4 + 4 * ig);
+                const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+                float xv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) xv[u] = xs[(4 * fg + u) * BROWS + row];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) a0[v] += gv[v];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float d = xv[u] - mv[u][v];
+                        const float t = gv[v] * d;
+                        a1[u][v] += t;
+                        a2[u][v] = fmaf(t, d, a2[u][v]);
+                    }
+            }
+        } else {
+            for (int row = grp; row < nrow; row += ngroups) {
+                const float4 g4 = *reinterpret_cast<const float4*>(gs + row * I4 + 4 * ig);
+                const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                for (int v = 0; v < 4; ++v) a0[v] += gv[v];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float x = xs[(4 * fg + u) * BROWS + row];
+                    if (isnan(x)) {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) cr[u][v] += gv[v];  // this row does not count for feature u
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const float d = x - mv[u][v];
+                            const float t = gv[v] * d;
+                            a1[u][v] += t;
+                            a2[u][v] = fmaf(t, d, a2[u][v]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // combine the row groups through shared memory: red[grp][tile][36]
+    __syncthreads();
+    float* red = sm;
+    if (worker) {
+        float* my = red + ((int64_t)grp * ntile + tile) * 36;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                my[u * 4 + v] = a1[u][v];
+                my[16 + u * 4 + v] = a2[u][v];
+            }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) my[32 + v] = a0[v];
+    }
+    __syncthreads();
+    // element e -> (tile, u, v): sum over groups, finish dmu / dsigma
+    for (int e = threadIdx.x; e < ntile * 16; e += blockDim.x) {
+        const int t = e / 16, uv = e % 16, u = uv / 4, v = uv % 4;
+        const int f = f_begin + 4 * (t / nig) + u, i = 4 * (t % nig) + v;
+        float s1 = 0.f, s2 = 0.f, s0 = 0.f;
+        for (int gq = 0; gq < ngroups; ++gq) {
+            const float* src = red + ((int64_t)gq * ntile + t) * 36;
+            s1 += src[uv]; s2 += src[16 + uv]; s0 += src[32 + v];
+        }
+        red[(int64_t)ngroups * ntile * 36 + e * 3] = s1;  // keep for the second pass (cr)
+        red[(int64_t)ngroups * ntile * 36 + e * 3 + 1] = s2;
+        red[(int64_t)ngroups * ntile * 36 + e * 3 + 2] = s0;
+        (void)f; (void)i;
+    }
+    __syncthreads();
+    if (worker) {  // second pass: the NaN corrections re-use the per-group slots
+        float* my = red + ((int64_t)grp * ntile + tile) * 36;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) my[u * 4 + v] = cr[u][v];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < ntile * 16; e += blockDim.x) {
+        const int t = e / 16, uv = e % 16, u = uv / 4, v = uv % 4;
+        const int f = f_begin + 4 * (t / nig) + u, i = 4 * (t % nig) + v;
+        if (f >= f_end || i >= a.I) continue;
+        float sc = 0.f;
+        for (int gq = 0; gq < ngroups; ++gq) sc += red[((int64_t)gq * ntile + t) * 36 + uv];
+        const float* fin = red + (int64_t)ngroups * ntile * 36 + e * 3;
+        const int64_t p = (int64_t)f * a.sp_f + (int64_t)i * a.sp_i + (int64_t)r * a.sp_r;
+        const float inv_sg = 1.f / a.sigma[p];
+        const float inv_var = inv_sg * inv_sg;
+        const float dmu = fin[0] * inv_var;
+        const float dsg = fin[1] * inv_var * inv_sg - (fin[2] - sc) * inv_sg;
+        if (a.nsplit == 1) {
+            a.dmu[p] = dmu;
+            a.dsigma[p] = dsg;
+        } else {
+            atomicAdd(a.dmu + p, dmu);
+            atomicAdd(a.dsigma + p, dsg);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int spn_leaf_transpose(const float* x, int64_t sx_b, int64_t sx_f, int B, int F, float* xT, void* stream) {
+    if (!x || !xT || B < 0 || F <= 0) return SPN_ERR_ARG;
+    if (B == 0) return SPN_OK;
+    leaf_transpose_kernel<<<dim3((B + 31) / 32, (F + 31) / 32), 256, 0, (cudaStream_t)stream>>>(x, sx_b, sx_f, B, F, xT);
+    return spn_launch_status();
+}
+
+extern "C" int spn_leaf_tiled_supported(int I, int R, int d0) { return (I >= 1 && I <= 128 && R <= 65535 && d0 <= 65535) ? 1 : 0; }
+
+extern "C" int spn_leaf_tiled_fwd(const float* xT, const int32_t* perm, const float* mu, const float* sigma, int64_t sp_f,
+                                  int64_t sp_i, int64_t sp_r, int B, int F, int I, int R, int card, int d0, int tanh_corr,
+                                  float* out, int64_t so_b, int64_t so_d, int64_t so_c, int64_t so_r, void* stream) {
+    if (!xT || !mu || !sigma || !out || B < 0 || F <= 0 || I <= 0 || R <= 0 || card <= 0 || d0 <= 0) return SPN_ERR_ARG;
+    if (!spn_leaf_tiled_supported(I, R, d0)) return SPN_ERR_UNSUPPORTED;
+    if (B == 0) return SPN_OK;
+    LeafTiledArgs a{};
+    a.xT = xT; a.perm = perm; a.mu = mu; a.sigma = sigma; a.sp_f = sp_f; a.sp_i = sp_i; a.sp_r = sp_r;
+    a.B = B; a.F = F; a.I = I; a.R = R; a.card = card; a.d0 = d0; a.tanh_corr = tanh_corr;
+    a.out = out; a.so_b = so_b; a.so_d = so_d; a.so_c = so_c; a.so_r = so_r;
+    const int ncg = (I + 3) / 4, I4 = ncg * 4;
+    const int big = FC * FROWS > FROWS * I4 ? FC * FROWS : FROWS * I4;
+    const int smem = (big + 3 * FC * I4 + I4) * (int)sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(leaf_tiled_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return spn_cuda_status(e);
+    leaf_tiled_fwd_kernel<<<dim3((B + FROWS - 1) / FROWS, R, d0), 32 * ncg, smem, (cudaStream_t)stream>>>(a);
+    return spn_launch_status();
+}
+
+extern "C" int spn_leaf_tiled_bwd_params(const float* xT, const float* g, int64_t sg_b, int64_t sg_d, int64_t sg_c,
+                                         int64_t sg_r, const int32_t* perm, const float* mu, const float* sigma,
+                                         int64_t sp_f, int64_t sp_i, int64_t sp_r, int B, int F, int I, int R, int card,
+                                         int d0, float* dmu, float* dsigma, void* stream) {
+    if (!xT || !g || !mu || !sigma || !dmu || !dsigma || B < 0 || F <= 0 || I <= 0 || R <= 0 || card <= 0 || d0 <= 0)
+        return SPN_ERR_ARG;
+    if (!spn_leaf_tiled_supported(I, R, d0)) return SPN_ERR_UNSUPPORTED;
+    LeafTiledArgs a{};
+    a.xT = xT; a.perm = perm; a.mu = mu; a.sigma = sigma; a.sp_f = sp_f; a.sp_i = sp_i; a.sp_r = sp_r;
+    a.B = B; a.F = F; a.I = I; a.R = R; a.card = card; a.d0 = d0;
+    a.g = g; a.so_b = sg_b; a.so_d = sg_d; a.so_c = sg_c; a.so_r = sg_r; a.dmu = dmu; a.dsigma = dsigma;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nig = (I + 3) / 4, I4 = nig * 4;
+    // feature chunks per scope: at most FC features and at most 256 thread tiles per block
+    int max_f = FC;
+    while (max_f > 4 && ((max_f + 3) / 4) * nig > 256) max_f -= 4;
+    a.nchunk = (card + max_f - 1) / max_f;
+    a.fchunk = (card + a.nchunk - 1) / a.nchunk;
+    const int nfg = (a.fchunk + 3) / 4, F4 = nfg * 4, ntile = nfg * nig;
+    int ngroups = 256 / ntile;
+    if (ngroups < 1) ngroups = 1;
+    if (ngroups > 8) ngroups = 8;
+    const int64_t blocks = (int64_t)R * d0 * a.nchunk;
+    int nsplit = 1;
+    if (blocks < 2 * 148) {
+        nsplit = (int)((2 * 148 + blocks - 1) / blocks);
+        const int max_split = (B + 4 * BROWS - 1) / (4 * BROWS);
+        if (nsplit > max_split) nsplit = max_split;
+        if (nsplit < 1) nsplit = 1;
+    }
+    a.nsplit = nsplit;
+    const size_t nparam = (size_t)F * I * R;
+    if (nsplit > 1 || B == 0) {
+        cudaError_t e = cudaMemsetAsync(dmu, 0, nparam * sizeof(float), st);
+        if (e != cudaSuccess) return spn_cuda_status(e);
+        e = cudaMemsetAsync(dsigma, 0, nparam * sizeof(float), st);
+        if (e != cudaSuccess) return spn_cuda_status(e);
+    }
+    if (B == 0) return SPN_OK;
+    const int tile_f = BROWS * I4 + F4 * BROWS;
+    const int red_f = ngroups * ntile * 36 + ntile * 16 * 3;
+    const int smem = (tile_f > red_f ? tile_f : red_f) * (int)sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(leaf_tiled_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return spn_cuda_status(e);
+    leaf_tiled_bwd_kernel<<<dim3(R * d0, a.nchunk, nsplit), ngroups * ntile, smem, st>>>(a);
+    return spn_launch_status();
+}

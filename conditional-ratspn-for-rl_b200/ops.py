@@ -43,25 +43,35 @@ class LeafFn(torch.autograd.Function):
             out = torch.empty(d0, R, B, I, device=x.device, dtype=torch.float32)
             so = (I, R * B * I, 1, B * I)
         shared = Wsets == 1
+        # shared parameters + plain inputs: register-tiled kernels on the feature-major copy of x
+        tiled = shared and oc == 1 and rr == 1 and B >= 32 and bool(_abi.lib().spn_leaf_tiled_supported(I, R, d0))
         sp, i_fast = (I * R, R, 1), 0
         if shared and layout != "ref":
             # parameters in the order of the activation layout ([F][R][I]) so that a warp's loads are contiguous
             mu, sigma = mu.permute(0, 1, 3, 2).contiguous(), sigma.permute(0, 1, 3, 2).contiguous()
             sp, i_fast = (R * I, 1, I), 1
-        if shared:
+        st = stream_ptr(x.device)
+        xT = None
+        if tiled:
+            xT = torch.empty(F, B, device=x.device, dtype=torch.float32)
+            call("spn_leaf_transpose", ptr(x), sx[0], sx[1], B, F, ptr(xT), st)
+            call("spn_leaf_tiled_fwd", ptr(xT), ptr(perm32), ptr(mu), ptr(sigma), *sp, B, F, I, R, card, d0,
+                 int(tanh_corr), ptr(out), *so, st)
+        elif shared:
             call("spn_leaf_shared_fwd", ptr(x), *sx, ptr(perm32), ptr(mu), ptr(sigma), *sp, i_fast, B, F, I, R, card, d0,
-                 int(tanh_corr), ptr(out), *so, stream_ptr(x.device))
+                 int(tanh_corr), ptr(out), *so, st)
         else:
             call("spn_leaf_fwd", ptr(x), *sx, ptr(perm32), ptr(mu), ptr(sigma), Wsets, w, B, F, I, R, card, d0,
-                 int(tanh_corr), ptr(out), *so, stream_ptr(x.device))
-        ctx.save_for_backward(x, mu, sigma, perm32 if perm32 is not None else torch.empty(0, device=x.device))
-        ctx.meta = (sx, so, Wsets, w, B, F, I, R, card, d0, int(tanh_corr), perm32 is not None, sp, i_fast)
+                 int(tanh_corr), ptr(out), *so, st)
+        empty = torch.empty(0, device=x.device)
+        ctx.save_for_backward(x, mu, sigma, perm32 if perm32 is not None else empty, xT if tiled else empty)
+        ctx.meta = (sx, so, Wsets, w, B, F, I, R, card, d0, int(tanh_corr), perm32 is not None, sp, i_fast, tiled)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x, mu, sigma, perm32 = ctx.saved_tensors
-        sx, so, Wsets, w, B, F, I, R, card, d0, tanh_corr, has_perm, sp, i_fast = ctx.meta
+        x, mu, sigma, perm32, xT = ctx.saved_tensors
+        sx, so, Wsets, w, B, F, I, R, card, d0, tanh_corr, has_perm, sp, i_fast, tiled = ctx.meta
         perm32 = perm32 if has_perm else None
         g = _f32c(g)
         dx = dmu = dsigma = None
@@ -69,14 +79,17 @@ class LeafFn(torch.autograd.Function):
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             dmu = torch.empty_like(mu)
             dsigma = torch.empty_like(sigma)
-            if Wsets == 1:
+            if tiled:
+                call("spn_leaf_tiled_bwd_params", ptr(xT), ptr(g), *so, ptr(perm32), ptr(mu), ptr(sigma), *sp, B, F, I, R,
+                     card, d0, ptr(dmu), ptr(dsigma), st)
+            elif Wsets == 1:
                 call("spn_leaf_shared_bwd_params", ptr(g), *so, ptr(x), *sx, ptr(perm32), ptr(mu), ptr(sigma), *sp,
                      i_fast, B, F, I, R, card, d0, ptr(dmu), ptr(dsigma), st)
-                if i_fast:  # back to the parameter layout [1, F, I, R]
-                    dmu, dsigma = dmu.permute(0, 1, 3, 2), dsigma.permute(0, 1, 3, 2)
             else:
                 call("spn_leaf_bwd_params", ptr(g), *so, ptr(x), *sx, ptr(perm32), ptr(mu), ptr(sigma), Wsets, w, B, F,
                      I, R, card, d0, ptr(dmu), ptr(dsigma), st)
+            if i_fast:  # back to the parameter layout [1, F, I, R]
+                dmu, dsigma = dmu.permute(0, 1, 3, 2), dsigma.permute(0, 1, 3, 2)
         if ctx.needs_input_grad[0]:
             if i_fast:
                 mu, sigma = mu.permute(0, 1, 3, 2).contiguous(), sigma.permute(0, 1, 3, 2).contiguous()

@@ -76,6 +76,19 @@ int spn_leaf_shared_bwd_params(const float* g, int64_t sg_b, int64_t sg_d, int64
                                const float* mu, const float* sigma, int64_t sp_f, int64_t sp_i, int64_t sp_r, int i_fast,
                                int B, int F, int I, int R, int card, int d0, float* dmu, float* dsigma, void* stream);
 
+/* Register-tiled variants for shared parameters and plain inputs x [B, F] (no channel / repetition dims): the fp32-pipe
+ * bound path used by RatSpn.forward.  spn_leaf_transpose writes the feature-major copy xT [F, B] (caller-allocated) that
+ * both kernels gather whole row segments from; parameter / output / gradient strides as in spn_leaf_shared_*. */
+int spn_leaf_transpose(const float* x, int64_t sx_b, int64_t sx_f, int B, int F, float* xT, void* stream);
+int spn_leaf_tiled_supported(int I, int R, int d0);
+int spn_leaf_tiled_fwd(const float* xT, const int32_t* perm, const float* mu, const float* sigma, int64_t sp_f,
+                       int64_t sp_i, int64_t sp_r, int B, int F, int I, int R, int card, int d0, int tanh_corr, float* out,
+                       int64_t so_b, int64_t so_d, int64_t so_c, int64_t so_r, void* stream);
+int spn_leaf_tiled_bwd_params(const float* xT, const float* g, int64_t sg_b, int64_t sg_d, int64_t sg_c, int64_t sg_r,
+                              const int32_t* perm, const float* mu, const float* sigma, int64_t sp_f, int64_t sp_i,
+                              int64_t sp_r, int B, int F, int I, int R, int card, int d0, float* dmu, float* dsigma,
+                              void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Sum layer, optionally fused with the CrossProduct layer below it (the c*c outer sum is never materialised).
  * Replaces layers.py:419-440 + :545-563 (CrossProduct.forward / split_shuffled_scopes), layers.py:110-128
