@@ -27,6 +27,7 @@ SIGNATURES = {
                             _P],
     "spn_leaf_shared_bwd_params": [_P, _L, _L, _L, _L, _P, _L, _L, _L, _L, _P, _P, _P, _L, _L, _L, _I, _I, _I, _I, _I,
                                    _I, _I, _P, _P, _P],
+    "spn_leaf_workspace_floats": [_I, _I],
     "spn_leaf_transpose": [_P, _L, _L, _I, _I, _P, _P],
     "spn_leaf_tiled_supported": [_I, _I, _I],
     "spn_leaf_tiled_fwd": [_P, _P, _P, _P, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _L, _P],
@@ -54,6 +55,8 @@ SIGNATURES = {
                         _I, _I, _P, _P, _P],
 }
 
+_RETURNS_INT64 = {"spn_leaf_workspace_floats"}
+
 _lib = None
 LAUNCHES = 0  # number of kernel-launching ABI calls made by this process (bench.py reports it)
 
@@ -74,7 +77,7 @@ def lib():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if a declared symbol is not exported
             fn.argtypes = argtypes
-            fn.restype = ctypes.c_int
+            fn.restype = ctypes.c_int64 if name in _RETURNS_INT64 else ctypes.c_int
         _lib = handle
     return _lib
 

@@ -62,3 +62,19 @@ __device__ __forceinline__ float spn_normal(uint64_t elem, uint64_t stream_id, u
     float rad = sqrtf(-2.f * __logf(u1));
     return rad * __cosf(6.283185307179586f * u2);
 }
+
+// ------------------------------------------------------------------------------------------------ cp.async (LDGSTS)
+// src_bytes < size zero-fills the remainder (src_bytes = 0: pure zero fill, the source is not read).
+__device__ __forceinline__ void spn_cp_async16(void* dst_smem, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src),
+                 "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void spn_cp_async4(void* dst_smem, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src),
+                 "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void spn_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void spn_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }

@@ -2,16 +2,17 @@
 //
 // The leaf layer evaluates N*F*I*R Gaussian log-densities (cfg 2: 5.1e9) from only N*F inputs and 2*F*I*R parameters,
 // so it is bound by the fp32 pipes, not by HBM -- provided operands are re-used from shared memory / registers:
-//   * x is first transposed to feature-major xT [F][B] (spn_leaf_transpose), so that the per-repetition feature
-//     permutation x[b, perm[f, r]] becomes a gather of whole contiguous 512-byte row segments instead of one 32-byte
-//     sector per value;
-//   * forward: block = (128 rows, scope s, repetition r); the features of the scope are staged in chunks of 32 as
-//     xs[feature][row] together with mu and 1/(2 sigma^2) per (feature, channel); each thread owns a 4-row x 4-channel
+//   * x is first transposed to feature-major xT [F][ldx] (spn_leaf_transpose; ldx = B rounded up to 4, zero padded), so
+//     that the per-repetition feature permutation x[b, perm[f, r]] becomes a gather of whole contiguous row segments
+//     instead of one 32-byte sector per value; the same pass records which 64-row groups contain NaN inputs;
+//   * forward: block = (scope s, repetition r) walking over 128-row tiles; the features of the scope are staged in
+//     chunks of 32 as xs[feature][row] by cp.async (double buffered: the next tile streams in while the current one is
+//     evaluated) next to mu, 1/(2 sigma^2) and log sigma per (feature, channel); each thread owns a 4-row x 4-channel
 //     register tile: 3 shared-memory vector loads feed 16 evaluations (sub, mul, fma) per feature;
 //   * backward (parameters): block = (scope s, repetition r, feature chunk); each thread owns a 4-feature x 4-channel
-//     tile of (sum g*d, sum g*d*d) accumulators and walks the rows in tiles of 64 staged in shared memory; row sub-groups
-//     of the block are combined through shared memory, so every gradient element is written once (no atomics unless the
-//     grid has to be split over rows to fill the machine).
+//     tile of (sum g*d, sum g*d*d) accumulators and walks the rows in double-buffered cp.async tiles of 64; row
+//     sub-groups of the block are combined through shared memory, so every gradient element is written once (no
+//     atomics unless the grid has to be split over rows to fill the machine).
 // NaN inputs (marginalised features, distributions.py:58-61, :243) take a block-uniform slow path with a validity mask.
 // Reference semantics: rat_spn.py:155-170, distributions.py:199-246, :366-382, layers.py:276-312.
 #include "common.cuh"
@@ -19,49 +20,75 @@
 namespace {
 
 constexpr int FC = 32;      // features per staged chunk
-constexpr int FROWS = 128;  // rows per forward block
-constexpr int BROWS = 64;   // rows per staged backward tile
+constexpr int FROWS = 128;  // rows per forward tile
+constexpr int BROWS = 64;   // rows per backward tile (= granularity of the NaN flags)
 
 struct LeafTiledArgs {
-    const float* xT;  // [F][B]
+    const float* xT;  // [F][ldx]
+    const int* nanflag;  // [ceil(B / 64)]
     const int32_t* perm;
     const float* mu; const float* sigma; int64_t sp_f, sp_i, sp_r;
-    int B, F, I, R, card, d0, tanh_corr;
+    int B, ldx, F, I, R, card, d0, tanh_corr;
     float* out; const float* g; int64_t so_b, so_d, so_c, so_r;
     float* dmu; float* dsigma;
-    int nsplit, nchunk, fchunk;
+    int nsplit, nchunk, fchunk, vec_io;
 };
 
+__host__ __device__ inline int leaf_ldx(int B) { return (B + 3) / 4 * 4; }
+
 __global__ void __launch_bounds__(256) leaf_transpose_kernel(const float* __restrict__ x, int64_t sx_b, int64_t sx_f, int B,
-                                                            int F, float* __restrict__ xT) {
+                                                            int ldx, int F, float* __restrict__ xT, int* __restrict__ nanflag) {
     __shared__ float tile[32][33];
     const int b0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    int has_nan = 0;
     for (int j = ty; j < 32; j += 8) {
         const int b = b0 + j, f = f0 + tx;
-        tile[j][tx] = (b < B && f < F) ? x[(int64_t)b * sx_b + (int64_t)f * sx_f] : 0.f;
+        const float v = (b < B && f < F) ? x[(int64_t)b * sx_b + (int64_t)f * sx_f] : 0.f;
+        if (isnan(v)) has_nan = 1;
+        tile[j][tx] = v;
     }
-    __syncthreads();
+    has_nan = __syncthreads_or(has_nan);
+    if (has_nan && threadIdx.x == 0) atomicOr(nanflag + b0 / BROWS, 1);
     for (int j = ty; j < 32; j += 8) {
         const int f = f0 + j, b = b0 + tx;
-        if (f < F && b < B) xT[(int64_t)f * B + b] = tile[tx][j];
+        if (f < F && b < ldx) xT[(int64_t)f * ldx + b] = tile[tx][j];
     }
 }
 
-// grid (ceil(B / FROWS), R, d0); block 32 * ceil(I / 4) threads: lane = row group (4 rows), warp = channel group (4 ch).
+// grid (row-tile groups, R, d0); block 32 * ceil(I / 4) threads: lane = row group (4 rows), warp = channel group (4 ch).
 __global__ void __launch_bounds__(1024) leaf_tiled_fwd_kernel(LeafTiledArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int I4 = (int)(blockDim.x >> 5) * 4;
-    float* xs = sm;                       // [FC][FROWS]            (re-used as the output staging tile [FROWS][I4])
-    float* pm = sm + max(FC * FROWS, FROWS * I4);  // [FC][I4] mu
+    float* xs = sm;                       // [2][FC][FROWS]
+    float* pm = sm + 2 * FC * FROWS;      // [FC][I4] mu
     float* pa = pm + FC * I4;             // [FC][I4] 1 / (2 sigma^2)
     float* pk = pa + FC * I4;             // [FC][I4] log sigma + log sqrt(2 pi)
     float* ks = pk + FC * I4;             // [I4]     sum of pk over the chunk
-    __shared__ int src_f[FC];
     const int s = blockIdx.z, r = blockIdx.y;
-    const int64_t b0 = (int64_t)blockIdx.x * FROWS;
     const int rg = threadIdx.x & 31, cg = threadIdx.x >> 5;
     const int f_begin = s * a.card, f_end = min(a.F, f_begin + a.card);
+    const int nchunks = (f_end - f_begin + FC - 1) / FC;
+    const int ntiles = (a.B + FROWS - 1) / FROWS;
+    const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int nstages = my_tiles * nchunks;
+    const int pi = threadIdx.x % I4, pj0 = threadIdx.x / I4;  // parameter staging: blockDim = 8 * I4
+
+    auto issue = [&](int k) {
+        const int tile = blockIdx.x + (k / nchunks) * gridDim.x, ch = k % nchunks;
+        const int fc0 = f_begin + ch * FC, cnt = min(FC, f_end - fc0);
+        const int b0 = tile * FROWS;
+        float* dst = xs + (k & 1) * FC * FROWS;
+        for (int c = threadIdx.x; c < cnt * 32; c += blockDim.x) {
+            const int j = c >> 5, q = c & 31;
+            const int f = fc0 + j;
+            const int src = a.perm ? a.perm[(int64_t)f * a.R + r] : f;
+            const int b = b0 + 4 * q;
+            const int bytes = max(0, min(16, (a.ldx - b) * 4));
+            spn_cp_async16(dst + j * FROWS + 4 * q, a.xT + (int64_t)src * a.ldx + (bytes ? b : 0), bytes);
+        }
+        spn_cp_async_commit();
+    };
 
     float acc[4][4];
 #pragma unroll
@@ -69,44 +96,40 @@ __global__ void __launch_bounds__(1024) leaf_tiled_fwd_kernel(LeafTiledArgs a) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
 
-    for (int fc0 = f_begin; fc0 < f_end; fc0 += FC) {
-        const int cnt = min(FC, f_end - fc0);
-        __syncthreads();  // previous chunk fully consumed
-        if (threadIdx.x < cnt) {
-            const int f = fc0 + threadIdx.x;
-            src_f[threadIdx.x] = a.perm ? a.perm[(int64_t)f * a.R + r] : f;
-        }
-        for (int e = threadIdx.x; e < cnt * I4; e += blockDim.x) {
-            const int j = e / I4, i = e % I4;
-            float m = 0.f, av = 0.f, kv = 0.f;
-            if (i < a.I) {
-                const int64_t p = (int64_t)(fc0 + j) * a.sp_f + (int64_t)i * a.sp_i + (int64_t)r * a.sp_r;
-                m = a.mu[p];
-                const float sg = a.sigma[p];
-                av = 1.f / (2.f * sg * sg);
-                kv = logf(sg) + SPN_LOG_SQRT_2PI;
+    if (nstages > 0) issue(0);
+    for (int k = 0; k < nstages; ++k) {
+        const int tile = blockIdx.x + (k / nchunks) * gridDim.x, ch = k % nchunks;
+        const int fc0 = f_begin + ch * FC, cnt = min(FC, f_end - fc0);
+        const int b0 = tile * FROWS;
+        if (k + 1 < nstages) issue(k + 1);
+        if (nchunks > 1 || k == 0) {
+            for (int j = pj0; j < cnt; j += 8) {
+                float m = 0.f, av = 0.f, kv = 0.f;
+                if (pi < a.I) {
+                    const int64_t p = (int64_t)(fc0 + j) * a.sp_f + (int64_t)pi * a.sp_i + (int64_t)r * a.sp_r;
+                    m = a.mu[p];
+                    const float sg = a.sigma[p];
+                    av = 1.f / (2.f * sg * sg);
+                    kv = logf(sg) + SPN_LOG_SQRT_2PI;
+                }
+                pm[j * I4 + pi] = m; pa[j * I4 + pi] = av; pk[j * I4 + pi] = kv;
             }
-            pm[e] = m; pa[e] = av; pk[e] = kv;
+            __syncthreads();
+            if (threadIdx.x < I4) {
+                float t = 0.f;
+                for (int j = 0; j < cnt; ++j) t += pk[j * I4 + threadIdx.x];
+                ks[threadIdx.x] = t;
+            }
         }
+        if (k + 1 < nstages) spn_cp_async_wait<1>(); else spn_cp_async_wait<0>();
         __syncthreads();
-        int has_nan = 0;
-        for (int e = threadIdx.x; e < cnt * FROWS; e += blockDim.x) {
-            const int j = e / FROWS, row = e % FROWS;
-            const int64_t b = b0 + row;
-            float v = b < a.B ? __ldg(a.xT + (int64_t)src_f[j] * a.B + b) : 0.f;
-            if (isnan(v)) has_nan = 1;
-            xs[e] = v;
-        }
-        if (threadIdx.x < I4) {
-            float t = 0.f;
-            for (int j = 0; j < cnt; ++j) t += pk[j * I4 + threadIdx.x];
-            ks[threadIdx.x] = t;
-        }
-        has_nan = __syncthreads_or(has_nan);
+        const float* xb = xs + (k & 1) * FC * FROWS;
+        int has_nan = a.nanflag[b0 / BROWS];
+        if (b0 + BROWS < a.B) has_nan |= a.nanflag[b0 / BROWS + 1];
         if (!has_nan && !a.tanh_corr) {
 #pragma unroll 2
             for (int j = 0; j < cnt; ++j) {
-                const float4 x4 = *reinterpret_cast<const float4*>(xs + j * FROWS + 4 * rg);
+                const float4 x4 = *reinterpret_cast<const float4*>(xb + j * FROWS + 4 * rg);
                 const float4 m4 = *reinterpret_cast<const float4*>(pm + j * I4 + 4 * cg);
                 const float4 a4 = *reinterpret_cast<const float4*>(pa + j * I4 + 4 * cg);
                 const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
@@ -129,7 +152,7 @@ __global__ void __launch_bounds__(1024) leaf_tiled_fwd_kernel(LeafTiledArgs a) {
         } else {
             // slow path: NaN -> contributes nothing; tanh change-of-variables correction per (row, feature)
             for (int j = 0; j < cnt; ++j) {
-                const float4 x4 = *reinterpret_cast<const float4*>(xs + j * FROWS + 4 * rg);
+                const float4 x4 = *reinterpret_cast<const float4*>(xb + j * FROWS + 4 * rg);
                 const float4 m4 = *reinterpret_cast<const float4*>(pm + j * I4 + 4 * cg);
                 const float4 a4 = *reinterpret_cast<const float4*>(pa + j * I4 + 4 * cg);
                 const float4 k4 = *reinterpret_cast<const float4*>(pk + j * I4 + 4 * cg);
@@ -149,19 +172,26 @@ __global__ void __launch_bounds__(1024) leaf_tiled_fwd_kernel(LeafTiledArgs a) {
                 }
             }
         }
-    }
-    // stage the [FROWS][I4] tile and write it with the channel index fastest
-    __syncthreads();
-    float* os = sm;
+        if (ch == nchunks - 1) {
+            // every thread writes its 4 x 4 tile straight from registers
+            float* obase = a.out + (int64_t)s * a.so_d + (int64_t)r * a.so_r;
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-        *reinterpret_cast<float4*>(os + (4 * rg + u) * I4 + 4 * cg) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
-    __syncthreads();
-    const int nrow = (int)min((int64_t)FROWS, a.B - b0);
-    float* obase = a.out + (int64_t)s * a.so_d + (int64_t)r * a.so_r;
-    for (int e = threadIdx.x; e < nrow * a.I; e += blockDim.x) {
-        const int row = e / a.I, i = e % a.I;
-        obase[(b0 + row) * a.so_b + (int64_t)i * a.so_c] = os[row * I4 + i];
+            for (int u = 0; u < 4; ++u) {
+                const int64_t b = (int64_t)b0 + 4 * rg + u;
+                if (b < a.B) {
+                    if (a.vec_io) {
+                        *reinterpret_cast<float4*>(obase + b * a.so_b + 4 * cg) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v)
+                            if (4 * cg + v < a.I) obase[b * a.so_b + (int64_t)(4 * cg + v) * a.so_c] = acc[u][v];
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+            }
+        }
+        __syncthreads();  // stage buffers / parameters may be overwritten from here on
     }
 }
 
@@ -172,8 +202,8 @@ __global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
     const int nfg = (a.fchunk + 3) / 4, F4 = nfg * 4;
     const int ntile = nfg * nig;
     const int ngroups = blockDim.x / ntile;
-    float* gs = sm;                    // [BROWS][I4]
-    float* xs = gs + BROWS * I4;       // [F4][BROWS]
+    float* gs = sm;                        // [2][BROWS][I4]
+    float* xs = gs + 2 * BROWS * I4;       // [2][BROWS][F4]
     __shared__ int src_f[FC];
     const int s = blockIdx.x / a.R, r = blockIdx.x % a.R;
     const int f_begin = s * a.card + blockIdx.y * a.fchunk;
@@ -181,7 +211,6 @@ __global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
     const int cnt = f_end - f_begin;
     if (cnt <= 0) return;
     const int tile = threadIdx.x % ntile, grp = threadIdx.x / ntile;
-    const bool worker = grp < ngroups;
     const int ig = tile % nig, fg = tile / nig;
 
     if (threadIdx.x < F4) {
@@ -206,34 +235,51 @@ __global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
     const int64_t rows_per = (((int64_t)a.B + a.nsplit - 1) / a.nsplit + BROWS - 1) / BROWS * BROWS;
     const int64_t row_begin = (int64_t)blockIdx.z * rows_per;
     const int64_t row_end = min((int64_t)a.B, row_begin + rows_per);
+    const int ntiles = row_end > row_begin ? (int)((row_end - row_begin + BROWS - 1) / BROWS) : 0;
     const float* gbase = a.g + (int64_t)s * a.so_d + (int64_t)r * a.so_r;
     __syncthreads();
 
-    for (int64_t b0 = row_begin; b0 < row_end; b0 += BROWS) {
+    auto issue = [&](int t) {
+        const int64_t b0 = row_begin + (int64_t)t * BROWS;
         const int nrow = (int)min((int64_t)BROWS, row_end - b0);
-        __syncthreads();
-        for (int e = threadIdx.x; e < BROWS * I4; e += blockDim.x) {
-            const int row = e / I4, i = e % I4;
-            gs[e] = (row < nrow && i < a.I) ? __ldg(gbase + (b0 + row) * a.so_b + (int64_t)i * a.so_c) : 0.f;
+        float* gd = gs + (t & 1) * BROWS * I4;
+        float* xd = xs + (t & 1) * BROWS * F4;
+        if (a.vec_io) {  // the g tile is one contiguous run of nrow * I floats (I % 4 == 0)
+            const float* src = gbase + b0 * a.so_b;
+            const int nvalid = nrow * a.I / 4;
+            for (int c = threadIdx.x; c < BROWS * I4 / 4; c += blockDim.x)
+                spn_cp_async16(gd + 4 * c, src + (c < nvalid ? 4 * c : 0), c < nvalid ? 16 : 0);
+        } else {
+            for (int e = threadIdx.x; e < BROWS * I4; e += blockDim.x) {
+                const int row = e / I4, i = e % I4;
+                const bool ok = row < nrow && i < a.I;
+                spn_cp_async4(gd + e, ok ? gbase + (b0 + row) * a.so_b + (int64_t)i * a.so_c : gbase, ok ? 4 : 0);
+            }
         }
-        int has_nan = 0;
         for (int e = threadIdx.x; e < F4 * BROWS; e += blockDim.x) {
             const int j = e / BROWS, row = e % BROWS;
-            float v = 0.f;
-            if (row < nrow && j < cnt) v = __ldg(a.xT + (int64_t)src_f[j] * a.B + b0 + row);
-            if (isnan(v)) has_nan = 1;
-            xs[e] = v;
+            const bool ok = row < nrow && j < cnt;
+            spn_cp_async4(xd + row * F4 + j, ok ? a.xT + (int64_t)src_f[j] * a.ldx + b0 + row : a.xT, ok ? 4 : 0);
         }
-        has_nan = __syncthreads_or(has_nan);
-        if (!worker) continue;
+        spn_cp_async_commit();
+    };
+
+    if (ntiles > 0) issue(0);
+    for (int t = 0; t < ntiles; ++t) {
+        const int64_t b0 = row_begin + (int64_t)t * BROWS;
+        const int nrow = (int)min((int64_t)BROWS, row_end - b0);
+        if (t + 1 < ntiles) { issue(t + 1); spn_cp_async_wait<1>(); } else { spn_cp_async_wait<0>(); }
+        __syncthreads();
+        const float* gb = gs + (t & 1) * BROWS * I4;
+        const float* xb = xs + (t & 1) * BROWS * F4;
+        const int has_nan = a.nanflag[b0 / BROWS];
         if (!has_nan) {
 #pragma unroll 2
             for (int row = grp; row < nrow; row += ngroups) {
-                const float4 g4 = *reinterpret_cast<const float4*>(gs + row * I4 + 4 * ig);
+                const float4 g4 = *reinterpret_cast<const float4*>(gb + row * I4 + 4 * ig);
+                const float4 x4 = *reinterpret_cast<const float4*>(xb + row * F4 + 4 * fg);
                 const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
-                float xv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) xv[u] = xs[(4 * fg + u) * BROWS + row];
+                const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
                 for (int v = 0; v < 4; ++v) a0[v] += gv[v];
 #pragma unroll
@@ -241,40 +287,42 @@ __global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
                         const float d = xv[u] - mv[u][v];
-                        const float t = gv[v] * d;
-                        a1[u][v] += t;
-                        a2[u][v] = fmaf(t, d, a2[u][v]);
+                        const float tt = gv[v] * d;
+                        a1[u][v] += tt;
+                        a2[u][v] = fmaf(tt, d, a2[u][v]);
                     }
             }
         } else {
             for (int row = grp; row < nrow; row += ngroups) {
-                const float4 g4 = *reinterpret_cast<const float4*>(gs + row * I4 + 4 * ig);
+                const float4 g4 = *reinterpret_cast<const float4*>(gb + row * I4 + 4 * ig);
+                const float4 x4 = *reinterpret_cast<const float4*>(xb + row * F4 + 4 * fg);
                 const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+                const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
                 for (int v = 0; v < 4; ++v) a0[v] += gv[v];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const float x = xs[(4 * fg + u) * BROWS + row];
-                    if (isnan(x)) {
+                    if (isnan(xv[u])) {
 #pragma unroll
                         for (int v = 0; v < 4; ++v) cr[u][v] += gv[v];  // this row does not count for feature u
                     } else {
 #pragma unroll
                         for (int v = 0; v < 4; ++v) {
-                            const float d = x - mv[u][v];
-                            const float t = gv[v] * d;
-                            a1[u][v] += t;
-                            a2[u][v] = fmaf(t, d, a2[u][v]);
+                            const float d = xv[u] - mv[u][v];
+                            const float tt = gv[v] * d;
+                            a1[u][v] += tt;
+                            a2[u][v] = fmaf(tt, d, a2[u][v]);
                         }
                     }
                 }
             }
         }
+        __syncthreads();  // the buffer read here is refilled by the next iteration's issue
     }
-    // combine the row groups through shared memory: red[grp][tile][36]
-    __syncthreads();
+    // combine the row groups through shared memory: red[grp][tile][36], then fin[tile * 16][3]
     float* red = sm;
-    if (worker) {
+    float* fin = red + (int64_t)ngroups * ntile * 36;
+    {
         float* my = red + ((int64_t)grp * ntile + tile) * 36;
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -287,22 +335,17 @@ __global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
         for (int v = 0; v < 4; ++v) my[32 + v] = a0[v];
     }
     __syncthreads();
-    // element e -> (tile, u, v): sum over groups, finish dmu / dsigma
     for (int e = threadIdx.x; e < ntile * 16; e += blockDim.x) {
-        const int t = e / 16, uv = e % 16, u = uv / 4, v = uv % 4;
-        const int f = f_begin + 4 * (t / nig) + u, i = 4 * (t % nig) + v;
+        const int t = e / 16, uv = e % 16, v = uv % 4;
         float s1 = 0.f, s2 = 0.f, s0 = 0.f;
         for (int gq = 0; gq < ngroups; ++gq) {
             const float* src = red + ((int64_t)gq * ntile + t) * 36;
             s1 += src[uv]; s2 += src[16 + uv]; s0 += src[32 + v];
         }
-        red[(int64_t)ngroups * ntile * 36 + e * 3] = s1;  // keep for the second pass (cr)
-        red[(int64_t)ngroups * ntile * 36 + e * 3 + 1] = s2;
-        red[(int64_t)ngroups * ntile * 36 + e * 3 + 2] = s0;
-        (void)f; (void)i;
+        fin[e * 3] = s1; fin[e * 3 + 1] = s2; fin[e * 3 + 2] = s0;
     }
     __syncthreads();
-    if (worker) {  // second pass: the NaN corrections re-use the per-group slots
+    {  // second pass: the NaN corrections re-use the per-group slots
         float* my = red + ((int64_t)grp * ntile + tile) * 36;
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -316,12 +359,11 @@ __global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
         if (f >= f_end || i >= a.I) continue;
         float sc = 0.f;
         for (int gq = 0; gq < ngroups; ++gq) sc += red[((int64_t)gq * ntile + t) * 36 + uv];
-        const float* fin = red + (int64_t)ngroups * ntile * 36 + e * 3;
         const int64_t p = (int64_t)f * a.sp_f + (int64_t)i * a.sp_i + (int64_t)r * a.sp_r;
         const float inv_sg = 1.f / a.sigma[p];
         const float inv_var = inv_sg * inv_sg;
-        const float dmu = fin[0] * inv_var;
-        const float dsg = fin[1] * inv_var * inv_sg - (fin[2] - sc) * inv_sg;
+        const float dmu = fin[e * 3] * inv_var;
+        const float dsg = fin[e * 3 + 1] * inv_var * inv_sg - (fin[e * 3 + 2] - sc) * inv_sg;
         if (a.nsplit == 1) {
             a.dmu[p] = dmu;
             a.dsigma[p] = dsg;
@@ -334,31 +376,46 @@ __global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
 
 }  // namespace
 
+extern "C" int64_t spn_leaf_workspace_floats(int B, int F) {
+    return (int64_t)F * leaf_ldx(B) + (B + BROWS - 1) / BROWS + 4;
+}
+
 extern "C" int spn_leaf_transpose(const float* x, int64_t sx_b, int64_t sx_f, int B, int F, float* xT, void* stream) {
     if (!x || !xT || B < 0 || F <= 0) return SPN_ERR_ARG;
     if (B == 0) return SPN_OK;
-    leaf_transpose_kernel<<<dim3((B + 31) / 32, (F + 31) / 32), 256, 0, (cudaStream_t)stream>>>(x, sx_b, sx_f, B, F, xT);
+    const int ldx = leaf_ldx(B);
+    int* flags = reinterpret_cast<int*>(xT + (size_t)F * ldx);
+    cudaError_t e = cudaMemsetAsync(flags, 0, ((B + BROWS - 1) / BROWS) * sizeof(int), (cudaStream_t)stream);
+    if (e != cudaSuccess) return spn_cuda_status(e);
+    leaf_transpose_kernel<<<dim3((ldx + 31) / 32, (F + 31) / 32), 256, 0, (cudaStream_t)stream>>>(x, sx_b, sx_f, B, ldx, F, xT, flags);
     return spn_launch_status();
 }
 
 extern "C" int spn_leaf_tiled_supported(int I, int R, int d0) { return (I >= 1 && I <= 128 && R <= 65535 && d0 <= 65535) ? 1 : 0; }
 
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 extern "C" int spn_leaf_tiled_fwd(const float* xT, const int32_t* perm, const float* mu, const float* sigma, int64_t sp_f,
                                   int64_t sp_i, int64_t sp_r, int B, int F, int I, int R, int card, int d0, int tanh_corr,
                                   float* out, int64_t so_b, int64_t so_d, int64_t so_c, int64_t so_r, void* stream) {
     if (!xT || !mu || !sigma || !out || B < 0 || F <= 0 || I <= 0 || R <= 0 || card <= 0 || d0 <= 0) return SPN_ERR_ARG;
-    if (!spn_leaf_tiled_supported(I, R, d0)) return SPN_ERR_UNSUPPORTED;
+    if (!spn_leaf_tiled_supported(I, R, d0) || !aligned16(xT)) return SPN_ERR_UNSUPPORTED;
     if (B == 0) return SPN_OK;
     LeafTiledArgs a{};
-    a.xT = xT; a.perm = perm; a.mu = mu; a.sigma = sigma; a.sp_f = sp_f; a.sp_i = sp_i; a.sp_r = sp_r;
+    a.xT = xT; a.ldx = leaf_ldx(B); a.nanflag = reinterpret_cast<const int*>(xT + (size_t)F * a.ldx);
+    a.perm = perm; a.mu = mu; a.sigma = sigma; a.sp_f = sp_f; a.sp_i = sp_i; a.sp_r = sp_r;
     a.B = B; a.F = F; a.I = I; a.R = R; a.card = card; a.d0 = d0; a.tanh_corr = tanh_corr;
     a.out = out; a.so_b = so_b; a.so_d = so_d; a.so_c = so_c; a.so_r = so_r;
+    a.vec_io = (so_c == 1 && I % 4 == 0 && so_b % 4 == 0 && so_d % 4 == 0 && so_r % 4 == 0 && aligned16(out)) ? 1 : 0;
     const int ncg = (I + 3) / 4, I4 = ncg * 4;
-    const int big = FC * FROWS > FROWS * I4 ? FC * FROWS : FROWS * I4;
-    const int smem = (big + 3 * FC * I4 + I4) * (int)sizeof(float);
+    const int smem = (2 * FC * FROWS + 3 * FC * I4 + I4) * (int)sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(leaf_tiled_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return spn_cuda_status(e);
-    leaf_tiled_fwd_kernel<<<dim3((B + FROWS - 1) / FROWS, R, d0), 32 * ncg, smem, (cudaStream_t)stream>>>(a);
+    const int ntiles = (B + FROWS - 1) / FROWS;
+    int gx = (16 * 148 + R * d0 - 1) / (R * d0);
+    if (gx > ntiles) gx = ntiles;
+    if (gx < 1) gx = 1;
+    leaf_tiled_fwd_kernel<<<dim3(gx, R, d0), 32 * ncg, smem, (cudaStream_t)stream>>>(a);
     return spn_launch_status();
 }
 
@@ -370,9 +427,12 @@ extern "C" int spn_leaf_tiled_bwd_params(const float* xT, const float* g, int64_
         return SPN_ERR_ARG;
     if (!spn_leaf_tiled_supported(I, R, d0)) return SPN_ERR_UNSUPPORTED;
     LeafTiledArgs a{};
-    a.xT = xT; a.perm = perm; a.mu = mu; a.sigma = sigma; a.sp_f = sp_f; a.sp_i = sp_i; a.sp_r = sp_r;
+    a.xT = xT; a.ldx = leaf_ldx(B); a.nanflag = reinterpret_cast<const int*>(xT + (size_t)F * a.ldx);
+    a.perm = perm; a.mu = mu; a.sigma = sigma; a.sp_f = sp_f; a.sp_i = sp_i; a.sp_r = sp_r;
     a.B = B; a.F = F; a.I = I; a.R = R; a.card = card; a.d0 = d0;
     a.g = g; a.so_b = sg_b; a.so_d = sg_d; a.so_c = sg_c; a.so_r = sg_r; a.dmu = dmu; a.dsigma = dsigma;
+    // contiguous g rows (internal layout): 16-byte cp.async of the whole tile
+    a.vec_io = (sg_c == 1 && sg_b == I && I % 4 == 0 && sg_d % 4 == 0 && sg_r % 4 == 0 && aligned16(g)) ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int nig = (I + 3) / 4, I4 = nig * 4;
     // feature chunks per scope: at most FC features and at most 256 thread tiles per block
@@ -401,7 +461,7 @@ extern "C" int spn_leaf_tiled_bwd_params(const float* xT, const float* g, int64_
         if (e != cudaSuccess) return spn_cuda_status(e);
     }
     if (B == 0) return SPN_OK;
-    const int tile_f = BROWS * I4 + F4 * BROWS;
+    const int tile_f = 2 * BROWS * (I4 + F4);
     const int red_f = ngroups * ntile * 36 + ntile * 16 * 3;
     const int smem = (tile_f > red_f ? tile_f : red_f) * (int)sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(leaf_tiled_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

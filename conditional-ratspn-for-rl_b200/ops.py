@@ -53,7 +53,7 @@ class LeafFn(torch.autograd.Function):
         st = stream_ptr(x.device)
         xT = None
         if tiled:
-            xT = torch.empty(F, B, device=x.device, dtype=torch.float32)
+            xT = torch.empty(_abi.lib().spn_leaf_workspace_floats(B, F), device=x.device, dtype=torch.float32)
             call("spn_leaf_transpose", ptr(x), sx[0], sx[1], B, F, ptr(xT), st)
             call("spn_leaf_tiled_fwd", ptr(xT), ptr(perm32), ptr(mu), ptr(sigma), *sp, B, F, I, R, card, d0,
                  int(tanh_corr), ptr(out), *so, st)

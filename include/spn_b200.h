@@ -77,8 +77,11 @@ int spn_leaf_shared_bwd_params(const float* g, int64_t sg_b, int64_t sg_d, int64
                                int B, int F, int I, int R, int card, int d0, float* dmu, float* dsigma, void* stream);
 
 /* Register-tiled variants for shared parameters and plain inputs x [B, F] (no channel / repetition dims): the fp32-pipe
- * bound path used by RatSpn.forward.  spn_leaf_transpose writes the feature-major copy xT [F, B] (caller-allocated) that
- * both kernels gather whole row segments from; parameter / output / gradient strides as in spn_leaf_shared_*. */
+ * bound path used by RatSpn.forward.  spn_leaf_transpose fills the caller-allocated workspace `xT`
+ * (spn_leaf_workspace_floats(B, F) floats, 16-byte aligned) with the feature-major, zero-padded copy of x followed by
+ * one NaN flag per 64 rows; both kernels gather whole row segments from it.  Parameter / output / gradient strides as
+ * in spn_leaf_shared_*. */
+int64_t spn_leaf_workspace_floats(int B, int F);
 int spn_leaf_transpose(const float* x, int64_t sx_b, int64_t sx_f, int B, int F, float* xT, void* stream);
 int spn_leaf_tiled_supported(int I, int R, int d0);
 int spn_leaf_tiled_fwd(const float* xT, const int32_t* perm, const float* mu, const float* sigma, int64_t sp_f,

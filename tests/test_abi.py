@@ -12,7 +12,7 @@ def declared_functions():
     src = open(os.path.join(ROOT, "include", "spn_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     out = {}
-    for m in re.finditer(r"\bint\s+(spn_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"\bint(?:64_t)?\s+(spn_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         args = [a for a in m.group(2).split(",") if a.strip()]
         out[m.group(1)] = len(args)
     return out
