@@ -21,7 +21,8 @@ namespace {
 
 constexpr int FC = 32;      // features per staged chunk
 constexpr int FROWS = 128;  // rows per forward tile
-constexpr int BROWS = 64;   // rows per backward tile (= granularity of the NaN flags)
+constexpr int NANROWS = 64; // granularity of the NaN flags written by the transpose pass
+constexpr int BROWS = 128;  // rows per backward tile
 
 struct LeafTiledArgs {
     const float* xT;  // [F][ldx]
@@ -31,7 +32,7 @@ struct LeafTiledArgs {
     int B, ldx, F, I, R, card, d0, tanh_corr;
     float* out; const float* g; int64_t so_b, so_d, so_c, so_r;
     float* dmu; float* dsigma;
-    int nsplit, nchunk, fchunk, vec_io;
+    int nsplit, nchunk, fchunk, vec_io, ngroups;
 };
 
 __host__ __device__ inline int leaf_ldx(int B) { return (B + 3) / 4 * 4; }
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(256) leaf_transpose_kernel(const float* __rest
         tile[j][tx] = v;
     }
     has_nan = __syncthreads_or(has_nan);
-    if (has_nan && threadIdx.x == 0) atomicOr(nanflag + b0 / BROWS, 1);
+    if (has_nan && threadIdx.x == 0) atomicOr(nanflag + b0 / NANROWS, 1);
     for (int j = ty; j < 32; j += 8) {
         const int f = f0 + j, b = b0 + tx;
         if (f < F && b < ldx) xT[(int64_t)f * ldx + b] = tile[tx][j];
@@ -124,8 +125,8 @@ __global__ void __launch_bounds__(1024) leaf_tiled_fwd_kernel(LeafTiledArgs a) {
         if (k + 1 < nstages) spn_cp_async_wait<1>(); else spn_cp_async_wait<0>();
         __syncthreads();
         const float* xb = xs + (k & 1) * FC * FROWS;
-        int has_nan = a.nanflag[b0 / BROWS];
-        if (b0 + BROWS < a.B) has_nan |= a.nanflag[b0 / BROWS + 1];
+        int has_nan = a.nanflag[b0 / NANROWS];
+        if (b0 + NANROWS < a.B) has_nan |= a.nanflag[b0 / NANROWS + 1];
         if (!has_nan && !a.tanh_corr) {
 #pragma unroll 2
             for (int j = 0; j < cnt; ++j) {
@@ -196,14 +197,15 @@ __global__ void __launch_bounds__(1024) leaf_tiled_fwd_kernel(LeafTiledArgs a) {
 }
 
 // grid (R * d0, nchunk, nsplit); block = ngroups * nfg * nig threads, nfg = ceil(fchunk / 4), nig = ceil(I / 4).
-__global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
+__global__ void __launch_bounds__(256, 3) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int nig = (a.I + 3) / 4, I4 = nig * 4;
     const int nfg = (a.fchunk + 3) / 4, F4 = nfg * 4;
     const int ntile = nfg * nig;
-    const int ngroups = blockDim.x / ntile;
+    const int ngroups = a.ngroups;  // blockDim is rounded up to whole warps: threads past ngroups * ntile only copy
     float* gs = sm;                        // [2][BROWS][I4]
     float* xs = gs + 2 * BROWS * I4;       // [2][BROWS][F4]
+    float* crs = xs + 2 * BROWS * F4;      // [F4][I4] sum of g over the rows whose feature is NaN (slow path only)
     __shared__ int src_f[FC];
     const int s = blockIdx.x / a.R, r = blockIdx.x % a.R;
     const int f_begin = s * a.card + blockIdx.y * a.fchunk;
@@ -211,12 +213,14 @@ __global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
     const int cnt = f_end - f_begin;
     if (cnt <= 0) return;
     const int tile = threadIdx.x % ntile, grp = threadIdx.x / ntile;
+    const bool worker = grp < ngroups;
     const int ig = tile % nig, fg = tile / nig;
 
     if (threadIdx.x < F4) {
         const int f = f_begin + min((int)threadIdx.x, cnt - 1);
         src_f[threadIdx.x] = a.perm ? a.perm[(int64_t)f * a.R + r] : f;
     }
+    for (int e = threadIdx.x; e < F4 * I4; e += blockDim.x) crs[e] = 0.f;
     float mv[4][4];  // mu of (feature u, channel v)
 #pragma unroll
     for (int u = 0; u < 4; ++u)
@@ -225,12 +229,12 @@ __global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
             const int f = f_begin + min(4 * fg + u, cnt - 1), i = min(4 * ig + v, a.I - 1);
             mv[u][v] = a.mu[(int64_t)f * a.sp_f + (int64_t)i * a.sp_i + (int64_t)r * a.sp_r];
         }
-    float a1[4][4], a2[4][4], cr[4][4], a0[4];
+    float a1[4][4], a2[4][4], a0[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         a0[u] = 0.f;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) { a1[u][v] = 0.f; a2[u][v] = 0.f; cr[u][v] = 0.f; }
+        for (int v = 0; v < 4; ++v) { a1[u][v] = 0.f; a2[u][v] = 0.f; }
     }
     const int64_t rows_per = (((int64_t)a.B + a.nsplit - 1) / a.nsplit + BROWS - 1) / BROWS * BROWS;
     const int64_t row_begin = (int64_t)blockIdx.z * rows_per;
@@ -256,10 +260,16 @@ __global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
                 spn_cp_async4(gd + e, ok ? gbase + (b0 + row) * a.so_b + (int64_t)i * a.so_c : gbase, ok ? 4 : 0);
             }
         }
-        for (int e = threadIdx.x; e < F4 * BROWS; e += blockDim.x) {
-            const int j = e / BROWS, row = e % BROWS;
-            const bool ok = row < nrow && j < cnt;
-            spn_cp_async4(xd + row * F4 + j, ok ? a.xT + (int64_t)src_f[j] * a.ldx + b0 + row : a.xT, ok ? 4 : 0);
+        // one warp per feature: the source row segment is contiguous, the destination is the transposed tile
+        const int lane = threadIdx.x & 31, nwarp = (blockDim.x + 31) >> 5;
+        for (int j = threadIdx.x >> 5; j < F4; j += nwarp) {
+            const float* src = a.xT + (int64_t)src_f[j] * a.ldx + b0;
+            const bool okj = j < cnt;
+#pragma unroll
+            for (int row = lane; row < BROWS; row += 32) {
+                const bool ok = okj && row < nrow;
+                spn_cp_async4(xd + row * F4 + j, ok ? src + row : a.xT, ok ? 4 : 0);
+            }
         }
         spn_cp_async_commit();
     };
@@ -272,8 +282,10 @@ __global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
         __syncthreads();
         const float* gb = gs + (t & 1) * BROWS * I4;
         const float* xb = xs + (t & 1) * BROWS * F4;
-        const int has_nan = a.nanflag[b0 / BROWS];
-        if (!has_nan) {
+        int has_nan = a.nanflag[b0 / NANROWS];
+        if (b0 + NANROWS < a.B) has_nan |= a.nanflag[b0 / NANROWS + 1];
+        if (!worker) {
+        } else if (!has_nan) {
 #pragma unroll 2
             for (int row = grp; row < nrow; row += ngroups) {
                 const float4 g4 = *reinterpret_cast<const float4*>(gb + row * I4 + 4 * ig);
@@ -304,7 +316,7 @@ __global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
                 for (int u = 0; u < 4; ++u) {
                     if (isnan(xv[u])) {
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) cr[u][v] += gv[v];  // this row does not count for feature u
+                        for (int v = 0; v < 4; ++v) atomicAdd(crs + (4 * fg + u) * I4 + 4 * ig + v, gv[v]);  // row does not count for feature u
                     } else {
 #pragma unroll
                         for (int v = 0; v < 4; ++v) {
@@ -319,10 +331,9 @@ __global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
         }
         __syncthreads();  // the buffer read here is refilled by the next iteration's issue
     }
-    // combine the row groups through shared memory: red[grp][tile][36], then fin[tile * 16][3]
+    // combine the row groups through shared memory: red[grp][tile][36] (aliases the tile buffers, not crs)
     float* red = sm;
-    float* fin = red + (int64_t)ngroups * ntile * 36;
-    {
+    if (worker) {
         float* my = red + ((int64_t)grp * ntile + tile) * 36;
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -336,34 +347,21 @@ __global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
     }
     __syncthreads();
     for (int e = threadIdx.x; e < ntile * 16; e += blockDim.x) {
-        const int t = e / 16, uv = e % 16, v = uv % 4;
+        const int t = e / 16, uv = e % 16, u = uv / 4, v = uv % 4;
+        const int fl = 4 * (t / nig) + u, i = 4 * (t % nig) + v;
+        const int f = f_begin + fl;
+        if (f >= f_end || i >= a.I) continue;
         float s1 = 0.f, s2 = 0.f, s0 = 0.f;
         for (int gq = 0; gq < ngroups; ++gq) {
             const float* src = red + ((int64_t)gq * ntile + t) * 36;
             s1 += src[uv]; s2 += src[16 + uv]; s0 += src[32 + v];
         }
-        fin[e * 3] = s1; fin[e * 3 + 1] = s2; fin[e * 3 + 2] = s0;
-    }
-    __syncthreads();
-    {  // second pass: the NaN corrections re-use the per-group slots
-        float* my = red + ((int64_t)grp * ntile + tile) * 36;
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) my[u * 4 + v] = cr[u][v];
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < ntile * 16; e += blockDim.x) {
-        const int t = e / 16, uv = e % 16, u = uv / 4, v = uv % 4;
-        const int f = f_begin + 4 * (t / nig) + u, i = 4 * (t % nig) + v;
-        if (f >= f_end || i >= a.I) continue;
-        float sc = 0.f;
-        for (int gq = 0; gq < ngroups; ++gq) sc += red[((int64_t)gq * ntile + t) * 36 + uv];
+        s0 -= crs[fl * I4 + i];
         const int64_t p = (int64_t)f * a.sp_f + (int64_t)i * a.sp_i + (int64_t)r * a.sp_r;
         const float inv_sg = 1.f / a.sigma[p];
         const float inv_var = inv_sg * inv_sg;
-        const float dmu = fin[e * 3] * inv_var;
-        const float dsg = fin[e * 3 + 1] * inv_var * inv_sg - (fin[e * 3 + 2] - sc) * inv_sg;
+        const float dmu = s1 * inv_var;
+        const float dsg = s2 * inv_var * inv_sg - s0 * inv_sg;
         if (a.nsplit == 1) {
             a.dmu[p] = dmu;
             a.dsigma[p] = dsg;
@@ -377,7 +375,7 @@ __global__ void __launch_bounds__(256) leaf_tiled_bwd_kernel(LeafTiledArgs a) {
 }  // namespace
 
 extern "C" int64_t spn_leaf_workspace_floats(int B, int F) {
-    return (int64_t)F * leaf_ldx(B) + (B + BROWS - 1) / BROWS + 4;
+    return (int64_t)F * leaf_ldx(B) + (B + NANROWS - 1) / NANROWS + 4;
 }
 
 extern "C" int spn_leaf_transpose(const float* x, int64_t sx_b, int64_t sx_f, int B, int F, float* xT, void* stream) {
@@ -385,7 +383,7 @@ extern "C" int spn_leaf_transpose(const float* x, int64_t sx_b, int64_t sx_f, in
     if (B == 0) return SPN_OK;
     const int ldx = leaf_ldx(B);
     int* flags = reinterpret_cast<int*>(xT + (size_t)F * ldx);
-    cudaError_t e = cudaMemsetAsync(flags, 0, ((B + BROWS - 1) / BROWS) * sizeof(int), (cudaStream_t)stream);
+    cudaError_t e = cudaMemsetAsync(flags, 0, ((B + NANROWS - 1) / NANROWS) * sizeof(int), (cudaStream_t)stream);
     if (e != cudaSuccess) return spn_cuda_status(e);
     leaf_transpose_kernel<<<dim3((ldx + 31) / 32, (F + 31) / 32), 256, 0, (cudaStream_t)stream>>>(x, sx_b, sx_f, B, ldx, F, xT, flags);
     return spn_launch_status();
@@ -444,6 +442,7 @@ extern "C" int spn_leaf_tiled_bwd_params(const float* xT, const float* g, int64_
     int ngroups = 256 / ntile;
     if (ngroups < 1) ngroups = 1;
     if (ngroups > 8) ngroups = 8;
+    a.ngroups = ngroups;
     const int64_t blocks = (int64_t)R * d0 * a.nchunk;
     int nsplit = 1;
     if (blocks < 2 * 148) {
@@ -462,10 +461,11 @@ extern "C" int spn_leaf_tiled_bwd_params(const float* xT, const float* g, int64_
     }
     if (B == 0) return SPN_OK;
     const int tile_f = 2 * BROWS * (I4 + F4);
-    const int red_f = ngroups * ntile * 36 + ntile * 16 * 3;
-    const int smem = (tile_f > red_f ? tile_f : red_f) * (int)sizeof(float);
+    const int red_f = ngroups * ntile * 36;
+    if (red_f > tile_f) return SPN_ERR_UNSUPPORTED;  // cannot happen: ngroups * ntile <= 256 and a tile holds >= 256 * 36 floats
+    const int smem = (tile_f + F4 * I4) * (int)sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(leaf_tiled_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return spn_cuda_status(e);
-    leaf_tiled_bwd_kernel<<<dim3(R * d0, a.nchunk, nsplit), ngroups * ntile, smem, st>>>(a);
+    leaf_tiled_bwd_kernel<<<dim3(R * d0, a.nchunk, nsplit), (ngroups * ntile + 31) / 32 * 32, smem, st>>>(a);
     return spn_launch_status();
 }
