@@ -10,7 +10,8 @@ when N > 1).  Metric: samples/s over all GPUs.
   value     device-timed (CUDA events, max over ranks), inputs resident in HBM
   e2e       same step through the public module API with the batch coming from pinned host memory every step
             (H2D copy inside the timed region) and the loss read back to the host (D2H)
-  roofline  the dominant kernel (the widest Sum layer's forward contraction), timed live with CUDA events
+  roofline  the dominant kernel (the slowest of the three tcgen05 kernels of the widest Sum layer S_1), timed live
+            with CUDA events, L2 flushed between launches
   cpu_baseline  the CPU oracle port of the reference algorithm on the host cores, on a bounded micro-batch sample
 
 ``--impl reference`` times only that CPU path (the reference is pure Python/PyTorch and is not present on the GPU box;
@@ -191,7 +192,12 @@ def main():
     host = [torch.rand(B, 1, CFG["F"], 1, 1, generator=gen).pin_memory() for _ in range(nbuf)]
     resident = [h.to(dev) for h in host]
 
+    sum_layers = [m for m in model.modules() if hasattr(m, "invalidate_weight_cache")]
+
     def step(x):
+        # a training step changes the weights, so the bf16 operand images are rebuilt every step (no cached weights)
+        for m in sum_layers:
+            m.invalidate_weight_cache()
         reducer.zero_()
         loss = -model(x).mean()
         loss.backward()
@@ -239,8 +245,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(t.item())
 
-    # ---- roofline of the dominant kernel: forward contraction of the widest Sum layer (S_1), timed alone
-    roof = None
+    # ---- roofline: the tensor-core kernels of the widest Sum layer (S_1), each timed alone with CUDA events
+    roof, kernels = None, None
     if rank == 0:
         peaks = {}
         try:
@@ -248,35 +254,61 @@ def main():
                 peaks = json.load(f)
         except Exception:
             pass
+        ncu = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+                ncu = json.load(f)
+        except Exception:
+            pass
         from ratspn_b200 import ops
-        with torch.no_grad():
-            h0 = model._leaf(resident[0], perm32=model._perm32()[0])
-            layer = model._inner_layers[1]
-            lw = layer.weights
+
+        def time_alone(fn, reps=10):
+            flush = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)  # 256 MB > 126 MB L2
             for _ in range(2):
-                ops.sum_forward(h0, lw, "xsum")
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 3
-            a.record()
+                fn()
+            ts = []
             for _ in range(reps):
-                ops.sum_forward(h0, lw, "xsum")
-            b.record()
-            torch.cuda.synchronize()
-            k_ms = a.elapsed_time(b) / reps
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            return float(np.mean(ts))
+
+        with torch.no_grad():
+            h0 = model._leaf(resident[0], perm32=model._perm32()[0], layout="drbc")
+            w1 = model._inner_layers[1].weight_param.detach()
+            wimg, logz = ops.tc_prepare(w1, True)
+            out1 = ops.tc_sum_forward(h0, wimg, w1, logz)
+            g1 = torch.randn_like(out1) / B
+            t_fwd = time_alone(lambda: ops.tc_sum_forward(h0, wimg, w1, logz))
+            t_bx = time_alone(lambda: ops.tc_sum_backward_x(h0, out1, g1, wimg, w1))
+            t_bw = time_alone(lambda: ops.tc_sum_backward_w(h0, out1, g1, w1, logz))
+            t_prep = time_alone(lambda: ops.tc_prepare(w1, True))
         _, per_layer = contraction_flops_fwd(B)
-        achieved = per_layer[0] / (k_ms / 1e3) / 1e12
+        fl = per_layer[0]
         peak = peaks.get("bf16_tflops", 1590.0)
-        roof = {"bound": "tensor", "kernel": "sum_fwd_kernel<xprod> (layer S_1: d=16, K=1600, N=40, R=40)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                "kernel_ms": k_ms, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)"
-                if peaks else "fallback 1590 (B200_PROFILING.md)"}
+        src = "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1590 (B200_PROFILING.md)"
+        kernels = {}
+        for name, t in (("sum_tc_fwd_kernel", t_fwd), ("sum_tc_bwd_x_kernel", t_bx), ("sum_tc_bwd_w_kernel", t_bw)):
+            ach = fl / (t / 1e3) / 1e12
+            kernels[name] = {"layer": "S_1 (d=16, K=1600, N=40, R=40)", "ms": t, "flops": fl, "achieved_tflops": ach,
+                             "frac": ach / peak, "traffic": ncu.get(name)}
+        kernels["tc_prepare (logz + operand image)"] = {"ms": t_prep}
+        dom = max(("sum_tc_fwd_kernel", "sum_tc_bwd_x_kernel", "sum_tc_bwd_w_kernel"), key=lambda k: kernels[k]["ms"])
+        roof = {"bound": "tensor", "kernel": f"{dom}<40,40,48> layer S_1 (d=16, K=1600, N=40, R=40), "
+                                             f"2*N*d*c^2*S*R = {fl:.3e} flop per launch",
+                "achieved": kernels[dom]["achieved_tflops"], "peak": peak, "unit": "TFLOP/s",
+                "frac": kernels[dom]["frac"], "traffic": ncu.get(dom), "kernel_ms": kernels[dom]["ms"],
+                "peak_source": src}
 
     if rank == 0:
         cb = None
         if not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
-            cb = cpu_baseline(micro=8, iters=1)
+            cb = cpu_baseline(micro=8, iters=5)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -286,7 +318,7 @@ def main():
                 "clocks": clk.summary(),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * CFG["F"] * 4,
                         "d2h_bytes_per_step": 4},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb, "loss": loss_host}
+                "gpu_launches": launches, "roofline": roof, "tc_kernels": kernels, "cpu_baseline": cb, "loss": loss_host}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

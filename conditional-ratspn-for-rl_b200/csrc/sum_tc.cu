@@ -23,6 +23,10 @@
 using namespace tc;
 
 __device__ int g_tc_aborts = 0;
+// SPN_TC_DEBUG=9: clock64 deltas per phase, accumulated by one thread per warpgroup of CTA 0 (spn_debug_tc_prof)
+__device__ unsigned long long g_tc_prof[16];
+#define TC_PROF_T(var) long long var = prof ? clock64() : 0
+#define TC_PROF_ADD(slot, t0, t1) do { if (prof) atomicAdd(&g_tc_prof[slot], (unsigned long long)((t1) - (t0))); } while (0)
 
 struct TcFwdArgs {
     const float* x;        // [d_in][R][B][C]
@@ -156,7 +160,9 @@ __global__ void __launch_bounds__(320, 1) sum_tc_fwd_kernel(TcFwdArgs a) {
             const int row = threadIdx.x & 127;
             const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
             bool ok = true;
+            const bool prof = a.debug == 9 && blockIdx.x == 0 && row == 0;
             for (int tile = tile_begin + wg; tile < tile_end && ok; tile += 2) {
+                TC_PROF_T(t_start);
                 const int64_t b = (int64_t)tile * 128 + row;
                 const bool valid = b < a.B;
                 const bool has_l = 2 * s < a.d_in, has_r = 2 * s + 1 < a.d_in;
@@ -186,6 +192,8 @@ __global__ void __launch_bounds__(320, 1) sum_tc_fwd_kernel(TcFwdArgs a) {
                     float m = vl[0], m2 = vr[0];
 #pragma unroll
                     for (int q = 1; q < C; ++q) { m = fmaxf(m, vl[q]); m2 = fmaxf(m2, vr[q]); }
+                    TC_PROF_T(t_loaded);
+                    TC_PROF_ADD(0, t_start, t_loaded);
                     mL = (m == -CUDART_INF_F) ? 0.f : m;
                     mR = (m2 == -CUDART_INF_F) ? 0.f : m2;
 #pragma unroll
@@ -194,12 +202,17 @@ __global__ void __launch_bounds__(320, 1) sum_tc_fwd_kernel(TcFwdArgs a) {
                         eR[q] = pack_bf16(__expf(vr[2 * q] - mR), __expf(vr[2 * q + 1] - mR));
                     }
                 }
+                TC_PROF_T(t_exp);
+                TC_PROF_ADD(1, t_start, t_exp);
 #pragma unroll
                 for (int step = 0; step < STEPS; ++step) {
                     const uint32_t st = g_stage % NST, par = (g_stage / NST) & 1;
+                    TC_PROF_T(t_w0);
                     ok = ok && mbar_wait(bar_empty + wg * NST + st, par ^ 1, abort_flag);
                     if (!ok) break;
                     fence_after_sync();
+                    TC_PROF_T(t_w1);
+                    TC_PROF_ADD(2, t_w0, t_w1);
                     const uint32_t stage_addr = tmem_base + lane_base + A_BASE + (wg * NST + st) * A_COLS;
 #pragma unroll
                     for (int h = 0; h < LPS / 2; ++h) {
@@ -214,17 +227,24 @@ __global__ void __launch_bounds__(320, 1) sum_tc_fwd_kernel(TcFwdArgs a) {
                         }
                         if (a.debug != 2) tmem_store_cols<C>(stage_addr + h * C, p);
                     }
+                    TC_PROF_T(t_g);
+                    TC_PROF_ADD(3, t_w1, t_g);
                     tmem_wait_st();
                     fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_full + wg * NST + st);
+                    TC_PROF_T(t_s);
+                    TC_PROF_ADD(4, t_g, t_s);
                     ++g_stage;
                 }
                 if (!ok) break;
+                TC_PROF_T(t_a0);
                 ok = mbar_wait(bar_acc + wg, g_tile & 1, abort_flag);
                 ++g_tile;
                 if (!ok) break;
                 fence_after_sync();
+                TC_PROF_T(t_a1);
+                TC_PROF_ADD(5, t_a0, t_a1);
                 uint32_t acc[NPAD];
 #pragma unroll
                 for (int q = 0; q < NPAD / 16; ++q) tmem_ld16(tmem_base + lane_base + wg * ACC_COLS + q * 16, acc + q * 16);
@@ -250,6 +270,10 @@ __global__ void __launch_bounds__(320, 1) sum_tc_fwd_kernel(TcFwdArgs a) {
                         *reinterpret_cast<float4*>(op + o4) = make_float4(res[0], res[1], res[2], res[3]);
                     }
                 }
+                TC_PROF_T(t_end);
+                TC_PROF_ADD(6, t_a1, t_end);
+                TC_PROF_ADD(7, t_start, t_end);
+                if (prof) atomicAdd(&g_tc_prof[8], 1ull);
             }
         }
     }
@@ -396,6 +420,19 @@ extern "C" int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw,
     if (c == 32) return launch_tc_fwd<32, 32, 32, 2, 4>(a, st);
     if (c == 16) return launch_tc_fwd<16, 16, 16, 2, 4>(a, st);
     return SPN_ERR_UNSUPPORTED;
+}
+
+extern "C" int spn_debug_tc_prof(unsigned long long* out_host, int reset) {
+    unsigned long long v[16] = {0};
+    cudaError_t e = cudaMemcpyFromSymbol(v, g_tc_prof, sizeof(v));
+    if (e != cudaSuccess) return spn_cuda_status(e);
+    if (out_host) for (int i = 0; i < 16; ++i) out_host[i] = v[i];
+    if (reset) {
+        unsigned long long z[16] = {0};
+        e = cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z));
+        if (e != cudaSuccess) return spn_cuda_status(e);
+    }
+    return SPN_OK;
 }
 
 // debug: number of CTAs that hit the bounded-wait timeout since the library was loaded (synchronises)

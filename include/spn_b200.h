@@ -204,6 +204,9 @@ int spn_root_shared_bwd(const float* x, int d_in, const float* lw, const float* 
 
 /* Debug aid (synchronises): number of CTAs that gave up on an mbarrier wait since the library was loaded. */
 int spn_debug_tc_aborts(int* out_host);
+/* Debug aid (synchronises): with SPN_TC_DEBUG=9 in the environment one thread per warpgroup of CTA 0 accumulates clock64
+ * deltas per pipeline phase of spn_sum_tc_fwd; copies the 16 counters to out_host (host pointer) and optionally resets. */
+int spn_debug_tc_prof(unsigned long long* out_host, int reset);
 
 #ifdef __cplusplus
 }

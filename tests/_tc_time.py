@@ -23,3 +23,13 @@ if which in ("all", "bwdx"): timeit("tc bwd_x S_1", lambda: ops.tc_sum_backward_
 if which in ("all", "bwdw"): timeit("tc bwd_w S_1", lambda: ops.tc_sum_backward_w(x, out, go, lw), fl)
 if which in ("all",): timeit("prepare", lambda: ops.tc_prepare(lw))
 print("aborts", ops.tc_aborts())
+import os, ctypes
+if os.environ.get("SPN_TC_DEBUG") == "9":
+    from ratspn_b200 import _abi
+    buf = (ctypes.c_ulonglong * 16)()
+    _abi.lib().spn_debug_tc_prof(buf, 1)
+    ops.tc_sum_forward(x, wimg, lw); torch.cuda.synchronize()
+    _abi.lib().spn_debug_tc_prof(buf, 0)
+    n = max(1, buf[8])
+    names = ["load", "load+exp", "wait_empty", "gen+st", "wait_st+arrive", "wait_acc", "epilogue", "tile_total"]
+    print("tiles", buf[8], " ".join(f"{names[i]}={buf[i]/n:.0f}" for i in range(8)))

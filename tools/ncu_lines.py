@@ -1,6 +1,6 @@
 """Per-source-line hot spots of one kernel from an .ncu-rep (ncu --page source --csv): samples, executed instructions,
 shared-memory excess wavefronts and the dominant stall reasons.  Usage: ncu_lines.py REP KERNEL_REGEX [TOP]"""
-import csv, subprocess, sys, io
+import csv, subprocess, sys, io, os
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kern}", "--print-source", "cuda,sass"],
@@ -39,7 +39,7 @@ agg = {}
 for s in stalls:
     agg[s] = sum(val(r, s) for r in lines)
 print("stalls:", ", ".join(f"{k[6:]} {100*v/tot_s:.0f}%" for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:8]))
-lines.sort(key=lambda r: -val(r, "# Samples"))
+lines.sort(key=lambda r: -val(r, "Instructions Executed" if os.environ.get("BY_INST") else "# Samples"))
 for r in lines[:top]:
     st = sorted(((val(r, s), s[6:]) for s in stalls), reverse=True)[:2]
     print(f"{r[0]:>4} smp {100*val(r,'# Samples')/tot_s:5.1f}% inst {100*val(r,'Instructions Executed')/tot_i:5.1f}% "
