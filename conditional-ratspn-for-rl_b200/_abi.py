@@ -43,6 +43,7 @@ SIGNATURES = {
     "spn_sample_sum": [_P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _I, _P, _P, _L, _L, _L, _L,
                        _I, _I, _I, _I, _I, _P, _I, _U, _U, _P, _P],
     "spn_sum_tc_supported": [_I, _I, _I],
+    "spn_sum_tc_image_bytes": [_I, _I, _I, _I],
     "spn_sum_tc_prepare": [_P, _I, _I, _I, _I, _P, _P, _P],
     "spn_sum_tc_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "spn_sum_tc_bwd_x": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
@@ -56,7 +57,7 @@ SIGNATURES = {
                         _I, _I, _P, _P, _P],
 }
 
-_RETURNS_INT64 = {"spn_leaf_workspace_floats"}
+_RETURNS_INT64 = {"spn_leaf_workspace_floats", "spn_sum_tc_image_bytes"}
 
 _lib = None
 LAUNCHES = 0  # number of kernel-launching ABI calls made by this process (bench.py reports it)

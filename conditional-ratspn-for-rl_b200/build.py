@@ -28,7 +28,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
+    extra = ["-DSPN_TC_PROFILE"] if os.environ.get("SPN_TC_PROFILE") else []  # per-phase clock64 hooks (perturbs timing)
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         print(res.stderr)

@@ -1,0 +1,756 @@
+// Shared-weight (RatSpn) CrossProduct+Sum on the 5th-generation tensor cores (tcgen05 + TMEM): forward and dX.
+//
+// For one sum scope s and repetition r the layer is a dense contraction over K = c*c in-channels:
+//   forward   out[b,o]  = mL + mR + log sum_{l,r'} eL[b,l] eR[b,r'] W[(l,r'),o]          eL = exp(xL - mL), eR = exp(xR - mR)
+//   dX right  dxR[b,r'] = eR[b,r'] * sum_{l,o}  eL[b,l] G[b,o] W[(l,r'),o]                G  = g * exp(mL + mR - out)
+//   dX left   dxL[b,l]  = eL[b,l]  * sum_{r',o} eR[b,r'] G[b,o] W[(l,r'),o]
+// All three are the SAME shape of GEMM: [128 rows x K = nu*nv] x [K x N <= 48], whose A operand is an outer product
+// A[b, u*C + v] = U[b,u] * V[b,v] of two per-row vectors that never exists in memory:
+//   mode FWD: U = eL, V = eR, N = o;   mode DXR: U = eL, V = G, N = r';   mode DXL: U = eR, V = G, N = l.
+// Mapping to the hardware:
+//   * A operand: produced by CUDA cores straight into TENSOR MEMORY (tcgen05.st), one bf16x2 multiply per two K-elements
+//     (an smem-staged A would need 170 B/clk/SM of shared-memory writes, more than an SM has); stages of 2*C K-values,
+//     NST-deep ring per warpgroup; the TMEM store of stage i is overlapped with the multiplies of stage i + 1.
+//   * B operand: the bf16 weight image [K/8][C/8][8][8] of W(s, r) (pitch C, no padding) copied once per work item by the
+//     TMA engine (cp.async.bulk).  FWD reads it as an MN-major operand (K = (l,r'), N = o).  DXR reads THE SAME bytes as
+//     a K-major operand with N = r' and K = (l, o): every 8x8 core matrix of the image is one (l, 8 r', 8 o) block, so
+//     only the descriptor strides change.  DXL needs the pair-transposed image W2[(r',l),o] (a 16-byte-chunk permutation
+//     written by spn_sum_tc_prepare).  N = 48 > C = 40: the sixth N-group aliases the following block; the accumulator
+//     columns it produces are never read.
+//   * accumulator: fp32 in TMEM (48 columns), read back with tcgen05.ld; branch-free epilogue.
+//   * roles: two producer/epilogue warpgroups (one row tile each, ping-pong) + one MMA-issuing warp per warpgroup.
+// Activations use the internal layout [scope][repetition][batch][channel] (one thread <-> one contiguous row).
+// Outputs whose linear-domain sum underflows are recomputed exactly in fp32, so results keep th.logsumexp semantics.
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+using namespace tc;
+
+__device__ int g_tc2_aborts = 0;
+__device__ unsigned long long g_tc2_prof[24];
+// Per-phase clock hooks (build with SPN_TC_PROFILE=1).  Every lane reads the clock and accumulates into registers; the
+// totals are flushed once at the end of the kernel, so the hooks add no branches to the pipeline loops (a divergent
+// `if (lane == 0)` inside the MMA issue loop costs the uniform-register code path).
+#ifdef SPN_TC_PROFILE
+#define TC2_DECL long long tc2_acc[6] = {0, 0, 0, 0, 0, 0}
+#define TC2_T(var) const long long var = clock64()
+#define TC2_ADD(slot, t0, t1) tc2_acc[(slot) % 6] += (t1) - (t0)
+#define TC2_COUNT(slot) tc2_acc[(slot) % 6] += 1
+#define TC2_FLUSH(base)                                                                                          \
+    do {                                                                                                         \
+        if (blockIdx.x == 0 && lane == 0)                                                                        \
+            for (int q = 0; q < 6; ++q) atomicAdd(&g_tc2_prof[(base) + q], (unsigned long long)tc2_acc[q]);      \
+    } while (0)
+#else
+#define TC2_DECL do { } while (0)
+#define TC2_T(var) do { } while (0)
+#define TC2_ADD(slot, t0, t1) do { } while (0)
+#define TC2_COUNT(slot) do { } while (0)
+#define TC2_FLUSH(base) do { } while (0)
+#endif
+
+enum { OPG_FWD = 0, OPG_DXR = 1, OPG_DXL = 2 };
+
+struct OpgArgs {
+    const float* x;        // [d_in][R][B][C]
+    const uint8_t* wimg;   // [2][d_out][R][K*C] bf16: image, then pair-transposed image
+    const float* lw;       // fp32 weights [1][d_out][K][OC][R] (exact rescue path, FWD)
+    const float* logz;     // NULL or [d_out][OC][R]
+    const float* out;      // [d_out][R][B][OC]  (DX: forward output)
+    const float* g;        // [d_out][R][B][OC]  (DX: upstream gradient)
+    float* y;              // FWD: out;  DX: dx [d_in][R][B][C]
+    int B, d_in, d_out, R;
+    int ntiles, nsplit, debug, dbg_n;
+};
+
+// exact fp32 log-sum-exp for one output (rare rescue path)
+template <int C, int NOUT>
+__device__ __noinline__ void opg_exact_row(const OpgArgs& a, int s, int r, int64_t b, int o_begin, float* op) {
+    const bool has_l = 2 * s < a.d_in, has_r = 2 * s + 1 < a.d_in;
+    const float* xl = a.x + (((int64_t)(2 * s) * a.R + r) * a.B + b) * C;
+    const float* xr = a.x + (((int64_t)(2 * s + 1) * a.R + r) * a.B + b) * C;
+    for (int oo = 0; oo < NOUT; ++oo) {
+        const int o = o_begin + oo;
+        const float* lwp = a.lw + ((int64_t)s * C * C * C + o) * a.R + r;
+        const int64_t sw_i = (int64_t)C * a.R;
+        float m = -CUDART_INF_F;
+        for (int l = 0; l < C; ++l)
+            for (int rp = 0; rp < C; ++rp)
+                m = fmaxf(m, (has_l ? xl[l] : 0.f) + (has_r ? xr[rp] : 0.f) + lwp[(int64_t)(l * C + rp) * sw_i]);
+        float res = m;
+        if (m != -CUDART_INF_F) {
+            float acc = 0.f;
+            for (int l = 0; l < C; ++l)
+                for (int rp = 0; rp < C; ++rp)
+                    acc += expf((has_l ? xl[l] : 0.f) + (has_r ? xr[rp] : 0.f) + lwp[(int64_t)(l * C + rp) * sw_i] - m);
+            res = m + logf(acc);
+            if (a.logz) res -= a.logz[((int64_t)s * C + o) * a.R + r];
+        }
+        op[oo] = res;
+    }
+}
+
+// ---- MMA issue: one PTX block per stage (one elect, descriptor arithmetic on block-local registers) --------------------
+// Descriptor of MMA kk of a stage = base descriptor of the stage + a compile-time constant:
+//   FWD  (B MN-major, K groups NVG*128 B apart): start advances by two K groups per MMA.
+//   DX   (B K-major over the flattened (u, o-group) index g = g0 + 2kk, g0 a multiple of 4*NVG): the start block is
+//        ((g / NVG) * NVG*NVG + g % NVG) and the leading-byte-offset field is the distance to the block of g + 1.
+template <int C, int MODE>
+__host__ __device__ constexpr long long opg_desc_delta(int kk) {
+    constexpr int NVG = C / 8;
+    if (MODE == OPG_FWD) return (long long)kk * 2 * NVG * 8;  // units of 16 bytes
+    const int ga = 2 * kk, gb = ga + 1;
+    const int ua = ga / NVG, oa = ga % NVG, ub = gb / NVG, ob = gb % NVG;
+    const long long start = (long long)(ua * NVG * NVG + oa) * 8;
+    const long long lbo = (long long)((ub - ua) * NVG * NVG + (ob - oa)) * 8;
+    return start + (lbo << 16);
+}
+
+#define OPG_MMA_LINE(IMM, AOFF)                                                                                   \
+    "add.s64 d, %1, " IMM ";\n\tadd.s32 ta, %0, " #AOFF ";\n\t"                                                     \
+    "@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+
+// Issues the C/4 MMAs of one stage: D[acc] (+)= A[tmem abase + 8 kk] * B[dbase + delta(kk)].
+template <int C, int MODE>
+__device__ __forceinline__ void opg_issue_stage(uint32_t acc, uint32_t abase, uint64_t dbase, uint32_t idesc, uint32_t accumulate_first) {
+    constexpr int MMAS = C / 4;
+    static_assert(MMAS == 10 || MMAS == 8 || MMAS == 4, "unsupported channel count");
+#define OPG_D(i) "n"(opg_desc_delta<C, MODE>(i))
+    if constexpr (MMAS == 10) {
+        asm volatile(
+            "{\n\t.reg .pred q, p;\n\t.reg .b64 d;\n\t.reg .b32 ta;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            OPG_MMA_LINE("%6", 0) OPG_MMA_LINE("%7", 8) OPG_MMA_LINE("%8", 16) OPG_MMA_LINE("%9", 24) OPG_MMA_LINE("%10", 32)
+            OPG_MMA_LINE("%11", 40) OPG_MMA_LINE("%12", 48) OPG_MMA_LINE("%13", 56) OPG_MMA_LINE("%14", 64) OPG_MMA_LINE("%15", 72)
+            "}" ::"r"(abase), "l"(dbase), "r"(idesc), "r"(0u), "r"(accumulate_first), "r"(acc),
+            OPG_D(0), OPG_D(1), OPG_D(2), OPG_D(3), OPG_D(4), OPG_D(5), OPG_D(6), OPG_D(7), OPG_D(8), OPG_D(9)
+            : "memory");
+    } else if constexpr (MMAS == 8) {
+        asm volatile(
+            "{\n\t.reg .pred q, p;\n\t.reg .b64 d;\n\t.reg .b32 ta;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            OPG_MMA_LINE("%6", 0) OPG_MMA_LINE("%7", 8) OPG_MMA_LINE("%8", 16) OPG_MMA_LINE("%9", 24) OPG_MMA_LINE("%10", 32)
+            OPG_MMA_LINE("%11", 40) OPG_MMA_LINE("%12", 48) OPG_MMA_LINE("%13", 56)
+            "}" ::"r"(abase), "l"(dbase), "r"(idesc), "r"(0u), "r"(accumulate_first), "r"(acc),
+            OPG_D(0), OPG_D(1), OPG_D(2), OPG_D(3), OPG_D(4), OPG_D(5), OPG_D(6), OPG_D(7)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred q, p;\n\t.reg .b64 d;\n\t.reg .b32 ta;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            OPG_MMA_LINE("%6", 0) OPG_MMA_LINE("%7", 8) OPG_MMA_LINE("%8", 16) OPG_MMA_LINE("%9", 24)
+            "}" ::"r"(abase), "l"(dbase), "r"(idesc), "r"(0u), "r"(accumulate_first), "r"(acc),
+            OPG_D(0), OPG_D(1), OPG_D(2), OPG_D(3)
+            : "memory");
+    }
+#undef OPG_D
+}
+
+template <int C>
+__device__ __forceinline__ void load_row(const float* p, bool on, float* v) {
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q) {
+        const float4 t = on ? __ldg(reinterpret_cast<const float4*>(p) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+}
+
+// max-shifted exp of one row, packed to bf16 pairs; returns the shift (0 for an all -inf row)
+template <int C>
+__device__ __forceinline__ float exp_pack(const float* v, uint32_t* e) {
+    float m = v[0];
+#pragma unroll
+    for (int q = 1; q < C; ++q) m = fmaxf(m, v[q]);
+    m = (m == -CUDART_INF_F) ? 0.f : m;
+    const float ms = m * 1.4426950408889634f;
+#pragma unroll
+    for (int q = 0; q < C / 2; ++q)
+        e[q] = pack_bf16(ex2_approx(fmaf(v[2 * q], 1.4426950408889634f, -ms)), ex2_approx(fmaf(v[2 * q + 1], 1.4426950408889634f, -ms)));
+    return m;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Thread organisation: 17 warps, specialised so that the resources of the pipeline run concurrently:
+//   warps 0-7   GENERATORS: the fp16 pipe.  Warp w serves TMEM lane quadrant w % 4 (32 rows); the two warps of a quadrant
+//               take alternate stages of the 4-deep A ring (bf16x2 multiplies -> tcgen05.st), so one multiplies while the
+//               other waits for its TMEM stores / stage slot.
+//   warps 8-15  LOADERS / EPILOGUE: LSU + MUFU.  Two threads per row (same lane, warps w and w + 4): "half" 0 / 1 owns the
+//               left / right child row and half of the outputs.  They run the prologue of tile t + 1 (max, exp, pack ->
+//               shared memory; the global loads were issued one tile earlier) and the epilogue of tile t - 1 (tcgen05.ld,
+//               log / scale, row stores) while tile t is being generated.
+//   warp 16     MMA issuer (also streams the weight image with the TMA engine).
+// Row vectors and accumulators are double buffered, A stages quadruple buffered; all hand-offs are mbarriers (producer
+// arrive = release, consumer try_wait = acquire).
+template <int C, int MODE>
+__global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
+    constexpr int NPAD = (C + 15) / 16 * 16;
+    constexpr int NVG = C / 8;                 // 8-element groups per vector
+    constexpr int K = C * C;
+    constexpr int W_BYTES = K * C * 2;         // image pitch = C columns
+    constexpr int NPAIR = C / 2;               // packed bf16 registers per vector
+    constexpr int STEPS = NPAIR / 2;           // stages per tile: two packed U registers (four u's, 4*C k-values) each
+    constexpr int MMAS = C / 4;                // K = 16 instructions per stage
+    constexpr int NST = 4;                     // A stage ring depth
+    constexpr int ACC_COLS = 64;
+    constexpr int A_COLS = 2 * C;              // 4*C bf16 = 2*C 32-bit columns per stage
+    constexpr int A_BASE = 2 * ACC_COLS;
+    constexpr int HC = C / 2;                  // outputs per loader half
+    static_assert(C % 8 == 0 && C <= 48 && NPAIR % 2 == 0 && A_BASE + NST * A_COLS <= 512, "unsupported shape");
+    constexpr uint32_t IDESC = instr_desc_bf16(128, NPAD, 0, MODE == OPG_FWD ? 1 : 0);
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* wsm = smem;                                                       // W_BYTES + 1024 (aliased N-group overrun)
+    uint32_t* Us = reinterpret_cast<uint32_t*>(smem + W_BYTES + 1024);         // [2 buf][NPAIR][128]  U vector (packed bf16)
+    uint32_t* Vs = Us + 2 * NPAIR * 128;                                       // [2 buf][NPAIR][128]  V vector
+    uint32_t* Es = Vs + 2 * NPAIR * 128;                                       // [2 buf][NPAIR][128]  DX: epilogue scale vector
+    float* Ms = reinterpret_cast<float*>(Es + 2 * NPAIR * 128);                // [2 buf][2][128]      row shifts mL, mR
+    uint64_t* st_full = reinterpret_cast<uint64_t*>(Ms + 2 * 2 * 128);         // [NST]  generators -> MMA
+    uint64_t* st_empty = st_full + NST;                                        // [NST]  MMA commit -> generators
+    uint64_t* vec_full = st_empty + NST;                                       // [2]    loaders -> generators
+    uint64_t* vec_empty = vec_full + 2;                                        // [2]    generators -> loaders
+    uint64_t* acc_full = vec_empty + 2;                                        // [2]    MMA commit -> epilogue
+    uint64_t* acc_empty = acc_full + 2;                                        // [2]    epilogue -> MMA
+    uint64_t* bar_w = acc_empty + 2;                                           // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 1);
+    volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+    // warp index through a shuffle: the idiom that tells the compiler the value (and every branch on it) is warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NST; ++i) {
+            mbar_init(st_full + i, 4);   // the four quadrant warps that produce this stage
+            mbar_init(st_empty + i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(vec_full + i, 8);
+            mbar_init(vec_empty + i, 8);
+            mbar_init(acc_full + i, 1);
+            mbar_init(acc_empty + i, 8);
+        }
+        mbar_init(bar_w, 1);
+        *abort_flag = 0;
+        mbar_fence_init();
+    }
+    if (warp == 16) tmem_alloc(tmem_slot, 512);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    // The whole TMEM (512 columns) of this SM is ours, so the allocation starts at lane 0 / column 0.
+    if (threadIdx.x == 0 && *tmem_slot != 0) *abort_flag = 1;
+    constexpr uint32_t tmem_base = 0;
+    __syncthreads();
+
+    const int nitems = a.d_out * a.R * a.nsplit;
+    const int tiles_per_split = (a.ntiles + a.nsplit - 1) / a.nsplit;
+    uint32_t n_stage = 0, n_tile = 0, n_epi = 0, items_done = 0;   // per-role ring positions (persist across items)
+    uint32_t m_stage = 0, m_tile = 0;                               // the MMA warp's own counters (kept warp-uniform)
+    TC2_DECL;
+
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++items_done) {
+        const int split = item % a.nsplit;
+        const int sr = item / a.nsplit;
+        const int r = sr % a.R, s = sr / a.R;
+        const int tile_begin = split * tiles_per_split;
+        const int tile_end = min(a.ntiles, tile_begin + tiles_per_split);
+        const bool has_l = 2 * s < a.d_in, has_r = 2 * s + 1 < a.d_in;
+        __syncthreads();  // the previous item is finished by every role (its last epilogue waited for its last MMA)
+        if (__shfl_sync(0xffffffffu, *abort_flag, 0)) break;
+        if (warp == 16) {
+            // =============================================== MMA issuer ===============================================
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar_w, W_BYTES);
+                const uint8_t* src = a.wimg + ((size_t)(MODE == OPG_DXL ? 1 : 0) * a.d_out * a.R + sr) * W_BYTES;
+                constexpr int CH = 16000;
+                for (int off = 0; off < W_BYTES; off += CH) bulk_g2s(wsm + off, src + off, min(CH, W_BYTES - off), bar_w);
+            }
+            __syncwarp();
+            TC2_T(t_mw0);
+            mbar_wait_sticky(bar_w, items_done & 1, abort_flag);
+            fence_after_sync();
+            TC2_T(t_mw1);
+            TC2_ADD(3, t_mw0, t_mw1);
+            const uint32_t wsm_addr = smem_u32(wsm);
+            // The tensor pipe queues only a few MMAs, so the issue of a stage returns when that stage is nearly finished; a
+            // blocking wait (~90 clk) for the next stage in between would leave the pipe idle.  The next hand-off is therefore
+            // PROBED before the current stage is issued (the probe's latency hides behind the issue); the blocking wait is
+            // only the fall-back when the generators are not ahead.
+            bool acc_ready = false, st_ready = false;
+            for (int tile = tile_begin; tile < tile_end; ++tile, ++m_tile) {
+                const uint32_t ab = m_tile & 1;
+                TC2_T(t_m0);
+                if (!acc_ready) mbar_wait_sticky(acc_empty + ab, ((m_tile >> 1) & 1) ^ 1, abort_flag);  // epilogue of tile n - 2 has read it
+                fence_after_sync();
+                TC2_T(t_m1);
+                TC2_ADD(0, t_m0, t_m1);
+                const uint32_t acc = tmem_base + ab * ACC_COLS;
+#pragma unroll 1
+                for (int step = 0; step < STEPS; ++step, ++m_stage) {
+                    const uint32_t st = m_stage % NST, par = (m_stage / NST) & 1;
+                    TC2_T(t_m2);
+                    if (!st_ready) mbar_wait_sticky(st_full + st, par, abort_flag);
+                    fence_after_sync();
+                    TC2_T(t_m3);
+                    TC2_ADD(1, t_m2, t_m3);
+                    {   // probe the hand-offs needed right after this stage
+                        const uint32_t nx = m_stage + 1;
+                        st_ready = mbar_probe_uniform(st_full + nx % NST, (nx / NST) & 1);
+                        if (step == STEPS - 1) acc_ready = mbar_probe_uniform(acc_empty + (ab ^ 1), (((m_tile + 1) >> 1) & 1) ^ 1);
+                    }
+                    const uint32_t abase = tmem_base + A_BASE + st * A_COLS;
+                    if (a.debug != 1 && a.debug != 8) {
+                        // base descriptor of the stage (see opg_desc_delta): FWD advances 4*NVG K groups of NVG*128 bytes per
+                        // stage; DX advances four u's = 4*NVG*NVG blocks of 128 bytes
+                        const uint32_t sbytes = (uint32_t)step * (4 * NVG * NVG * 128);
+                        const uint64_t dbase = MODE == OPG_FWD ? smem_desc(wsm_addr + sbytes, NVG * 128, 128) : smem_desc(wsm_addr + sbytes, 0, NVG * 128);
+                        opg_issue_stage<C, MODE>(acc, abase, dbase, a.dbg_n ? instr_desc_bf16(128, a.dbg_n, 0, MODE == OPG_FWD ? 1 : 0) : IDESC,
+                                                 step ? 1u : 0u);
+                    }
+                    mma_commit_uniform(st_empty + st);
+                    if (step == STEPS - 1) mma_commit_uniform(acc_full + ab);
+                    TC2_T(t_m4);
+                    TC2_ADD(2, t_m3, t_m4);
+                }
+                TC2_COUNT(5);
+            }
+            // the probes must not leak into the next item: its barriers are waited for from scratch
+            (void)acc_ready; (void)st_ready;
+        } else if (warp < 8) {
+            // =============================================== generators ===============================================
+            const uint32_t gsel = warp >> 2;          // this warp produces the stages with n_stage % 2 == gsel
+            const int row = (warp & 3) * 32 + lane;
+            const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+            for (int tile = tile_begin; tile < tile_end; ++tile, ++n_tile) {
+                TC2_T(t_start);
+                const uint32_t vb = n_tile & 1;
+                mbar_wait_sticky(vec_full + vb, (n_tile >> 1) & 1, abort_flag);
+                const uint32_t* my_u = Us + vb * NPAIR * 128 + row;
+                const uint32_t* my_v = Vs + vb * NPAIR * 128 + row;
+                uint32_t V[NPAIR];
+#pragma unroll
+                for (int q = 0; q < NPAIR; ++q) V[q] = my_v[q * 128];
+                TC2_T(t_v);
+                TC2_ADD(0, t_start, t_v);
+                // our stages of this tile; the first half of a stage is multiplied before its slot is known to be free and
+                // while the previous stage's TMEM stores are still in flight.  The packed U registers of the stage (and of the
+                // next one) are fetched from shared memory BEFORE the TMEM stores are issued: both go through the MIO queue,
+                // and a load queued behind 5 KB of tcgen05.st data would stall the multiplies that depend on it.
+                int i = (int)((gsel - n_stage) & 1);
+                uint32_t p[C];
+                uint32_t e0 = 0, e1 = 0, e0n = 0;
+                if (i < STEPS) {
+                    e0 = my_u[(2 * i) * 128];
+                    e1 = my_u[(2 * i + 1) * 128];
+                    if ((a.debug != 3 && a.debug < 7 || a.debug == 9)) {
+                        const uint32_t u0 = bcast_lo(e0), u1 = bcast_hi(e0);
+#pragma unroll
+                        for (int q = 0; q < NPAIR; ++q) { p[q] = hmul2_bf16(u0, V[q]); p[NPAIR + q] = hmul2_bf16(u1, V[q]); }
+                    }
+                }
+                for (; i < STEPS; i += 2) {
+                    const uint32_t ns = n_stage + i;
+                    const uint32_t st = ns % NST, use = ns / NST;
+                    const uint32_t cols = tmem_base + lane_base + A_BASE + st * A_COLS;
+                    const bool more = i + 2 < STEPS;
+                    if (more) e0n = my_u[(2 * (i + 2)) * 128];
+                    TC2_T(t_w0);
+                    mbar_wait_sticky(st_empty + st, (use & 1) ^ 1, abort_flag);
+                    fence_after_sync();
+                    TC2_T(t_w1);
+                    TC2_ADD(1, t_w0, t_w1);
+                    if (a.debug != 2 && (a.debug != 3 && a.debug < 7 || a.debug == 9)) tmem_store_cols<C>(cols, p);
+                    if ((a.debug != 3 && a.debug < 7 || a.debug == 9)) {
+                        const uint32_t u0 = bcast_lo(e1), u1 = bcast_hi(e1);
+#pragma unroll
+                        for (int q = 0; q < NPAIR; ++q) { p[q] = hmul2_bf16(u0, V[q]); p[NPAIR + q] = hmul2_bf16(u1, V[q]); }
+                    }
+                    if (more) e1 = my_u[(2 * (i + 2) + 1) * 128];
+                    if (a.debug != 2 && (a.debug != 3 && a.debug < 7 || a.debug == 9)) tmem_store_cols<C>(cols + C, p);
+                    if (more && (a.debug != 3 && a.debug < 7 || a.debug == 9)) {
+                        const uint32_t u0 = bcast_lo(e0n), u1 = bcast_hi(e0n);
+#pragma unroll
+                        for (int q = 0; q < NPAIR; ++q) { p[q] = hmul2_bf16(u0, V[q]); p[NPAIR + q] = hmul2_bf16(u1, V[q]); }
+                    }
+                    TC2_T(t_g);
+                    TC2_ADD(2, t_w1, t_g);
+                    tmem_wait_st();
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(st_full + st);
+                    TC2_T(t_s);
+                    TC2_ADD(3, t_g, t_s);
+                    TC2_COUNT(4);
+                }
+                n_stage += STEPS;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(vec_empty + vb);  // U / V of this tile are no longer read by this warp
+                TC2_COUNT(5);
+            }
+        } else {
+            // ========================================== loaders / epilogue ==========================================
+            const int lw_ = warp - 8;
+            const int half = lw_ >> 2;
+            const int row = (lw_ & 3) * 32 + lane;
+            const uint32_t lane_base = (uint32_t)((lw_ & 3) * 32) << 16;
+            const bool has_mine = half ? has_r : has_l;
+            const float* xbase = a.x + ((int64_t)(2 * s + half) * a.R + r) * a.B * C;
+            const int nt = tile_end - tile_begin;
+            float v[C];  // this thread's child row of the NEXT tile to be prepared (loaded one tile ahead)
+            {
+                const int64_t b = (int64_t)tile_begin * 128 + row;
+                load_row<C>(xbase + (b < a.B ? b : 0) * C, b < a.B && has_mine && nt > 0, v);
+            }
+            for (int i = 0; i <= nt; ++i) {
+                if (i < nt) {
+                    // ---------------- prologue of tile i: half 0 owns the left child row, half 1 the right child row
+                    TC2_T(t_p0);
+                    const int tile = tile_begin + i;
+                    const uint32_t vb = n_tile & 1;
+                    const int64_t b = (int64_t)tile * 128 + row;
+                    const bool valid = b < a.B;
+                    const int64_t bb = valid ? b : 0;
+                    uint32_t* my_u = Us + vb * NPAIR * 128 + row;
+                    uint32_t* my_v = Vs + vb * NPAIR * 128 + row;
+                    uint32_t* my_e = Es + vb * NPAIR * 128 + row;
+                    float* my_m = Ms + vb * 2 * 128 + row;
+                    uint32_t e[NPAIR];
+                    float m = 0.f;
+                    if ((a.debug != 4 && a.debug < 7 || a.debug == 9)) m = exp_pack<C>(v, e);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < NPAIR; ++j) e[j] = __float_as_uint(v[j]);
+                    }
+                    {   // issue the loads of the next tile now; they complete while this tile is finished and stored
+                        const int64_t bn = b + 128;
+                        load_row<C>(xbase + (bn < a.B ? bn : 0) * C, bn < a.B && has_mine && i + 1 < nt && (a.debug != 5 && a.debug < 7 || a.debug == 9), v);
+                        if (i + 2 < nt && b + 256 < a.B && has_mine) {
+                            const char* nx = reinterpret_cast<const char*>(xbase + (b + 256) * C);
+                            prefetch_l2(nx);
+                            prefetch_l2(nx + C * 4 - 4);
+                        }
+                    }
+                    mbar_wait_sticky(vec_empty + vb, ((n_tile >> 1) & 1) ^ 1, abort_flag);  // generators are done with tile n - 2
+                    // every loader thread has finished the epilogue that read this buffer (partner rows' shift / scale)
+                    named_bar_sync(1, 256);
+                    my_m[half * 128] = m;
+                    // FWD: U = eL, V = eR.  DXR: U = eL, scale = eR.  DXL: U = eR, scale = eL.
+                    uint32_t* dst = MODE == OPG_FWD ? (half ? my_v : my_u) : MODE == OPG_DXR ? (half ? my_e : my_u) : (half ? my_u : my_e);
+#pragma unroll
+                    for (int j = 0; j < NPAIR; ++j) dst[j * 128] = e[j];
+                    if (MODE != OPG_FWD) {
+                        // G = g * exp(shift - out) = g / (linear-domain sum); out = -inf (impossible row): no gradient.  The
+                        // exponent is capped so that rows whose sum underflowed in the forward (rescue path) stay finite.
+                        const float* op = a.out + (((int64_t)s * a.R + r) * a.B + bb) * C + half * HC;
+                        const float* gp = a.g + (((int64_t)s * a.R + r) * a.B + bb) * C + half * HC;
+                        float vo[HC], vg[HC];
+                        load_row<HC>(op, valid, vo);
+                        load_row<HC>(gp, valid, vg);
+                        named_bar_sync(2, 256);  // both shifts are in shared memory
+                        const float sh2 = (my_m[0] + my_m[128]) * 1.4426950408889634f;
+#pragma unroll
+                        for (int q = 0; q < HC / 2; ++q) {
+                            const float o0 = vo[2 * q], o1 = vo[2 * q + 1];
+                            const float g0v = o0 == -CUDART_INF_F ? 0.f : vg[2 * q] * ex2_approx(fminf(fmaf(o0, -1.4426950408889634f, sh2), 115.f));
+                            const float g1v = o1 == -CUDART_INF_F ? 0.f : vg[2 * q + 1] * ex2_approx(fminf(fmaf(o1, -1.4426950408889634f, sh2), 115.f));
+                            my_v[(half * (HC / 2) + q) * 128] = pack_bf16(g0v, g1v);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(vec_full + vb);
+                    ++n_tile;
+                    TC2_T(t_p1);
+                    TC2_ADD(0, t_p0, t_p1);
+                }
+                if (i >= 1) {
+                    // ---------------- epilogue of tile i - 1: this thread owns outputs [half*HC, half*HC + HC)
+                    TC2_T(t_e0);
+                    const int tile = tile_begin + i - 1;
+                    const uint32_t ab = n_epi & 1;
+                    const int64_t b = (int64_t)tile * 128 + row;
+                    const bool valid = b < a.B;
+                    const int64_t bb = valid ? b : 0;
+                    mbar_wait_sticky(acc_full + ab, (n_epi >> 1) & 1, abort_flag);
+                    fence_after_sync();
+                    TC2_T(t_e1);
+                    TC2_ADD(1, t_e0, t_e1);
+                    constexpr int LD0 = (HC / 8) * 8;          // first column block loaded by half 1 (multiple of 8 <= HC)
+                    constexpr int NLD = ((HC + 7) / 8) * 8 + (HC % 8 ? 8 : 0);   // columns loaded per thread (multiple of 8)
+                    constexpr int OFF1 = HC - LD0;             // position of half 1's first output inside its loaded columns
+                    uint32_t accv[NLD];
+                    {
+                        const uint32_t cbase = tmem_base + lane_base + ab * ACC_COLS + (half ? LD0 : 0);
+#pragma unroll
+                        for (int q = 0; q < NLD / 8; ++q) tmem_ld8(cbase + q * 8, accv + q * 8);
+                    }
+                    tmem_wait_ld();
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + ab);  // the accumulator may be overwritten by tile n + 2
+                    float av[HC];
+#pragma unroll
+                    for (int q = 0; q < HC; ++q) av[q] = __uint_as_float(half ? accv[q + OFF1] : accv[q]);
+                    const float* my_m = Ms + ab * 2 * 128 + row;
+                    if ((a.debug == 4 || a.debug == 7 || a.debug == 8)) {
+                    } else if (MODE == OPG_FWD) {
+                        const float shift = my_m[0] + my_m[128];
+                        float* op = a.y + (((int64_t)s * a.R + r) * a.B + bb) * C + half * HC;
+                        bool bad = false;
+#pragma unroll
+                        for (int o4 = 0; o4 < HC; o4 += 4) {
+                            float res[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float sum = av[o4 + u];
+                                bad |= !(sum >= 1e-30f);
+                                res[u] = fmaf(__log2f(sum), 0.6931471805599453f, shift);
+                            }
+                            if (valid) *reinterpret_cast<float4*>(op + o4) = make_float4(res[0], res[1], res[2], res[3]);
+                        }
+                        if (bad && valid && !a.debug) opg_exact_row<C, HC>(a, s, r, b, half * HC, op);
+                    } else {
+                        const uint32_t* my_e = Es + ab * NPAIR * 128 + row;
+                        const int sc = MODE == OPG_DXR ? 2 * s + 1 : 2 * s;
+                        if (valid && sc < a.d_in) {
+                            float* dp = a.y + (((int64_t)sc * a.R + r) * a.B + b) * C + half * HC;
+#pragma unroll
+                            for (int q = 0; q < HC / 4; ++q) {
+                                const uint32_t e0 = my_e[(half * (HC / 2) + 2 * q) * 128], e1 = my_e[(half * (HC / 2) + 2 * q + 1) * 128];
+                                *reinterpret_cast<float4*>(dp + 4 * q) =
+                                    make_float4(bf16_lo(e0) * av[4 * q], bf16_hi(e0) * av[4 * q + 1], bf16_lo(e1) * av[4 * q + 2],
+                                                bf16_hi(e1) * av[4 * q + 3]);
+                            }
+                        }
+                    }
+                    ++n_epi;
+                    TC2_T(t_e2);
+                    TC2_ADD(2, t_e1, t_e2);
+                }
+            }
+        }
+    }
+    // teardown
+    if (warp == 0) TC2_FLUSH(0);
+    if (warp == 8) TC2_FLUSH(6);
+    if (warp == 16) TC2_FLUSH(12);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (threadIdx.x == 0 && *abort_flag) atomicAdd(&g_tc2_aborts, 1);
+    if (warp == 16) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight operand preparation
+// ---------------------------------------------------------------------------------------------------------------
+// Log-normaliser of the unnormalised weights: logz[s][o][r] = logsumexp_k param[s][k][o][r]  (F.log_softmax(dim=2) of
+// layers.py:85 is then lw = param - logz, applied by the consumers).  Block = 64 consecutive (o, r) columns x 4 k-phases;
+// every warp load is one 128-byte line; online max/sum so the parameters are read once.
+__global__ void __launch_bounds__(256) tc_logz_kernel(const float* __restrict__ param, float* __restrict__ logz, int K,
+                                                     int ocr, int tiles_per_s) {
+    __shared__ float sm_m[4][64], sm_s[4][64];
+    const int s = blockIdx.x / tiles_per_s;
+    const int col = (blockIdx.x % tiles_per_s) * 64 + (threadIdx.x & 63);
+    const int ph = threadIdx.x >> 6;
+    float m = -CUDART_INF_F, acc = 0.f;
+    if (col < ocr) {
+        const float* p = param + (int64_t)s * K * ocr + col;
+        int k = ph;
+        for (; k + 12 < K; k += 16) {  // four independent loads in flight per thread
+            const float v0 = p[(int64_t)k * ocr], v1 = p[(int64_t)(k + 4) * ocr], v2 = p[(int64_t)(k + 8) * ocr],
+                        v3 = p[(int64_t)(k + 12) * ocr];
+            const float mn = fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), m);
+            if (mn != -CUDART_INF_F) {
+                acc = acc * __expf(m - mn) + __expf(v0 - mn) + __expf(v1 - mn) + __expf(v2 - mn) + __expf(v3 - mn);
+                m = mn;
+            }
+        }
+        for (; k < K; k += 4) {
+            const float v = p[(int64_t)k * ocr];
+            const float mn = fmaxf(m, v);
+            if (mn != -CUDART_INF_F) {
+                acc = acc * __expf(m - mn) + __expf(v - mn);
+                m = mn;
+            }
+        }
+    }
+    sm_m[ph][threadIdx.x & 63] = m;
+    sm_s[ph][threadIdx.x & 63] = acc;
+    __syncthreads();
+    if (ph == 0 && col < ocr) {
+        float mm = fmaxf(fmaxf(sm_m[0][threadIdx.x], sm_m[1][threadIdx.x]), fmaxf(sm_m[2][threadIdx.x], sm_m[3][threadIdx.x]));
+        float tot = 0.f;
+        if (mm != -CUDART_INF_F) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tot += sm_s[q][threadIdx.x] * __expf(sm_m[q][threadIdx.x] - mm);
+        }
+        logz[(int64_t)s * ocr + col] = mm == -CUDART_INF_F ? -CUDART_INF_F : mm + logf(tot);
+    }
+}
+
+// fp32 (log-)weights [1][d][K][OC][R]  ->  bf16 exp() core-matrix image [d][R][K/8][OC/8][8 (k)][8 (o)].
+// One block per (scope, group of 8 k-values).
+__global__ void __launch_bounds__(256) tc_wimage_kernel(const float* __restrict__ lw, const float* __restrict__ logz,
+                                                       uint8_t* __restrict__ wimg, int d, int K, int OC, int R) {
+    extern __shared__ float tile[];  // [8][OC][R]
+    const int kg = blockIdx.x % (K / 8);
+    const int s = blockIdx.x / (K / 8);
+    const int n = 8 * OC * R;
+    const float* src = lw + ((int64_t)s * K + (int64_t)kg * 8) * OC * R;
+    const int ocr = OC * R;
+    const float* zp = logz ? logz + (int64_t)s * ocr : nullptr;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) tile[i] = __expf(src[i] - (zp ? zp[i % ocr] : 0.f));
+    __syncthreads();
+    const int per_r = OC * 8;  // bf16 elements per (r, kg)
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(wimg);
+    for (int i = threadIdx.x; i < R * per_r; i += blockDim.x) {
+        const int r = i / per_r, e = i % per_r;
+        const int og = e / 64, kk = (e / 8) % 8, oo = e % 8;
+        const int o = og * 8 + oo;
+        dst[(((int64_t)s * R + r) * (K / 8) + kg) * per_r + e] = __float2bfloat16(tile[(kk * OC + o) * R + r]);
+    }
+}
+
+// Pair-transposed image: W2[(r',l),o] = W[(l,r'),o], a permutation of the image's 16-byte rows (8 o-values each).
+// One thread per 16-byte chunk of the destination (coalesced writes).
+__global__ void __launch_bounds__(256) tc_wimage_t_kernel(const uint4* __restrict__ img, uint4* __restrict__ img2, int C,
+                                                         int64_t nchunks) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nchunks) return;
+    const int NVG = C / 8;
+    const int per_sr = C * C * NVG;       // chunks per (s, r): K rows x NVG o-groups
+    const int64_t sr = i / per_sr;
+    const int e = (int)(i % per_sr);
+    // destination chunk (k2 = rp*C + l, og): block (k2/8, og), row k2%8
+    const int row = e % 8, og = (e / 8) % NVG, k2g = e / (8 * NVG);
+    const int k2 = k2g * 8 + row;
+    const int rp = k2 / C, l = k2 % C;
+    const int k = l * C + rp;
+    const int srce = ((k / 8) * NVG + og) * 8 + (k % 8);
+    img2[i] = img[sr * per_sr + srce];
+}
+
+template <int C, int MODE>
+static int launch_opg(const OpgArgs& a, cudaStream_t st) {
+    constexpr int W_BYTES = C * C * C * 2;
+    constexpr int SMEM = W_BYTES + 1024 + 3 * 2 * (C / 2) * 128 * 4 + 2 * 2 * 128 * 4 + (2 * 4 + 9) * 8 + 16;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(opg_kernel<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return spn_cuda_status(e);
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int nitems = a.d_out * a.R * a.nsplit;
+    opg_kernel<C, MODE><<<nitems < sms ? nitems : sms, 544, SMEM, st>>>(a);
+    return spn_launch_status();
+}
+
+template <int MODE>
+static int dispatch_opg(int c, const OpgArgs& a, cudaStream_t st) {
+    if (c == 40) return launch_opg<40, MODE>(a, st);
+    if (c == 32) return launch_opg<32, MODE>(a, st);
+    if (c == 16) return launch_opg<16, MODE>(a, st);
+    return SPN_ERR_UNSUPPORTED;
+}
+
+// SPN_TC_DEBUG (timing experiments only; results are garbage): 1 no MMA issue, 2 no TMEM stores, 3 generators idle,
+// 4 loaders skip exp / epilogue arithmetic, 5 loaders skip the row loads, 7 = 3 + 4 + 5, 8 = 7 + 1, 9 phase profile.
+static void opg_split(OpgArgs& a, int B, int d_out, int R) {
+    a.ntiles = (B + 127) / 128;
+    int nsplit = (8 * 148 + d_out * R - 1) / (d_out * R);
+    if (nsplit > a.ntiles / 4) nsplit = a.ntiles / 4;
+    if (nsplit < 1) nsplit = 1;
+    a.nsplit = nsplit;
+    const char* dbg = getenv("SPN_TC_DEBUG");
+    a.debug = dbg ? atoi(dbg) : 0;
+    const char* dn = getenv("SPN_TC_N");
+    a.dbg_n = dn ? atoi(dn) : 0;
+}
+
+extern "C" int spn_sum_tc_supported(int c, int oc, int R) {
+    (void)R;
+    return (c == 40 && oc == 40) || (c == 32 && oc == 32) || (c == 16 && oc == 16) ? 1 : 0;
+}
+
+extern "C" int64_t spn_sum_tc_image_bytes(int d_out, int c, int oc, int R) {
+    return 2 * (int64_t)d_out * R * c * c * oc * 2 + 1024;
+}
+
+extern "C" int spn_sum_tc_prepare(const float* lw, int d_out, int c, int oc, int R, float* logz, void* wimg, void* stream) {
+    if (!lw || !wimg || !spn_sum_tc_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
+    const int K = c * c;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (logz) {
+        const int ocr = oc * R, tiles = (ocr + 63) / 64;
+        tc_logz_kernel<<<d_out * tiles, 256, 0, st>>>(lw, logz, K, ocr, tiles);
+        int rc = spn_launch_status();
+        if (rc != SPN_OK) return rc;
+    }
+    const size_t smem = (size_t)8 * oc * R * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(tc_wimage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return spn_cuda_status(e);
+    }
+    tc_wimage_kernel<<<d_out * (K / 8), 256, smem, st>>>(lw, logz, (uint8_t*)wimg, d_out, K, oc, R);
+    int rc = spn_launch_status();
+    if (rc != SPN_OK) return rc;
+    const int64_t img_bytes = (int64_t)d_out * R * K * oc * 2;
+    const int64_t nchunks = img_bytes / 16;
+    tc_wimage_t_kernel<<<spn_blocks(nchunks, 256), 256, 0, st>>>((const uint4*)wimg, (uint4*)((uint8_t*)wimg + img_bytes), c, nchunks);
+    return spn_launch_status();
+}
+
+extern "C" int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw, const float* logz, int B, int d_in,
+                              int d_out, int c, int oc, int R, float* out, void* stream) {
+    if (!x || !wimg || !lw || !out || B <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
+    if (!spn_sum_tc_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
+    OpgArgs a{};
+    a.x = x; a.wimg = (const uint8_t*)wimg; a.lw = lw; a.logz = logz; a.y = out;
+    a.B = B; a.d_in = d_in; a.d_out = d_out; a.R = R;
+    opg_split(a, B, d_out, R);
+    return dispatch_opg<OPG_FWD>(c, a, (cudaStream_t)stream);
+}
+
+extern "C" int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g, const void* wimg, int B, int d_in,
+                                int d_out, int c, int oc, int R, float* dx, void* stream) {
+    if (!x || !out || !g || !wimg || !dx || B <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
+    if (!spn_sum_tc_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
+    OpgArgs a{};
+    a.x = x; a.wimg = (const uint8_t*)wimg; a.out = out; a.g = g; a.y = dx;
+    a.B = B; a.d_in = d_in; a.d_out = d_out; a.R = R;
+    opg_split(a, B, d_out, R);
+    int rc = dispatch_opg<OPG_DXL>(c, a, (cudaStream_t)stream);
+    if (rc != SPN_OK) return rc;
+    return dispatch_opg<OPG_DXR>(c, a, (cudaStream_t)stream);
+}
+
+extern "C" int spn_debug_tc_prof(unsigned long long* out_host, int reset) {
+    unsigned long long v[24] = {0};
+    cudaError_t e = cudaMemcpyFromSymbol(v, g_tc2_prof, sizeof(v));
+    if (e != cudaSuccess) return spn_cuda_status(e);
+    if (out_host) for (int i = 0; i < 24; ++i) out_host[i] = v[i];
+    if (reset) {
+        unsigned long long z[24] = {0};
+        e = cudaMemcpyToSymbol(g_tc2_prof, z, sizeof(z));
+        if (e != cudaSuccess) return spn_cuda_status(e);
+    }
+    return SPN_OK;
+}
+
+// debug: number of CTAs that hit the bounded-wait timeout since the library was loaded (synchronises)
+int tc_bwd_aborts_host(int* out);
+
+extern "C" int spn_debug_tc_aborts(int* out_host) {
+    int v = 0, w = 0;
+    cudaError_t e = cudaMemcpyFromSymbol(&v, g_tc2_aborts, sizeof(int));
+    if (e != cudaSuccess) return spn_cuda_status(e);
+    int rc = tc_bwd_aborts_host(&w);
+    if (rc != SPN_OK) return rc;
+    if (out_host) *out_host = v + w;
+    return SPN_OK;
+}

@@ -1,5 +1,5 @@
-// Backward of the shared-weight CrossProduct+Sum layer on the tensor cores (tcgen05 + TMEM); see sum_tc.cu for the
-// forward formulation.  With E[b,k] = eL[b,l] eR[b,r'] (k = l*c + r'), W = exp(log-weights) and
+// dW of the shared-weight CrossProduct+Sum layer on the tensor cores (tcgen05 + TMEM); see sum_tc2.cu for the forward
+// and dX formulation.  With E[b,k] = eL[b,l] eR[b,r'] (k = l*c + r'), W = exp(log-weights) and
 // G[b,o] = g[b,o] * exp(mL + mR - out[b,o])  (= g / linear-domain sum), SURVEY A.5 becomes two GEMMs:
 //
 //   dX:  dE[b,k] = sum_o G[b,o] W[k,o]            (M = 128 rows, N = k-chunk, K = o)      -> spn_sum_tc_bwd_x
@@ -79,191 +79,6 @@ __device__ __forceinline__ void tc_bwd_prologue(const TcBwdArgs& a, int s, int r
     for (int q = OC; q < NPAD; ++q) G[q] = 0.f;
 #pragma unroll
     for (int q = 0; q < NPAD / 2; ++q) Gp[q] = pack_bf16(G[2 * q], G[2 * q + 1]);
-}
-
-// ================================================================================================================
-// dX
-// ================================================================================================================
-// Roles as in the forward: warps 0-3 / 4-7 = two row-tile warpgroups (prologue + TMEM epilogue), warp 8 / 9 = their MMA
-// issuers (warp 8 also streams the weight image).  Per tile the k axis is processed in chunks of LPS*C columns
-// through NBUF TMEM buffers per warpgroup.
-template <int C, int OC, int NPAD, int LPS, int NBUF>
-__global__ void __launch_bounds__(320, 1) sum_tc_bwd_x_kernel(TcBwdArgs a) {
-    constexpr int NG = NPAD / 8;
-    constexpr int K = C * C;
-    constexpr int W_BYTES = K * NPAD * 2;
-    constexpr int NCH = LPS * C;               // dE columns per chunk
-    constexpr int CHUNKS = C / LPS;
-    constexpr int G_COLS = 32;                 // NPAD/2 <= 32 packed-bf16 columns for the A operand
-    constexpr int WG_COLS = G_COLS + NBUF * NCH;
-    static_assert(NPAD <= 64 && NCH % 16 == 0 && NCH <= 256 && 2 * WG_COLS <= 512, "unsupported shape");
-    constexpr uint32_t IDESC = instr_desc_bf16(128, NCH, 0, 0);
-    constexpr int STAGE_F = 128 * (C + 1);     // per-warpgroup dxL staging (row-major, +1 float padding)
-
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* wsm = smem;
-    float* stage = reinterpret_cast<float*>(smem + W_BYTES);              // [2][128][C+1]
-    uint64_t* bar_a = reinterpret_cast<uint64_t*>(stage + 2 * STAGE_F);   // [2]       G operand written (4 warp arrivals)
-    uint64_t* bar_dfull = bar_a + 2;                                      // [2][NBUF] chunk product ready (commit)
-    uint64_t* bar_dfree = bar_dfull + 2 * NBUF;                           // [2][NBUF] chunk consumed (4 warp arrivals)
-    uint64_t* bar_w = bar_dfree + 2 * NBUF;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 1);
-    volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        mbar_init(bar_a + 0, 4);
-        mbar_init(bar_a + 1, 4);
-        for (int i = 0; i < 2 * NBUF; ++i) {
-            mbar_init(bar_dfull + i, 1);
-            mbar_init(bar_dfree + i, 4);
-        }
-        mbar_init(bar_w, 1);
-        *abort_flag = 0;
-        mbar_fence_init();
-    }
-    if (warp == 8) tmem_alloc(tmem_slot, 512);
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    if (threadIdx.x == 0 && *tmem_slot != 0) *abort_flag = 1;
-    constexpr uint32_t tmem_base = 0;
-    __syncthreads();
-
-    const int nitems = a.d_out * a.R * a.nsplit;
-    const int tiles_per_split = (a.ntiles + a.nsplit - 1) / a.nsplit;
-    uint32_t n_tiles_done = 0;   // per role: tiles processed by this warpgroup (bar_a phase)
-    uint32_t n_chunks = 0;       // per role: chunks processed by this warpgroup (buffer ring position)
-    uint32_t items_done = 0;
-
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++items_done) {
-        const int split = item % a.nsplit;
-        const int sr = item / a.nsplit;
-        const int r = sr % a.R, s = sr / a.R;
-        const int tile_begin = split * tiles_per_split;
-        const int tile_end = min(a.ntiles, tile_begin + tiles_per_split);
-        __syncthreads();
-        if (*abort_flag) break;
-        if (warp >= 8) {
-            const int wg = warp - 8;
-            if (wg == 0 && lane == 0) {
-                mbar_arrive_expect_tx(bar_w, W_BYTES);
-                const uint8_t* src = a.wimg + (size_t)sr * W_BYTES;
-                constexpr int CH = 16384;
-                for (int off = 0; off < W_BYTES; off += CH) bulk_g2s(wsm + off, src + off, min(CH, W_BYTES - off), bar_w);
-            }
-            __syncwarp();
-            bool ok = mbar_wait(bar_w, items_done & 1, abort_flag);
-            fence_after_sync();
-            const uint32_t wsm_addr = smem_u32(wsm);
-            const uint32_t wg_base = tmem_base + wg * WG_COLS;
-            for (int tile = tile_begin + wg; tile < tile_end && ok; tile += 2) {
-                ok = mbar_wait(bar_a + wg, n_tiles_done & 1, abort_flag);
-                ++n_tiles_done;
-                if (!ok) break;
-                fence_after_sync();
-                for (int ch = 0; ch < CHUNKS; ++ch) {
-                    const uint32_t buf = n_chunks % NBUF, par = (n_chunks / NBUF) & 1;
-                    ok = mbar_wait(bar_dfree + wg * NBUF + buf, par ^ 1, abort_flag);
-                    if (!ok) break;
-                    fence_after_sync();
-                    const uint32_t dcol = wg_base + G_COLS + buf * NCH;
-                    const int kg0 = ch * (NCH / 8);
-#pragma unroll
-                    for (int kk = 0; kk < NPAD / 16; ++kk) {
-                        // B[N = k, K = o] K-major: 8-row groups along N are NG*128 bytes apart, the two K halves 128 bytes
-                        const uint64_t bdesc = smem_desc(wsm_addr + (uint32_t)(kg0 * NG + 2 * kk) * 128, 128, NG * 128);
-                        mma_ts_uniform(dcol, wg_base + kk * 8, bdesc, IDESC, kk ? 1u : 0u);
-                    }
-                    mma_commit_uniform(bar_dfull + wg * NBUF + buf);
-                    ++n_chunks;
-                }
-            }
-        } else {
-            const int wg = warp >> 2;
-            const int row = threadIdx.x & 127;
-            const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-            const uint32_t wg_base = tmem_base + lane_base + wg * WG_COLS;
-            float* my_stage = stage + wg * STAGE_F + row * (C + 1);
-            bool ok = true;
-            for (int tile = tile_begin + wg; tile < tile_end && ok; tile += 2) {
-                const int64_t b = (int64_t)tile * 128 + row;
-                const bool valid = b < a.B;
-                uint32_t eL[C / 2], eRp[C / 2], Gp[NPAD / 2];
-                tc_bwd_prologue<C, OC, NPAD>(a, s, r, b, valid, eL, eRp, Gp);
-                // the previous tile's MMAs (which read the G columns) completed before its last chunk was consumed
-                {
-                    uint32_t gz[G_COLS];
-#pragma unroll
-                    for (int q = 0; q < G_COLS; ++q) gz[q] = q < NPAD / 2 ? Gp[q] : 0u;
-                    tmem_store_cols<G_COLS>(wg_base, gz);
-                }
-                tmem_wait_st();
-                fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_a + wg);
-                float eR[C], tR[C];
-#pragma unroll
-                for (int q = 0; q < C / 2; ++q) {
-                    eR[2 * q] = bf16_lo(eRp[q]);
-                    eR[2 * q + 1] = bf16_hi(eRp[q]);
-                    tR[2 * q] = 0.f;
-                    tR[2 * q + 1] = 0.f;
-                }
-#pragma unroll
-                for (int ch = 0; ch < CHUNKS; ++ch) {
-                    const uint32_t buf = n_chunks % NBUF, par = (n_chunks / NBUF) & 1;
-                    ok = ok && mbar_wait(bar_dfull + wg * NBUF + buf, par, abort_flag);
-                    if (!ok) break;
-                    fence_after_sync();
-#pragma unroll
-                    for (int h = 0; h < LPS; ++h) {
-                        const int l = ch * LPS + h;
-                        uint32_t v[C];
-#pragma unroll
-                        for (int q = 0; q < C / 8; ++q) tmem_ld8(wg_base + G_COLS + buf * NCH + h * C + q * 8, v + q * 8);
-                        tmem_wait_ld();
-                        const float el = (l & 1) ? bf16_hi(eL[l / 2]) : bf16_lo(eL[l / 2]);
-                        float tl = 0.f;
-#pragma unroll
-                        for (int q = 0; q < C; ++q) {
-                            const float d = __uint_as_float(v[q]);
-                            tl = fmaf(eR[q], d, tl);
-                            tR[q] = fmaf(el, d, tR[q]);
-                        }
-                        my_stage[l] = el * tl;
-                    }
-                    fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_dfree + wg * NBUF + buf);
-                    ++n_chunks;
-                }
-                if (!ok) break;
-                if (valid) {
-                    if (2 * s < a.d_in) {
-                        float* dl = a.dx + (((int64_t)(2 * s) * a.R + r) * a.B + b) * C;
-#pragma unroll
-                        for (int q = 0; q < C / 4; ++q)
-                            reinterpret_cast<float4*>(dl)[q] =
-                                make_float4(my_stage[4 * q], my_stage[4 * q + 1], my_stage[4 * q + 2], my_stage[4 * q + 3]);
-                    }
-                    if (2 * s + 1 < a.d_in) {
-                        float* dr = a.dx + (((int64_t)(2 * s + 1) * a.R + r) * a.B + b) * C;
-#pragma unroll
-                        for (int q = 0; q < C / 4; ++q)
-                            reinterpret_cast<float4*>(dr)[q] =
-                                make_float4(eR[4 * q] * tR[4 * q], eR[4 * q + 1] * tR[4 * q + 1],
-                                            eR[4 * q + 2] * tR[4 * q + 2], eR[4 * q + 3] * tR[4 * q + 3]);
-                    }
-                }
-            }
-        }
-    }
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    if (threadIdx.x == 0 && *abort_flag) atomicAdd(&g_tc_bwd_aborts, 1);
-    if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
 // ================================================================================================================
@@ -531,24 +346,6 @@ __global__ void __launch_bounds__(256) tc_dw_finish_kernel(const float* __restri
 
 extern "C" int spn_sum_tc_supported(int c, int oc, int R);
 
-template <int C, int OC, int NPAD, int LPS, int NBUF>
-static int launch_bwd_x(const TcBwdArgs& a, cudaStream_t st) {
-    constexpr int SMEM = C * C * NPAD * 2 + 2 * 128 * (C + 1) * 4 + (3 + 4 * NBUF) * 8 + 16;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(sum_tc_bwd_x_kernel<C, OC, NPAD, LPS, NBUF>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-        if (e != cudaSuccess) return spn_cuda_status(e);
-        configured = true;
-    }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int nitems = a.d_out * a.R * a.nsplit;
-    sum_tc_bwd_x_kernel<C, OC, NPAD, LPS, NBUF><<<nitems < sms ? nitems : sms, 320, SMEM, st>>>(a);
-    return spn_launch_status();
-}
-
 template <int C, int OC, int NPAD, int GC>
 static int launch_bwd_w(const TcBwdArgs& a, cudaStream_t st) {
     constexpr int NCHUNK = ((C / 8) * (C / 8) + 1) / 2;
@@ -566,25 +363,6 @@ static int launch_bwd_w(const TcBwdArgs& a, cudaStream_t st) {
     const int nitems = a.d_out * a.R * NGROUPS;
     sum_tc_bwd_w_kernel<C, OC, NPAD, GC><<<nitems < sms ? nitems : sms, 288, SMEM, st>>>(a, NGROUPS);
     return spn_launch_status();
-}
-
-extern "C" int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g, const void* wimg, int B, int d_in,
-                                int d_out, int c, int oc, int R, float* dx, void* stream) {
-    if (!x || !out || !g || !wimg || !dx || B <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
-    if (!spn_sum_tc_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
-    TcBwdArgs a{};
-    a.x = x; a.out = out; a.g = g; a.wimg = (const uint8_t*)wimg; a.dx = dx;
-    a.B = B; a.d_in = d_in; a.d_out = d_out; a.R = R;
-    a.ntiles = (B + 127) / 128;
-    int nsplit = (4 * 148 + d_out * R - 1) / (d_out * R);
-    if (nsplit > a.ntiles / 4) nsplit = a.ntiles / 4;
-    if (nsplit < 1) nsplit = 1;
-    a.nsplit = nsplit;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (c == 40) return launch_bwd_x<40, 40, 48, 2, 2>(a, st);
-    if (c == 32) return launch_bwd_x<32, 32, 32, 2, 2>(a, st);
-    if (c == 16) return launch_bwd_x<16, 16, 16, 2, 2>(a, st);
-    return SPN_ERR_UNSUPPORTED;
 }
 
 extern "C" int spn_sum_tc_bwd_w(const float* x, const float* out, const float* g, const float* lw, const float* logz,

@@ -21,14 +21,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the hint expires, so a
+// waiting warp does not burn issue slots on a polling loop (18 warps share four schedulers).
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
@@ -44,6 +46,48 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
             return false;
         }
     }
+}
+
+// Wait as ONE opaque PTX block (spin loop, suspend-time hint, bounded): the compiler sees no loop, no branch and no
+// result, so control flow around it stays provably warp-uniform and ptxas keeps loop counters and the tcgen05 descriptors
+// derived from them in UNIFORM registers (with a C-level loop / bool result every later MMA cost ~14 R2UR / VOTE / ELECT
+// instructions, ~56 clk).  A timeout (protocol bug; ~2 s) raises the CTA-wide abort flag in shared memory; from then on
+// every wait falls through at once, the kernel drains with garbage results and the host sees the abort count.
+__device__ __forceinline__ void mbar_wait_sticky(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 cnt, flg;\n\t"
+        "mov.u32 cnt, 0;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra LAB_DONE;\n\t"
+        "ld.volatile.shared.u32 flg, [%3];\n\t"
+        "setp.ne.u32 p, flg, 0;\n\t"
+        "@p bra LAB_DONE;\n\t"
+        "add.u32 cnt, cnt, 1;\n\t"
+        "setp.lt.u32 p, cnt, %4;\n\t"
+        "@p bra LAB_WAIT;\n\t"
+        "st.volatile.shared.u32 [%3], 1;\n\t"
+        "LAB_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(100000u), "r"(smem_u32((const void*)abort_flag)), "r"(20000u)
+        : "memory");
+}
+
+// Non-blocking probe of an mbarrier phase, returned as a warp-uniform value (lane 0's result, broadcast by a shuffle so
+// that the compiler knows a branch on it is not divergent).  Used to learn EARLY -- before a long blocking instruction
+// sequence -- that the next hand-off has already happened, so that its ~90-clk try_wait latency is not paid in series.
+__device__ __forceinline__ bool mbar_probe_uniform(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
 }
 
 // ------------------------------------------------------------------------------------------------ bulk copy (TMA, 1-D)
@@ -210,6 +254,11 @@ __device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) {
     uint32_t d;
     asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
     return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }

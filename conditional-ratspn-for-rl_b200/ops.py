@@ -361,8 +361,7 @@ def tc_prepare(w: torch.Tensor, raw: bool = False):
     _, d, ic, oc, R = w.shape
     c = int(round(math.sqrt(ic)))
     assert c * c == ic
-    npad = (oc + 15) // 16 * 16
-    wimg = torch.empty(d * R * ic * npad * 2, device=w.device, dtype=torch.uint8)
+    wimg = torch.empty(_abi.lib().spn_sum_tc_image_bytes(d, c, oc, R), device=w.device, dtype=torch.uint8)
     logz = torch.empty(d, oc, R, device=w.device, dtype=torch.float32) if raw else None
     call("spn_sum_tc_prepare", ptr(w), d, c, oc, R, ptr(logz), ptr(wimg), stream_ptr(w.device))
     return (wimg, logz) if raw else wimg

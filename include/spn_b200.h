@@ -167,19 +167,22 @@ int spn_sample_leaf(const float* mu, const float* sigma, int Wsets, int w, int Q
  * fp32 accumulation; replaces the same reference lines as spn_sum_fwd(xprod = 1) for RatSpn models whose channel
  * counts are supported (spn_sum_tc_supported).  Activations use the internal layout [scope][repetition][batch][channel]:
  *   x [d_in, R, B, c] contiguous, out [d_out, R, B, oc] contiguous.
- * spn_sum_tc_prepare turns fp32 log-weights lw [1, d_out, c*c, oc, R] into the bf16 operand image
- * (d_out * R * c*c * ceil16(oc) * 2 bytes, caller-allocated) that spn_sum_tc_fwd streams through shared memory.
+ * spn_sum_tc_prepare turns fp32 log-weights lw [1, d_out, c*c, oc, R] into the bf16 operand images
+ * (spn_sum_tc_image_bytes() bytes, caller-allocated: the core-matrix image used by the forward and the right-child
+ * gradient, followed by its pair-transposed copy used by the left-child gradient) that the kernels stream through
+ * shared memory with the TMA engine.
  * Weight normalisation (layers.py:85, F.log_softmax over the in-channels on every read) is fused: when `logz`
  * ([d_out, oc, R], caller-allocated) is non-NULL, `lw` is the UNNORMALISED parameter tensor, spn_sum_tc_prepare writes
  * logz = logsumexp_k lw and every consumer uses lw - logz; with logz == NULL, lw must already be normalised.
  * Outputs whose linear-domain sum underflows are recomputed exactly in fp32 from lw (logsumexp semantics are kept).
  * ------------------------------------------------------------------------------------------------------------- */
 int spn_sum_tc_supported(int c, int oc, int R);
+int64_t spn_sum_tc_image_bytes(int d_out, int c, int oc, int R);
 int spn_sum_tc_prepare(const float* lw, int d_out, int c, int oc, int R, float* logz, void* wimg, void* stream);
 int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw, const float* logz, int B, int d_in, int d_out,
                    int c, int oc, int R, float* out, void* stream);
-/* Backward of spn_sum_tc_fwd (SURVEY A.5 as two tensor-core GEMMs; layouts as in the forward).
- *   spn_sum_tc_bwd_x: dx [d_in, R, B, c] fully overwritten.
+/* Backward of spn_sum_tc_fwd (SURVEY A.5 as tensor-core GEMMs; layouts as in the forward).
+ *   spn_sum_tc_bwd_x: dx [d_in, R, B, c] fully overwritten (two forward-shaped outer-product GEMMs, one per child).
  *   spn_sum_tc_bwd_w: dlw [1, d_out, c*c, oc, R] = gradient w.r.t. the tensor passed as lw, fully overwritten: the
  *                     log-weights (logz == NULL) or the unnormalised parameters (logz from spn_sum_tc_prepare; the
  *                     softmax backward is fused); dwt_workspace: caller-provided scratch of
@@ -205,7 +208,7 @@ int spn_root_shared_bwd(const float* x, int d_in, const float* lw, const float* 
 /* Debug aid (synchronises): number of CTAs that gave up on an mbarrier wait since the library was loaded. */
 int spn_debug_tc_aborts(int* out_host);
 /* Debug aid (synchronises): with SPN_TC_DEBUG=9 in the environment one thread per warpgroup of CTA 0 accumulates clock64
- * deltas per pipeline phase of spn_sum_tc_fwd; copies the 16 counters to out_host (host pointer) and optionally resets. */
+ * deltas per pipeline phase of the spn_sum_tc_fwd / _bwd_x kernels; copies the 24 counters to out_host (host pointer) and optionally resets. */
 int spn_debug_tc_prof(unsigned long long* out_host, int reset);
 
 #ifdef __cplusplus

@@ -24,12 +24,13 @@ if which in ("all", "bwdw"): timeit("tc bwd_w S_1", lambda: ops.tc_sum_backward_
 if which in ("all",): timeit("prepare", lambda: ops.tc_prepare(lw))
 print("aborts", ops.tc_aborts())
 import os, ctypes
-if os.environ.get("SPN_TC_DEBUG") == "9":
+if os.environ.get("SPN_TC_DEBUG") in ("9", "3"):
     from ratspn_b200 import _abi
-    buf = (ctypes.c_ulonglong * 16)()
+    buf = (ctypes.c_ulonglong * 24)()
     _abi.lib().spn_debug_tc_prof(buf, 1)
     ops.tc_sum_forward(x, wimg, lw); torch.cuda.synchronize()
     _abi.lib().spn_debug_tc_prof(buf, 0)
-    n = max(1, buf[8])
-    names = ["load", "load+exp", "wait_empty", "gen+st", "wait_st+arrive", "wait_acc", "epilogue", "tile_total"]
-    print("tiles", buf[8], " ".join(f"{names[i]}={buf[i]/n:.0f}" for i in range(8)))
+    n = max(1, buf[5])
+    names = ["g.wait_vec", "g.wait_empty", "g.gen", "g.wait_st", "g.stages", "g.tiles", "l.prologue", "l.wait_acc", "l.epilogue",
+             "-", "-", "-", "m.wait_acc_empty", "m.wait_full", "m.issue", "m.wait_w", "-", "m.tiles"]
+    print(" ".join(f"{names[i]}={buf[i]/n:.0f}" for i in range(18) if names[i] != "-"))
