@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(288, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 1);
     volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2 * NSTA; ++i) {
             mbar_init(bar_full + i, 4);
@@ -143,20 +143,18 @@ __global__ void __launch_bounds__(288, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
         const int chunk_begin = grp * GC;
         const int chunk_end = min(NCHUNK, chunk_begin + GC);
         __syncthreads();
-        if (*abort_flag) break;
+        if (__shfl_sync(0xffffffffu, *abort_flag, 0)) break;
         if (warp == 8) {
             // ---------------------------------------- MMA issuer ----------------------------------------
-            bool ok = true;
             const uint32_t abuf_addr = smem_u32(abuf), gbuf_addr = smem_u32(gbuf);
-            for (int t0 = 0; t0 < a.ntiles && ok; t0 += 2) {
+            for (int t0 = 0; t0 < a.ntiles; t0 += 2) {
 #pragma unroll
                 for (int wg = 0; wg < 2; ++wg) {
                     const int tile = t0 + wg;
                     if (tile >= a.ntiles) continue;
                     for (int ch = chunk_begin; ch < chunk_end; ++ch) {
                         const uint32_t st = n_stage[wg] % NSTA, par = (n_stage[wg] / NSTA) & 1;
-                        ok = ok && mbar_wait(bar_full + wg * NSTA + st, par, abort_flag);
-                        if (!ok) break;
+                        mbar_wait_sticky(bar_full + wg * NSTA + st, par, abort_flag);
                         fence_after_sync();
                         const uint32_t aaddr = abuf_addr + (wg * NSTA + st) * A_BYTES;
                         const uint32_t gaddr = gbuf_addr + wg * G_BYTES;
@@ -172,18 +170,16 @@ __global__ void __launch_bounds__(288, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
                         mma_commit_uniform(bar_empty + wg * NSTA + st);
                         ++n_stage[wg];
                     }
-                    if (!ok) break;
                     mma_commit_uniform(bar_gfree + wg);
                 }
             }
-            if (ok) mma_commit_uniform(bar_done);
+            mma_commit_uniform(bar_done);
         } else {
             // ---------------------------------------- operand producers ----------------------------------------
             const int wg = warp >> 2;
             const int row = threadIdx.x & 127;
-            bool ok = true;
             uint8_t* my_g = gbuf + wg * G_BYTES + ((row >> 3) * NG) * 128 + (row & 7) * 16;
-            for (int tile = wg; tile < a.ntiles && ok; tile += 2) {
+            for (int tile = wg; tile < a.ntiles; tile += 2) {
                 const int64_t b = (int64_t)tile * 128 + row;
                 const bool valid = b < a.B;
                 uint32_t eL[C / 2], eR[C / 2], Gp[NPAD / 2];
@@ -193,17 +189,15 @@ __global__ void __launch_bounds__(288, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
                     for (int q = 0; q < NPAD / 2; ++q) Gp[q] = 0u;  // rows past the batch contribute nothing
                 }
                 // G tile of the previous tile of this warpgroup must have been consumed
-                ok = mbar_wait(bar_gfree + wg, (n_gtile[0] & 1) ^ 1, abort_flag);
+                mbar_wait_sticky(bar_gfree + wg, (n_gtile[0] & 1) ^ 1, abort_flag);
                 ++n_gtile[0];
-                if (!ok) break;
 #pragma unroll
                 for (int og = 0; og < NG; ++og)
                     *reinterpret_cast<uint4*>(my_g + og * 128) = make_uint4(Gp[4 * og], Gp[4 * og + 1], Gp[4 * og + 2], Gp[4 * og + 3]);
 #pragma unroll 1
                 for (int ch = chunk_begin; ch < chunk_end; ++ch) {
                     const uint32_t st = n_stage[0] % NSTA, par = (n_stage[0] / NSTA) & 1;
-                    ok = mbar_wait(bar_empty + wg * NSTA + st, par ^ 1, abort_flag);
-                    if (!ok) break;
+                    mbar_wait_sticky(bar_empty + wg * NSTA + st, par ^ 1, abort_flag);
                     uint8_t* my_a = abuf + (wg * NSTA + st) * A_BYTES + ((row >> 3) * 16) * 128 + (row & 7) * 16;
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
@@ -239,8 +233,8 @@ __global__ void __launch_bounds__(288, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
                 }
             }
             // ---------------------------------------- epilogue: TMEM -> dwt ----------------------------------------
-            ok = ok && mbar_wait(bar_done, items_done & 1, abort_flag);
-            if (ok) {
+            mbar_wait_sticky(bar_done, items_done & 1, abort_flag);
+            {
                 fence_after_sync();
                 const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
                 for (int ch = chunk_begin + wg; ch < chunk_end; ch += 2) {
