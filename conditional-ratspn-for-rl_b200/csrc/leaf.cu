@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256) leaf_fwd_kernel(LeafArgs a) {
 
     const int f_begin = s * a.card;
     const int f_end = min(a.F, f_begin + a.card);
+#pragma unroll 4
     for (int f = f_begin; f < f_end; ++f) {
         const int src = a.perm ? a.perm[(int64_t)f * a.R + r] : f;
         const int64_t xoff = (int64_t)src * a.sx_f + (int64_t)i * a.sx_i + (int64_t)r * a.sx_r;

@@ -121,6 +121,14 @@ int spn_sum_bwd_x(int xprod, const float* x, int64_t sx_b, int64_t sx_d, int64_t
                   const float* g, int64_t so_b, int64_t so_d, int64_t so_o, int64_t so_r, float* dx, int64_t sdx_b,
                   int64_t sdx_d, int64_t sdx_c, int64_t sdx_r, void* stream);
 
+/* Per-sample-weight (CSPN, Wsets == w) fused CrossProduct + Sum forward, HBM streaming: the contiguous weight slab
+ * [ic, oc, R] of every (row, scope) is staged through shared memory by the TMA engine (cp.async.bulk) while one thread per
+ * output accumulates.  Same semantics as spn_sum_fwd(xprod = 1, reduce_r = 0) for x [B, d_in, c, R] with c and R
+ * contiguous (sx_b, sx_d in elements), lw [w, d_out, c*c, oc, R] contiguous, out [B, d_out, oc, R] contiguous. */
+int spn_sum_ps_supported(int c, int oc, int R);
+int spn_sum_ps_fwd(const float* x, int64_t sx_b, int64_t sx_d, int d_in, int c, const float* lw, int w, int B, int d_out,
+                   int oc, int R, float* out, void* stream);
+
 /* Stand-alone CrossProduct (materialising) and its backward: layers.py:419-440.  x [B, d_in, c, R] contiguous,
  * out [B, ceil_pow2(d_in)/2, c*c, R] contiguous; dx [B, d_in, c, R] contiguous. */
 int spn_xprod_fwd(const float* x, int B, int d_in, int c, int R, float* out, void* stream);

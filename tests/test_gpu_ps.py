@@ -1,0 +1,58 @@
+"""GPU: TMA-staged per-sample-weight (CSPN) Sum forward against the general exact kernel (bit-level agreement is not
+required -- different summation order -- but both are exact fp32 log-sum-exp: <= 1e-5 relative)."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _general(x, lw):
+    """spn_sum_fwd (general kernel) on the same tensors, bypassing the dispatch in ops.SumFn."""
+    from ratspn_b200 import ops
+    from ratspn_b200._abi import call, ptr, stream_ptr
+    xprod, sx, d_in, c, sw, ints, so, out_shape = ops._sum_geometry(x, lw, "xsum", "ref")
+    out = torch.empty(out_shape, device=x.device, dtype=torch.float32)
+    call("spn_sum_fwd", xprod, ptr(x), *sx, d_in, c, ptr(lw), *sw, *ints, ptr(out), *so, stream_ptr(x.device))
+    return out
+
+
+@pytest.mark.parametrize("n,w,d_in,c,oc,R", [(1, 48, 4, 16, 16, 8), (3, 20, 3, 8, 16, 4), (1, 7, 2, 16, 8, 8), (2, 5, 8, 12, 64, 16)])
+def test_per_sample_sum_forward_matches_general_kernel(n, w, d_in, c, oc, R):
+    from ratspn_b200 import ops
+    from ratspn_b200 import _abi
+    assert _abi.lib().spn_sum_ps_supported(c, oc, R)
+    g = torch.Generator().manual_seed(n * 100 + w)
+    x = (torch.randn(n, w, d_in, c, R, generator=g) * 3.0 - 10.0)
+    x[0, 0, 0, :, 0] = float("-inf")     # impossible child for one repetition -> -inf outputs there
+    x[0, 1, 1, 2, :] = 200.0             # dominant channel
+    d_out = max(1, (1 << (d_in - 1).bit_length()) // 2)
+    raw = torch.randn(w, d_out, c * c, oc, R, generator=g) * 2.0
+    raw[1, 0, 2 * c:3 * c] = -400.0      # ... whose products carry negligible weight: linear-domain underflow -> rescue
+    lw = torch.log_softmax(raw, dim=2)
+    x, lw = x.to(DEV), lw.to(DEV)
+    ref = _general(x, lw)
+    got = ops.sum_forward(x, lw, "xsum")
+    if c * c * oc * R * 4 >= 16384:
+        pass  # the dispatch took the streaming kernel
+    assert got.shape == ref.shape
+    both_inf = torch.isinf(ref) & torch.isinf(got) & (ref == got)
+    assert not torch.isnan(got).any()
+    err = torch.where(both_inf, torch.zeros_like(ref), (got - ref).abs())
+    assert err.max().item() <= 1e-5 * ref[torch.isfinite(ref)].abs().max().item() + 1e-5
+    assert torch.isinf(got[0, 0, 0, :, 0]).all()
+
+
+def test_per_sample_sum_gradients_flow_through_general_backward():
+    from ratspn_b200 import ops
+    n, w, d_in, c, oc, R = 1, 6, 2, 16, 16, 8
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, w, d_in, c, R, generator=g).to(DEV).requires_grad_(True)
+    raw = torch.randn(w, 1, c * c, oc, R, generator=g).to(DEV).requires_grad_(True)
+    out = ops.sum_forward(x, torch.log_softmax(raw, dim=2), "xsum")
+    out.sum().backward()
+    # every output is a normalised mixture: d out / d raw sums to zero over the in-channels, d out / d x sums to oc per child
+    assert raw.grad.sum(dim=2).abs().max().item() < 1e-4
+    assert (x.grad.sum(dim=3) - oc).abs().max().item() < 1e-3

@@ -1,0 +1,169 @@
+"""Secondary measurements for the BASELINE.json configs other than the headline one (cfg 1, 3, 4, 5).
+
+Not the driver's bench (that is bench.py, cfg 2): this script records absolute numbers for the other call patterns of the
+hot path on one B200 and writes them as JSON (default: gpurun_out/configs.json).  CUDA-event timing, 3 warm-ups.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ratspn_b200 as rb  # noqa: E402
+from ratspn_b200 import _abi  # noqa: E402
+
+DEV = torch.device("cuda", 0)
+
+
+def timed(fn, reps=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    l0 = _abi.LAUNCHES
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps, (_abi.LAUNCHES - l0) / reps
+
+
+def ratspn(F, D, R, S, I, C=1, tanh=False, leaf_kwargs=None):
+    cfg = rb.RatSpnConfig()
+    cfg.F, cfg.D, cfg.R, cfg.S, cfg.I, cfg.C = F, D, R, S, I, C
+    cfg.dropout, cfg.leaf_base_class, cfg.leaf_base_kwargs, cfg.tanh_squash = 0.0, rb.RatNormal, leaf_kwargs or {}, tanh
+    return rb.RatSpn(cfg).to(DEV)
+
+
+def cfg1():
+    torch.manual_seed(0); np.random.seed(0)
+    m = ratspn(784, 3, 5, 10, 10)
+    x = torch.randn(256, 1, 784, 1, 1, device=DEV)
+
+    def step():
+        for p in m.parameters():
+            p.grad = None
+        (-m(x).mean()).backward()
+    ms, launches = timed(step, reps=20)
+    return {"config": "cfg1 RatSpn F=784 D=3 R=5 S=I=10 B=256 fwd+bwd", "ms": ms, "samples_per_s": 256 / ms * 1e3,
+            "abi_calls_per_step": launches, "reference_cpu_ms (SURVEY 6, 8 cores)": 320.0}
+
+
+def cfg3():
+    """CSPN SAC policy update pattern (sb3.py:89-109, :146-184, :336-344)."""
+    torch.manual_seed(0); np.random.seed(0)
+    cfg = rb.CspnConfig()
+    cfg.F_cond = (376,)
+    cfg.F, cfg.R, cfg.D, cfg.I, cfg.S, cfg.C = 17, 3, 4, 3, 3, 1
+    cfg.dropout = 0.0
+    cfg.leaf_base_class = rb.RatNormal
+    cfg.leaf_base_kwargs = {"min_sigma": 0.001, "max_sigma": 1.0}
+    cfg.tanh_squash = True
+    cfg.feat_layers, cfg.sum_param_layers, cfg.dist_param_layers = [64], [64], [64]
+    cfg.cond_layers_inner_act = torch.nn.LeakyReLU
+    m = rb.CSPN(cfg).to(DEV)
+    B = 256
+    obs = torch.randn(B, 376, device=DEV)
+    failed = torch.rand(B, 17, device=DEV) < 0.05
+    ev = torch.where(failed, torch.atanh(torch.rand(B, 17, device=DEV) * 1.8 - 0.9), torch.full((B, 17), float("nan"), device=DEV))
+    ev = ev.view(1, B, 17, 1, 1)
+    xs = torch.randn(1, B, 17, 1, 1, device=DEV).clamp(-2, 2)
+
+    def update():
+        m.zero_grad(set_to_none=True)
+        ctx = m.sample(mode="onehot", condition=obs, evidence=ev)
+        H, _ = m.recursive_entropy_approx(condition=obs, sample_size=5, marginal_mask=failed)
+        act = ctx.sample.reshape(B, 17)
+        (-(0.1 * H + act.sum(-1)).mean()).backward()
+        m.zero_grad(set_to_none=True)
+        (-m(xs, condition=obs).mean()).backward()
+
+    def rollout():
+        with torch.no_grad():
+            m.sample(mode="index", condition=obs[:1], evidence=ev[:, :1])
+
+    ms, launches = timed(update, reps=5)
+    ms_r, launches_r = timed(rollout, reps=20)
+    return {"config": "cfg3 CSPN SAC update obs 376 / act 17, R=I=S=3 D=4, B=256: onehot sample + evidence, recursive "
+                      "entropy (n=5, mask) fwd+bwd, LL fwd+bwd", "us_per_update": ms * 1e3, "abi_calls_per_update": launches,
+            "rollout_index_sample_with_evidence_B1_us": ms_r * 1e3, "abi_calls_per_rollout": launches_r,
+            "reference_cpu_ms (SURVEY 6, 8 cores)": 2700.0,
+            "note": "latency bound: 1467 circuit parameters per conditional; roofline fractions are meaningless here"}
+
+
+def cfg4():
+    torch.manual_seed(0); np.random.seed(0)
+    m = ratspn(784, 5, 40, 40, 40)
+    n = 65536
+    out = {}
+    with torch.no_grad():
+        for tag, kw in (("index", {}), ("mpe", {"is_mpe": True})):
+            ms, launches = timed(lambda: m.sample(mode="index", n=n, **kw), reps=5)
+            out[tag] = {"ms": ms, "samples_per_s": n / ms * 1e3, "output_GB_per_s": n * 784 * 4 / ms / 1e6,
+                        "abi_calls": launches}
+    out["config"] = "cfg4 RatSpn F=784 D=5 R=40 S=I=40 ancestral sampling, 65536 samples"
+    out["reference_cpu_samples_per_s (SURVEY 6, n=64)"] = 90.0
+    return out
+
+
+def cfg5_narrow(w=2048):
+    """Per-sample-weight (CSPN) regime: R=8, S=I=16, D=6, F=1024; one weight set per conditional, injected directly."""
+    torch.manual_seed(0); np.random.seed(0)
+    cfg = rb.CspnConfig()
+    cfg.F_cond = (4,)
+    cfg.F, cfg.R, cfg.D, cfg.I, cfg.S, cfg.C = 1024, 8, 6, 16, 16, 1
+    cfg.dropout = 0.0
+    cfg.leaf_base_class = rb.RatNormal
+    cfg.leaf_base_kwargs = {"min_sigma": 0.001, "max_sigma": 1.0}
+    cfg.tanh_squash = False
+    cfg.feat_layers, cfg.sum_param_layers, cfg.dist_param_layers = [4], [4], [4]
+    # the gating heads of this width would be huge (Linear(4, 2e6)); build the structure only and inject weights
+    m = rb.RatSpn.__new__(rb.CSPN)
+    rb.RatSpn.__init__(m, cfg)
+    m.replace_layer_params()
+    m = m.to(DEV)
+    nbytes = 0
+    for layer in list(m._inner_layers) + [m.root]:
+        if isinstance(layer, rb.Sum):
+            shape = (w, layer.in_features, layer.in_channels, layer.out_channels, layer.num_repetitions)
+            layer.weight_param = torch.log_softmax(torch.randn(shape, device=DEV), dim=2)
+            nbytes += layer.weight_param.numel() * 4
+        else:
+            layer.num_conditionals = w
+    base = m._leaf.base_leaf
+    base.mean_param = torch.randn(w, 1024, 16, 8, device=DEV)
+    base.std_param = torch.rand(w, 1024, 16, 8, device=DEV) * 0.9 + 0.05
+    nbytes += 2 * base.mean_param.numel() * 4
+    x = torch.randn(1, w, 1024, 1, 1, device=DEV)
+    with torch.no_grad():
+        ms, launches = timed(lambda: rb.RatSpn.forward(m, x), reps=5)
+    return {"config": f"cfg5-narrow per-sample weights R=8 S=I=16 D=6 F=1024, w={w} conditionals, n=1: LL forward",
+            "ms": ms, "conditionals_per_s": w / ms * 1e3, "parameter_bytes_read": nbytes,
+            "achieved_GB_per_s": nbytes / ms / 1e6, "hbm_peak_GB_per_s": 6548.2, "frac": nbytes / ms / 1e6 / 6548.2,
+            "abi_calls": launches}
+
+
+def main():
+    out_path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "configs.json")
+    res = {"device": torch.cuda.get_device_name(0), "lib": _abi.version()}
+    for name, fn in (("cfg1", cfg1), ("cfg3", cfg3), ("cfg4", cfg4), ("cfg5_narrow", cfg5_narrow)):
+        t0 = time.time()
+        try:
+            res[name] = fn()
+        except Exception as e:  # keep going: every config is independent
+            res[name] = {"error": f"{type(e).__name__}: {e}"}
+        res[name]["wall_s"] = time.time() - t0
+        print(name, json.dumps(res[name]), flush=True)
+        torch.cuda.empty_cache()
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    with open(out_path, "w") as f:
+        json.dump(res, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
