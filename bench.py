@@ -186,7 +186,7 @@ def main():
     B = args.batch
     model = build_model(dev)
     broadcast_parameters(model)
-    reducer = FlatGradAllReducer(model.parameters())
+    reducer = FlatGradAllReducer(model.parameters(), overlap=True)
     nbuf = 4
     gen = torch.Generator().manual_seed(1234 + rank)
     host = [torch.rand(B, 1, CFG["F"], 1, 1, generator=gen).pin_memory() for _ in range(nbuf)]

@@ -25,10 +25,15 @@ def shard_batch(x: torch.Tensor, dim: int = 0, world_size: int = None, rank: int
 
 
 class FlatGradAllReducer:
-    """Keeps every trainable parameter's ``.grad`` as a view into one flat fp32 buffer, so that the gradient exchange
-    is a single ``all_reduce`` (sum, then scale by 1/world_size) on that buffer -- no per-tensor launches, no copies."""
+    """Keeps every trainable parameter's ``.grad`` as a view into one flat fp32 buffer.
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], average: bool = True):
+    ``overlap=False``: the gradient exchange is a single ``all_reduce`` on that buffer after the backward pass.
+    ``overlap=True``: every parameter's slice is all-reduced asynchronously as soon as autograd has finished accumulating
+    it (post-accumulate-grad hook), so the collectives of the upper layers run on NCCL's stream while the backward kernels
+    of the lower layers are still executing; ``all_reduce()`` then only waits for the outstanding handles.  The largest
+    bucket of a RAT-SPN (the bottom Sum layer, ~half of all bytes) is produced before the leaf backward, which hides it."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], average: bool = True, overlap: bool = False):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         assert self.params, "no trainable parameters"
         dev, dt = self.params[0].device, self.params[0].dtype
@@ -36,10 +41,26 @@ class FlatGradAllReducer:
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(self.numel, device=dev, dtype=dt)
         self.average = average
+        self.overlap = overlap
+        self._handles = []
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
+        if overlap and self._distributed():
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._hook)
+
+    @staticmethod
+    def _distributed() -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _hook(self, p: torch.nn.Parameter):
+        if p.grad is None:
+            return
+        if self.average:
+            p.grad.mul_(1.0 / dist.get_world_size())
+        self._handles.append(dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=True))
 
     def zero_(self):
         self.flat.zero_()
@@ -57,7 +78,12 @@ class FlatGradAllReducer:
             off += p.numel()
 
     def all_reduce(self, async_op: bool = False):
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        if not self._distributed():
+            return None
+        if self.overlap:
+            for h in self._handles:
+                h.wait()
+            self._handles.clear()
             return None
         if self.average:
             self.flat.mul_(1.0 / dist.get_world_size())

@@ -46,7 +46,16 @@ def _worker(rank, world, port, ret):
     lin.zero_grad(set_to_none=True)
     red.rebind()
     rebound = all(p.grad is not None for p in lin.parameters())
-    ret[rank] = bool(ok and views and rebound and red.numel == sum(p.numel() for p in lin.parameters()))
+    # overlapped mode: per-parameter async all-reduce from post-accumulate-grad hooks, waited for in all_reduce()
+    torch.manual_seed(100)
+    lin2 = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    lin2.load_state_dict(ref.state_dict())
+    red2 = FlatGradAllReducer(lin2.parameters(), average=False, overlap=True)
+    red2.zero_()
+    (lin2(mine).sum() / full.shape[0]).backward()
+    red2.all_reduce()
+    overlap_ok = all(torch.allclose(p.grad, q.grad, atol=1e-6) for p, q in zip(lin2.parameters(), ref.parameters()))
+    ret[rank] = bool(ok and views and rebound and overlap_ok and red.numel == sum(p.numel() for p in lin.parameters()))
     dist.destroy_process_group()
 
 
