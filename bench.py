@@ -284,22 +284,26 @@ def main():
             out1 = ops.tc_sum_forward(h0, wimg, w1, logz)
             g1 = torch.randn_like(out1) / B
             t_fwd = time_alone(lambda: ops.tc_sum_forward(h0, wimg, w1, logz))
-            t_bx = time_alone(lambda: ops.tc_sum_backward_x(h0, out1, g1, wimg, w1))
-            t_bw = time_alone(lambda: ops.tc_sum_backward_w(h0, out1, g1, w1, logz))
+            hand = ops.tc_hand_buffer(h0, out1)
+            t_bx = time_alone(lambda: ops.tc_sum_backward_x(h0, out1, g1, wimg, w1, hand))
+            t_bw = time_alone(lambda: ops.tc_sum_backward_w(hand, h0, out1, g1, w1, logz))
             t_prep = time_alone(lambda: ops.tc_prepare(w1, True))
         _, per_layer = contraction_flops_fwd(B)
         fl = per_layer[0]
         peak = peaks.get("bf16_tflops", 1590.0)
         src = "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1590 (B200_PROFILING.md)"
         kernels = {}
-        for name, t in (("sum_tc_fwd_kernel", t_fwd), ("sum_tc_bwd_x_kernel", t_bx), ("sum_tc_bwd_w_kernel", t_bw)):
-            ach = fl / (t / 1e3) / 1e12
-            kernels[name] = {"layer": "S_1 (d=16, K=1600, N=40, R=40)", "ms": t, "flops": fl, "achieved_tflops": ach,
-                             "frac": ach / peak, "traffic": ncu.get(name)}
+        # flops executed per call: forward one [B x 1600] x [1600 x 40] GEMM per (scope, repetition); dX two of them (one
+        # per child: opg_kernel<DXL> + opg_kernel<DXR>); dW one [1600 x B] x [B x 40] GEMM
+        for name, t, mult in (("opg_kernel<FWD> (spn_sum_tc_fwd)", t_fwd, 1), ("opg_kernel<DXL>+<DXR> (spn_sum_tc_bwd_x)", t_bx, 2),
+                              ("sum_tc_bwd_w_kernel (spn_sum_tc_bwd_w, incl. gsum + finish)", t_bw, 1)):
+            ach = mult * fl / (t / 1e3) / 1e12
+            kernels[name] = {"layer": "S_1 (d=16, K=1600, N=40, R=40)", "ms": t, "flops": mult * fl, "achieved_tflops": ach,
+                             "frac": ach / peak, "traffic": ncu.get(name.split(" ")[0])}
         kernels["tc_prepare (logz + operand image)"] = {"ms": t_prep}
-        dom = max(("sum_tc_fwd_kernel", "sum_tc_bwd_x_kernel", "sum_tc_bwd_w_kernel"), key=lambda k: kernels[k]["ms"])
-        roof = {"bound": "tensor", "kernel": f"{dom}<40,40,48> layer S_1 (d=16, K=1600, N=40, R=40), "
-                                             f"2*N*d*c^2*S*R = {fl:.3e} flop per launch",
+        dom = max((k for k in kernels if "flops" in kernels[k]), key=lambda k: kernels[k]["ms"])
+        roof = {"bound": "tensor", "kernel": f"{dom}, layer S_1 (d=16, K=1600, N=40, R=40), "
+                                             f"{kernels[dom]['flops']:.3e} flop per call (2*N*d*c^2*S*R per GEMM)",
                 "achieved": kernels[dom]["achieved_tflops"], "peak": peak, "unit": "TFLOP/s",
                 "frac": kernels[dom]["frac"], "traffic": ncu.get(dom), "kernel_ms": kernels[dom]["ms"],
                 "peak_source": src}

@@ -60,6 +60,7 @@ struct OpgArgs {
     const float* out;      // [d_out][R][B][OC]  (DX: forward output)
     const float* g;        // [d_out][R][B][OC]  (DX: upstream gradient)
     float* y;              // FWD: out;  DX: dx [d_in][R][B][C]
+    uint8_t* hand;         // DXR, optional: per (s, r, tile) the packed eL / eR / G tiles for the dW kernel (see spn_sum_tc_bwd_w)
     int B, d_in, d_out, R;
     int ntiles, nsplit, debug, dbg_n;
 };
@@ -330,8 +331,18 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
                 const uint32_t* my_u = Us + vb * NPAIR * 128 + row;
                 const uint32_t* my_v = Vs + vb * NPAIR * 128 + row;
                 uint32_t V[NPAIR];
+                if (MODE == OPG_FWD) {
 #pragma unroll
-                for (int q = 0; q < NPAIR; ++q) V[q] = my_v[q * 128];
+                    for (int q = 0; q < NPAIR; ++q) V[q] = my_v[q * 128];
+                } else {
+                    // DX: V = G lives in the core-matrix layout of the dW kernel's B operand: [row/8][o/8][row%8][4 words]
+                    const uint4* gv = reinterpret_cast<const uint4*>(Vs + vb * NPAIR * 128 + (row >> 3) * (NVG * 32) + (row & 7) * 4);
+#pragma unroll
+                    for (int og = 0; og < NVG; ++og) {
+                        const uint4 t4 = gv[og * 8];
+                        V[4 * og] = t4.x; V[4 * og + 1] = t4.y; V[4 * og + 2] = t4.z; V[4 * og + 3] = t4.w;
+                    }
+                }
                 TC2_T(t_v);
                 TC2_ADD(0, t_start, t_v);
                 // our stages of this tile; the first half of a stage is multiplied before its slot is known to be free and
@@ -398,8 +409,11 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
             const bool has_mine = half ? has_r : has_l;
             const float* xbase = a.x + ((int64_t)(2 * s + half) * a.R + r) * a.B * C;
             const int nt = tile_end - tile_begin;
-            float v[C];  // this thread's child row of the NEXT tile to be prepared (loaded one tile ahead)
-            {
+            // FWD: this thread's child row of the NEXT tile is loaded one tile ahead (registers).  DX: the loader also needs
+            // out / g slices, so everything of a tile is requested together at its start instead (register budget).
+            constexpr bool PREFETCH = MODE == OPG_FWD;
+            float v[C];
+            if (PREFETCH) {
                 const int64_t b = (int64_t)tile_begin * 128 + row;
                 load_row<C>(xbase + (b < a.B ? b : 0) * C, b < a.B && has_mine && nt > 0, v);
             }
@@ -416,6 +430,7 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
                     uint32_t* my_v = Vs + vb * NPAIR * 128 + row;
                     uint32_t* my_e = Es + vb * NPAIR * 128 + row;
                     float* my_m = Ms + vb * 2 * 128 + row;
+                    if (!PREFETCH) load_row<C>(xbase + bb * C, valid && has_mine, v);
                     uint32_t e[NPAIR];
                     float m = 0.f;
                     if ((a.debug != 4 && a.debug < 7 || a.debug == 9)) m = exp_pack<C>(v, e);
@@ -425,7 +440,8 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
                     }
                     {   // issue the loads of the next tile now; they complete while this tile is finished and stored
                         const int64_t bn = b + 128;
-                        load_row<C>(xbase + (bn < a.B ? bn : 0) * C, bn < a.B && has_mine && i + 1 < nt && (a.debug != 5 && a.debug < 7 || a.debug == 9), v);
+                        if (PREFETCH)
+                            load_row<C>(xbase + (bn < a.B ? bn : 0) * C, bn < a.B && has_mine && i + 1 < nt && (a.debug != 5 && a.debug < 7 || a.debug == 9), v);
                         if (i + 2 < nt && b + 256 < a.B && has_mine) {
                             const char* nx = reinterpret_cast<const char*>(xbase + (b + 256) * C);
                             prefetch_l2(nx);
@@ -433,6 +449,7 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
                         }
                     }
                     mbar_wait_sticky(vec_empty + vb, ((n_tile >> 1) & 1) ^ 1, abort_flag);  // generators are done with tile n - 2
+                    if (MODE == OPG_DXR && a.hand && warp == 8 && lane == 0) bulk_wait_group_read<1>();  // ... and so is the TMA store
                     // every loader thread has finished the epilogue that read this buffer (partner rows' shift / scale)
                     named_bar_sync(1, 256);
                     my_m[half * 128] = m;
@@ -443,23 +460,52 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
                     if (MODE != OPG_FWD) {
                         // G = g * exp(shift - out) = g / (linear-domain sum); out = -inf (impossible row): no gradient.  The
                         // exponent is capped so that rows whose sum underflowed in the forward (rescue path) stay finite.
-                        const float* op = a.out + (((int64_t)s * a.R + r) * a.B + bb) * C + half * HC;
-                        const float* gp = a.g + (((int64_t)s * a.R + r) * a.B + bb) * C + half * HC;
-                        float vo[HC], vg[HC];
-                        load_row<HC>(op, valid, vo);
-                        load_row<HC>(gp, valid, vg);
+                        // Half 0 produces the o-groups [0, GH0), half 1 [GH0, NVG) (whole 16-byte chunks of 8 outputs), written
+                        // in the core-matrix layout [row/8][o/8][row%8][8 bf16] that the dW kernel's B operand uses.
+                        constexpr int GH0 = (NVG + 1) / 2;
+                        constexpr int NGH = GH0;                       // chunks handled per half (half 1 may have fewer)
+                        const int og0 = half ? GH0 : 0;
+                        const int nog = half ? NVG - GH0 : GH0;
+                        const float* op = a.out + (((int64_t)s * a.R + r) * a.B + bb) * C + og0 * 8;
+                        const float* gp = a.g + (((int64_t)s * a.R + r) * a.B + bb) * C + og0 * 8;
+                        float vo[NGH * 8], vg[NGH * 8];
+#pragma unroll
+                        for (int q = 0; q < NGH * 2; ++q) {
+                            const bool on = valid && q < 2 * nog;
+                            const float4 t4 = on ? __ldg(reinterpret_cast<const float4*>(op) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 u4 = on ? __ldg(reinterpret_cast<const float4*>(gp) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            vo[4 * q] = t4.x; vo[4 * q + 1] = t4.y; vo[4 * q + 2] = t4.z; vo[4 * q + 3] = t4.w;
+                            vg[4 * q] = u4.x; vg[4 * q + 1] = u4.y; vg[4 * q + 2] = u4.z; vg[4 * q + 3] = u4.w;
+                        }
                         named_bar_sync(2, 256);  // both shifts are in shared memory
                         const float sh2 = (my_m[0] + my_m[128]) * 1.4426950408889634f;
+                        uint4* gdst = reinterpret_cast<uint4*>(Vs + vb * NPAIR * 128 + (row >> 3) * (NVG * 32) + (row & 7) * 4);
 #pragma unroll
-                        for (int q = 0; q < HC / 2; ++q) {
-                            const float o0 = vo[2 * q], o1 = vo[2 * q + 1];
-                            const float g0v = o0 == -CUDART_INF_F ? 0.f : vg[2 * q] * ex2_approx(fminf(fmaf(o0, -1.4426950408889634f, sh2), 115.f));
-                            const float g1v = o1 == -CUDART_INF_F ? 0.f : vg[2 * q + 1] * ex2_approx(fminf(fmaf(o1, -1.4426950408889634f, sh2), 115.f));
-                            my_v[(half * (HC / 2) + q) * 128] = pack_bf16(g0v, g1v);
+                        for (int og = 0; og < NGH; ++og) {
+                            uint32_t w4[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float o0 = vo[8 * og + 2 * q], o1 = vo[8 * og + 2 * q + 1];
+                                const float g0v = (!valid || o0 == -CUDART_INF_F) ? 0.f : vg[8 * og + 2 * q] * ex2_approx(fminf(fmaf(o0, -1.4426950408889634f, sh2), 115.f));
+                                const float g1v = (!valid || o1 == -CUDART_INF_F) ? 0.f : vg[8 * og + 2 * q + 1] * ex2_approx(fminf(fmaf(o1, -1.4426950408889634f, sh2), 115.f));
+                                w4[q] = pack_bf16(g0v, g1v);
+                            }
+                            if (og < nog) gdst[(og0 + og) * 8] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                         }
                     }
+                    if (MODE == OPG_DXR && a.hand) fence_proxy_async();  // the row vectors are also read by the TMA engine below
                     __syncwarp();
                     if (lane == 0) mbar_arrive(vec_full + vb);
+                    if (MODE == OPG_DXR && a.hand && warp == 8 && lane == 0) {
+                        // hand the packed eL / eR / G tiles of this row tile to the dW kernel: three bulk stores by the TMA
+                        // engine once all eight loader warps have written them (the barrier completes on the 8th arrival)
+                        mbar_wait_sticky(vec_full + vb, (n_tile >> 1) & 1, abort_flag);
+                        uint8_t* dst = a.hand + ((size_t)sr * a.ntiles + tile) * (3 * NPAIR * 512);
+                        bulk_s2g(dst, Us + vb * NPAIR * 128, NPAIR * 512);
+                        bulk_s2g(dst + NPAIR * 512, Es + vb * NPAIR * 128, NPAIR * 512);
+                        bulk_s2g(dst + 2 * NPAIR * 512, Vs + vb * NPAIR * 128, NPAIR * 512);
+                        bulk_commit_group();
+                    }
                     ++n_tile;
                     TC2_T(t_p1);
                     TC2_ADD(0, t_p0, t_p1);
@@ -532,6 +578,7 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
         }
     }
     // teardown
+    if (MODE == OPG_DXR && warp == 8 && lane == 0) bulk_wait_group<0>();
     if (warp == 0) TC2_FLUSH(0);
     if (warp == 8) TC2_FLUSH(6);
     if (warp == 16) TC2_FLUSH(12);
@@ -716,12 +763,16 @@ extern "C" int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw,
     return dispatch_opg<OPG_FWD>(c, a, (cudaStream_t)stream);
 }
 
+extern "C" int64_t spn_sum_tc_hand_bytes(int B, int d_out, int c, int R) {
+    return (int64_t)d_out * R * ((B + 127) / 128) * 3 * (c / 2) * 512;
+}
+
 extern "C" int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g, const void* wimg, int B, int d_in,
-                                int d_out, int c, int oc, int R, float* dx, void* stream) {
+                                int d_out, int c, int oc, int R, float* dx, void* hand, void* stream) {
     if (!x || !out || !g || !wimg || !dx || B <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
     if (!spn_sum_tc_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
     OpgArgs a{};
-    a.x = x; a.wimg = (const uint8_t*)wimg; a.out = out; a.g = g; a.y = dx;
+    a.x = x; a.wimg = (const uint8_t*)wimg; a.out = out; a.g = g; a.y = dx; a.hand = (uint8_t*)hand;
     a.B = B; a.d_in = d_in; a.d_out = d_out; a.R = R;
     opg_split(a, B, d_out, R);
     int rc = dispatch_opg<OPG_DXL>(c, a, (cudaStream_t)stream);

@@ -1,17 +1,10 @@
 // dW of the shared-weight CrossProduct+Sum layer on the tensor cores (tcgen05 + TMEM); see sum_tc2.cu for the forward
 // and dX formulation.  With E[b,k] = eL[b,l] eR[b,r'] (k = l*c + r'), W = exp(log-weights) and
-// G[b,o] = g[b,o] * exp(mL + mR - out[b,o])  (= g / linear-domain sum), SURVEY A.5 becomes two GEMMs:
+// G[b,o] = g[b,o] * exp(mL + mR - out[b,o])  (= g / linear-domain sum), SURVEY A.5 gives
 //
-//   dX:  dE[b,k] = sum_o G[b,o] W[k,o]            (M = 128 rows, N = k-chunk, K = o)      -> spn_sum_tc_bwd_x
-//        dxL[b,l] = eL[b,l] * sum_r' eR[b,r'] dE[b,l,r'],  dxR[b,r'] = eR[b,r'] * sum_l eL[b,l] dE[b,l,r']
-//   dW:  dWlin[k,o] = sum_b E[b,k] G[b,o]         (M = k-chunk of 128, N = o, K = rows)   -> spn_sum_tc_bwd_w
-//        d(log w)[k,o] = W[k,o] * dWlin[k,o]      (applied by the layout-restoring epilogue kernel)
-//
-// dX reuses the forward's weight image as a K-major B operand (same bytes, other descriptor); its A operand (G) is
-// written to TMEM once per tile and the 128 x N fp32 product is consumed straight out of TMEM by the CUDA cores.
-// dW contracts over the batch, so both operands are generated per row into shared memory (MN-major core matrices:
-// one 16-byte store per 8 elements, conflict free) and the accumulators for up to 7 k-chunks stay resident in TMEM
-// while the CTA walks over every batch tile.
+//   dWlin[k,o] = sum_b E[b,k] G[b,o]         (M = k-chunk of 128, N = o, K = rows)   -> spn_sum_tc_bwd_w
+//   d(log w)[k,o] = W[k,o] * dWlin[k,o]      (applied by the layout-restoring epilogue kernel, which also fuses the
+//                                             softmax backward of the weight normalisation)
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -21,109 +14,94 @@ using namespace tc;
 __device__ int g_tc_bwd_aborts = 0;
 
 struct TcBwdArgs {
-    const float* x;       // [d_in][R][B][C]
-    const float* out;     // [d_out][R][B][OC]
-    const float* g;       // [d_out][R][B][OC]
-    const uint8_t* wimg;  // forward weight image (dX only)
-    float* dx;            // [d_in][R][B][C]                (dX)
-    float* dwt;           // [d_out][R][K][OC] linear-domain weight gradient (dW)
+    const uint8_t* hand;  // per (s, r, row tile): packed eL, eR ([pair][128 rows] words) and G (B-operand layout) from the dX kernel
+    float* dwt;           // [d_out][R][K][OC] linear-domain weight gradient
     int B, d_in, d_out, R;
-    int ntiles, nsplit;
+    int ntiles, debug;    // debug (SPN_TC_DEBUG, timing experiments only): 1 no MMA issue, 3 generators idle
 };
 
-// Recompute the forward's per-row quantities: packed bf16 eL / eR, and G = g * exp(mL + mR - out) packed bf16.
-template <int C, int OC, int NPAD>
-__device__ __forceinline__ void tc_bwd_prologue(const TcBwdArgs& a, int s, int r, int64_t b, bool valid, uint32_t* eL,
-                                                uint32_t* eR, uint32_t* Gp) {
-    const bool has_l = 2 * s < a.d_in, has_r = 2 * s + 1 < a.d_in;
-    const float* xl = a.x + (((int64_t)(2 * s) * a.R + r) * a.B + (valid ? b : 0)) * C;
-    const float* xr = a.x + (((int64_t)(2 * s + 1) * a.R + r) * a.B + (valid ? b : 0)) * C;
-    const float* op = a.out + (((int64_t)s * a.R + r) * a.B + (valid ? b : 0)) * OC;
-    const float* gp = a.g + (((int64_t)s * a.R + r) * a.B + (valid ? b : 0)) * OC;
-    float vl[C], vr[C];
-#pragma unroll
-    for (int q = 0; q < C / 4; ++q) {
-        const float4 t = (valid && has_l) ? reinterpret_cast<const float4*>(xl)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-        vl[4 * q] = t.x; vl[4 * q + 1] = t.y; vl[4 * q + 2] = t.z; vl[4 * q + 3] = t.w;
-    }
-#pragma unroll
-    for (int q = 0; q < C / 4; ++q) {
-        const float4 t = (valid && has_r) ? reinterpret_cast<const float4*>(xr)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-        vr[4 * q] = t.x; vr[4 * q + 1] = t.y; vr[4 * q + 2] = t.z; vr[4 * q + 3] = t.w;
-    }
-    float m = vl[0], m2 = vr[0];
-#pragma unroll
-    for (int q = 1; q < C; ++q) { m = fmaxf(m, vl[q]); m2 = fmaxf(m2, vr[q]); }
-    const float mL = (m == -CUDART_INF_F) ? 0.f : m;
-    const float mR = (m2 == -CUDART_INF_F) ? 0.f : m2;
-#pragma unroll
-    for (int q = 0; q < C / 2; ++q) {
-        eL[q] = pack_bf16(__expf(vl[2 * q] - mL), __expf(vl[2 * q + 1] - mL));
-        eR[q] = pack_bf16(__expf(vr[2 * q] - mR), __expf(vr[2 * q + 1] - mR));
-    }
-    const float shift = mL + mR;
-    float G[NPAD];
-#pragma unroll
-    for (int q = 0; q < OC / 4; ++q) {
-        const float4 o4 = valid ? reinterpret_cast<const float4*>(op)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 g4 = valid ? reinterpret_cast<const float4*>(gp)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-        // out = -inf (impossible row): no gradient.  exp argument <= ~0 whenever out is finite.
-        // G = g / (linear-domain sum) = g * exp(shift - out) >= g.  out = -inf (impossible row): no gradient.  The
-        // exponent is capped so that rows whose sum underflowed in the forward (rescue path) stay finite.
-        G[4 * q] = o4.x == -CUDART_INF_F ? 0.f : g4.x * __expf(fminf(shift - o4.x, 80.f));
-        G[4 * q + 1] = o4.y == -CUDART_INF_F ? 0.f : g4.y * __expf(fminf(shift - o4.y, 80.f));
-        G[4 * q + 2] = o4.z == -CUDART_INF_F ? 0.f : g4.z * __expf(fminf(shift - o4.z, 80.f));
-        G[4 * q + 3] = o4.w == -CUDART_INF_F ? 0.f : g4.w * __expf(fminf(shift - o4.w, 80.f));
-    }
-#pragma unroll
-    for (int q = OC; q < NPAD; ++q) G[q] = 0.f;
-#pragma unroll
-    for (int q = 0; q < NPAD / 2; ++q) Gp[q] = pack_bf16(G[2 * q], G[2 * q + 1]);
+// Issues the 8 MMAs (K = 16 rows each) of one (tile, chunk): D[128 k x NPAD] (+)= A[128 k x 128 rows] * B[128 rows x NPAD],
+// both operands MN-major in shared memory, from ONE PTX block (uniform-register issue path, see sum_tc2.cu).
+__device__ __forceinline__ void dw_issue_chunk(uint32_t dcol, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate_first,
+                                               uint32_t bstep) {
+#define DW_LINE(AOFF, T)                                                                                              \
+    "add.s64 da, %1, " #AOFF ";\n\tmad.wide.u32 db, %5, " #T ", %2;\n\t"                                              \
+    "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, {%6, %6, %6, %6}, p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+    asm volatile(
+        "{\n\t.reg .pred q, p;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        DW_LINE(0, 0) DW_LINE(256, 1) DW_LINE(512, 2) DW_LINE(768, 3) DW_LINE(1024, 4) DW_LINE(1280, 5) DW_LINE(1536, 6) DW_LINE(1792, 7)
+        "}" ::"r"(dcol), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(bstep), "r"(0u)
+        : "memory");
+#undef DW_LINE
 }
 
 // ================================================================================================================
 // dW
 // ================================================================================================================
 // The k axis (c*c products) is split into 8x8 blocks (8 left channels x 8 right channels); a chunk is two blocks =
-// 128 k-values = the M extent of one MMA.  chunk -> k mapping (also used by tc_dw_finish_kernel):
+// 128 k-values = the M extent of one MMA.  chunk -> k mapping (also used by the epilogue):
 //   block = 2*chunk + m/64, l = 8*(block / (C/8)) + (m%64)/8, r' = 8*(block % (C/8)) + m%8, k = l*C + r'.
-// One work item = (scope, repetition, group of <= GC chunks); it walks over all row tiles and keeps its accumulators
-// in TMEM.  Warps 0-3 / 4-7 produce the operands of alternating tiles into shared memory, warp 8 issues every MMA.
+// One work item = (scope, repetition, group of <= GC chunks); it walks over all row tiles and keeps its accumulators in
+// TMEM.  Both operands contract over the batch, so the A operand E[row, k] = eL[row, l] * eR[row, r'] is generated per row
+// into shared memory (MN-major core matrices: one 16-byte store per 8 elements); the kernel is bound by shared-memory
+// bandwidth (A is written once and read once by the tensor core: ~0.8 MB per 128-row tile), not by the tensor pipe.
+//
+// The per-row inputs are NOT recomputed here: the dX kernel that runs just before (sum_tc2.cu, mode DXR) hands over, per
+// (scope, repetition, row tile), the packed bf16 vectors eL, eR ([pair][row] words) and G = g * exp(shift - out) already in
+// the core-matrix layout of this kernel's B operand.  Three TMA bulk copies per tile bring them into shared memory, so
+// this kernel has no global-load instructions, no exp and no prologue at all (one row per thread with 16-byte loads of
+// four fp32 arrays cost ~5000 L1 wavefronts per tile and was the limiter of the previous version).
+// Thread organisation (10 warps):
+//   warps 0-7   GENERATORS: two sets of 128 threads (one per row) that take alternate (tile, chunk) stages: bf16x2
+//               multiplies of the row's eL / eR sub-vectors -> 16-byte stores into the 4-deep A ring; at the end of the
+//               item they run the epilogue (TMEM -> linear-domain weight gradient).
+//   warp 8      TMA: streams the hand-off tiles (double buffered).
+//   warp 9      MMA issuer.
 template <int C, int OC, int NPAD, int GC>
-__global__ void __launch_bounds__(288, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int ngroups) {
-    constexpr int NG = NPAD / 8;
+__global__ void __launch_bounds__(320, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int ngroups) {
     constexpr int K = C * C;
-    constexpr int NBLK = (C / 8) * (C / 8);
+    constexpr int CB = C / 8;                  // 8-channel blocks per child = o-groups of the G tile
+    constexpr int NBLK = CB * CB;
     constexpr int NCHUNK = (NBLK + 1) / 2;
+    constexpr int NPAIR = C / 2;
     constexpr int A_BYTES = 128 * 128 * 2;     // [16 row-groups][16 m-groups][8][8] bf16
-    constexpr int G_BYTES = 128 * NPAD * 2;    // [16 row-groups][NG][8][8] bf16
-    constexpr int NSTA = 2;                    // A stages per warpgroup
-    static_assert(GC * NPAD <= 512, "TMEM budget exceeded");
+    constexpr int V_BYTES = NPAIR * 512;       // one hand-off tile: eL / eR as [pair][128 rows] words, G as [16][CB][8][8] bf16
+    constexpr int G_BYTES = V_BYTES + 1024;    // + aliased N-group overrun (N = NPAD > OC reads one block past the tile)
+    constexpr int NSTA = 4;                    // A ring depth
+    static_assert(GC * NPAD <= 512 && OC == C, "unsupported shape");
     constexpr uint32_t IDESC = instr_desc_bf16(128, NPAD, 1, 1);
 
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* abuf = smem;                                   // [2 wg][NSTA][A_BYTES]
-    uint8_t* gbuf = smem + 2 * NSTA * A_BYTES;              // [2 wg][G_BYTES]
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(gbuf + 2 * G_BYTES);  // [2][NSTA]
-    uint64_t* bar_empty = bar_full + 2 * NSTA;                              // [2][NSTA]
-    uint64_t* bar_gfree = bar_empty + 2 * NSTA;                             // [2] G tile no longer read
-    uint64_t* bar_done = bar_gfree + 2;                                     // [1] all MMAs of the item complete
+    uint8_t* abuf = smem;                                                     // [NSTA][A_BYTES]
+    uint8_t* gbuf = smem + NSTA * A_BYTES;                                    // [2][G_BYTES]
+    uint32_t* Ls = reinterpret_cast<uint32_t*>(gbuf + 2 * G_BYTES);           // [2][NPAIR][128] packed eL
+    uint32_t* Rs = Ls + 2 * NPAIR * 128;                                      // [2][NPAIR][128] packed eR
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(Rs + 2 * NPAIR * 128);     // [NSTA] generators -> MMA
+    uint64_t* a_empty = a_full + NSTA;                                        // [NSTA] MMA commit -> generators
+    uint64_t* vec_full = a_empty + NSTA;                                      // [2] TMA -> generators, MMA
+    uint64_t* vec_empty = vec_full + 2;                                       // [2] generators -> TMA
+    uint64_t* g_empty = vec_empty + 2;                                        // [2] MMA commit -> TMA
+    uint64_t* bar_done = g_empty + 2;                                         // [1] all MMAs of the item complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 1);
     volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 * NSTA; ++i) {
-            mbar_init(bar_full + i, 4);
-            mbar_init(bar_empty + i, 1);
+        for (int i = 0; i < NSTA; ++i) {
+            mbar_init(a_full + i, 4);
+            mbar_init(a_empty + i, 1);
         }
-        mbar_init(bar_gfree + 0, 1);
-        mbar_init(bar_gfree + 1, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(vec_full + i, 1);
+            mbar_init(vec_empty + i, 8);
+            mbar_init(g_empty + i, 1);
+        }
         mbar_init(bar_done, 1);
         *abort_flag = 0;
         mbar_fence_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    if (warp == 9) tmem_alloc(tmem_slot, 512);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -132,9 +110,8 @@ __global__ void __launch_bounds__(288, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
     __syncthreads();
 
     const int nitems = a.d_out * a.R * ngroups;
-    uint32_t n_stage[2] = {0, 0};   // producer: own counter in [0]; MMA warp: one per warpgroup
-    uint32_t n_gtile[2] = {0, 0};
-    uint32_t items_done = 0;
+    uint32_t n_stage = 0, n_tile = 0, items_done = 0;   // per-role ring positions (persist across items)
+    uint32_t m_stage = 0, m_tile = 0;                   // the MMA warp's own counters (kept warp-uniform)
 
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++items_done) {
         const int grp = item % ngroups;
@@ -142,126 +119,123 @@ __global__ void __launch_bounds__(288, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
         const int r = sr % a.R, s = sr / a.R;
         const int chunk_begin = grp * GC;
         const int chunk_end = min(NCHUNK, chunk_begin + GC);
-        __syncthreads();
+        const int nch = chunk_end - chunk_begin;
+        __syncthreads();  // the previous item (incl. its epilogue reads of TMEM) is finished by every role
         if (__shfl_sync(0xffffffffu, *abort_flag, 0)) break;
-        if (warp == 8) {
-            // ---------------------------------------- MMA issuer ----------------------------------------
+        if (warp == 9) {
+            // =============================================== MMA issuer ===============================================
             const uint32_t abuf_addr = smem_u32(abuf), gbuf_addr = smem_u32(gbuf);
-            for (int t0 = 0; t0 < a.ntiles; t0 += 2) {
-#pragma unroll
-                for (int wg = 0; wg < 2; ++wg) {
-                    const int tile = t0 + wg;
-                    if (tile >= a.ntiles) continue;
-                    for (int ch = chunk_begin; ch < chunk_end; ++ch) {
-                        const uint32_t st = n_stage[wg] % NSTA, par = (n_stage[wg] / NSTA) & 1;
-                        mbar_wait_sticky(bar_full + wg * NSTA + st, par, abort_flag);
-                        fence_after_sync();
-                        const uint32_t aaddr = abuf_addr + (wg * NSTA + st) * A_BYTES;
-                        const uint32_t gaddr = gbuf_addr + wg * G_BYTES;
-                        const uint32_t dcol = tmem_base + (ch - chunk_begin) * NPAD;
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            // A[M = k, K = row] MN-major: 8-element groups along M are 128 B apart, 8-row groups along K 2048 B
-                            const uint64_t adesc = smem_desc(aaddr + (uint32_t)(2 * t) * 2048, 2048, 128);
-                            // B[K = row, N = o] MN-major: 8-element groups along N 128 B apart, 8-row groups NG*128 B
-                            const uint64_t bdesc = smem_desc(gaddr + (uint32_t)(2 * t) * (NG * 128), NG * 128, 128);
-                            mma_ss_uniform(dcol, adesc, bdesc, IDESC, (tile | t) ? 1u : 0u);
-                        }
-                        mma_commit_uniform(bar_empty + wg * NSTA + st);
-                        ++n_stage[wg];
-                    }
-                    mma_commit_uniform(bar_gfree + wg);
+            for (int tile = 0; tile < a.ntiles; ++tile, ++m_tile) {
+                const uint32_t vb = m_tile & 1;
+                mbar_wait_sticky(vec_full + vb, (m_tile >> 1) & 1, abort_flag);   // G operand tile of this row tile
+                fence_after_sync();
+                // B[K = row, N = o] MN-major: 8-element groups along N 128 B apart, 8-row groups CB*128 B
+                const uint64_t bdesc = smem_desc(gbuf_addr + vb * G_BYTES, CB * 128, 128);
+#pragma unroll 1
+                for (int ch = 0; ch < nch; ++ch, ++m_stage) {
+                    const uint32_t st = m_stage % NSTA, par = (m_stage / NSTA) & 1;
+                    mbar_wait_sticky(a_full + st, par, abort_flag);
+                    fence_after_sync();
+                    // A[M = k, K = row] MN-major: 8-element groups along M are 128 B apart, 8-row groups along K 2048 B
+                    const uint64_t adesc = smem_desc(abuf_addr + st * A_BYTES, 2048, 128);
+                    if (a.debug != 1) dw_issue_chunk(tmem_base + ch * NPAD, adesc, bdesc, IDESC, tile ? 1u : 0u, (2 * CB * 128) >> 4);
+                    mma_commit_uniform(a_empty + st);
                 }
+                mma_commit_uniform(g_empty + vb);
             }
             mma_commit_uniform(bar_done);
-        } else {
-            // ---------------------------------------- operand producers ----------------------------------------
-            const int wg = warp >> 2;
-            const int row = threadIdx.x & 127;
-            uint8_t* my_g = gbuf + wg * G_BYTES + ((row >> 3) * NG) * 128 + (row & 7) * 16;
-            for (int tile = wg; tile < a.ntiles; tile += 2) {
-                const int64_t b = (int64_t)tile * 128 + row;
-                const bool valid = b < a.B;
-                uint32_t eL[C / 2], eR[C / 2], Gp[NPAD / 2];
-                tc_bwd_prologue<C, OC, NPAD>(a, s, r, b, valid, eL, eR, Gp);
-                if (!valid) {
-#pragma unroll
-                    for (int q = 0; q < NPAD / 2; ++q) Gp[q] = 0u;  // rows past the batch contribute nothing
+        } else if (warp == 8) {
+            // =============================================== TMA ===============================================
+            for (int tile = 0; tile < a.ntiles; ++tile, ++n_tile) {
+                const uint32_t vb = n_tile & 1;
+                // the buffers of tile n - 2 must have been consumed: row vectors by the generators, G tile by the MMAs
+                mbar_wait_sticky(vec_empty + vb, ((n_tile >> 1) & 1) ^ 1, abort_flag);
+                mbar_wait_sticky(g_empty + vb, ((n_tile >> 1) & 1) ^ 1, abort_flag);
+                if (lane == 0) {
+                    const uint8_t* src = a.hand + ((size_t)sr * a.ntiles + tile) * (3 * V_BYTES);
+                    mbar_arrive_expect_tx(vec_full + vb, 3 * V_BYTES);
+                    bulk_g2s(Ls + vb * NPAIR * 128, src, V_BYTES, vec_full + vb);
+                    bulk_g2s(Rs + vb * NPAIR * 128, src + V_BYTES, V_BYTES, vec_full + vb);
+                    bulk_g2s(gbuf + vb * G_BYTES, src + 2 * V_BYTES, V_BYTES, vec_full + vb);
                 }
-                // G tile of the previous tile of this warpgroup must have been consumed
-                mbar_wait_sticky(bar_gfree + wg, (n_gtile[0] & 1) ^ 1, abort_flag);
-                ++n_gtile[0];
-#pragma unroll
-                for (int og = 0; og < NG; ++og)
-                    *reinterpret_cast<uint4*>(my_g + og * 128) = make_uint4(Gp[4 * og], Gp[4 * og + 1], Gp[4 * og + 2], Gp[4 * og + 3]);
-#pragma unroll 1
-                for (int ch = chunk_begin; ch < chunk_end; ++ch) {
-                    const uint32_t st = n_stage[0] % NSTA, par = (n_stage[0] / NSTA) & 1;
-                    mbar_wait_sticky(bar_empty + wg * NSTA + st, par ^ 1, abort_flag);
-                    uint8_t* my_a = abuf + (wg * NSTA + st) * A_BYTES + ((row >> 3) * 16) * 128 + (row & 7) * 16;
+                __syncwarp();
+            }
+        } else {
+            // =============================================== generators ===============================================
+            const uint32_t gsel = warp >> 2;          // this set produces the stages with n_stage % 2 == gsel
+            const int row = (warp & 3) * 32 + lane;
+            for (int tile = 0; tile < a.ntiles; ++tile, ++n_tile) {
+                const uint32_t vb = n_tile & 1;
+                mbar_wait_sticky(vec_full + vb, (n_tile >> 1) & 1, abort_flag);
+                const uint32_t* my_l = Ls + vb * NPAIR * 128 + row;
+                const uint32_t* my_r = Rs + vb * NPAIR * 128 + row;
+                for (int i = (int)((gsel - n_stage) & 1); i < nch; i += 2) {
+                    const int ch = chunk_begin + i;
+                    const uint32_t ns = n_stage + i;
+                    const uint32_t st = ns % NSTA, use = ns / NSTA;
+                    // the eL / eR sub-vectors of the chunk's two 8x8 blocks (fetched before the slot wait)
+                    uint32_t el4[2][4], er4[2][4];
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         const int blk = 2 * ch + half;
-                        const int lb = blk / (C / 8), rb = blk % (C / 8);
-                        // eR for r' in [8 rb, 8 rb + 8): 4 packed registers, selected without dynamic register indexing
-                        uint32_t er[4], el4[4];
+                        const bool on = blk < NBLK;
+                        const int lb = on ? blk / CB : 0, rb = on ? blk % CB : 0;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) { er[q] = 0u; el4[q] = 0u; }
-#pragma unroll
-                        for (int j = 0; j < C / 8; ++j) {
-                            if (j == rb && blk < NBLK) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) er[q] = eR[4 * j + q];
-                            }
-                            if (j == lb && blk < NBLK) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) el4[q] = eL[4 * j + q];
-                            }
+                        for (int q = 0; q < 4; ++q) {
+                            el4[half][q] = on ? my_l[(4 * lb + q) * 128] : 0u;
+                            er4[half][q] = on ? my_r[(4 * rb + q) * 128] : 0u;
                         }
+                    }
+                    mbar_wait_sticky(a_empty + st, (use & 1) ^ 1, abort_flag);
+                    uint8_t* my_a = abuf + st * A_BYTES + ((row >> 3) * 16) * 128 + (row & 7) * 16;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        if (a.debug == 3) continue;
 #pragma unroll
                         for (int li = 0; li < 8; ++li) {
-                            const uint32_t e = el4[li >> 1];
+                            const uint32_t e = el4[half][li >> 1];
                             const uint32_t l2 = (li & 1) ? bcast_hi(e) : bcast_lo(e);
                             *reinterpret_cast<uint4*>(my_a + (half * 8 + li) * 128) =
-                                make_uint4(hmul2_bf16(l2, er[0]), hmul2_bf16(l2, er[1]), hmul2_bf16(l2, er[2]), hmul2_bf16(l2, er[3]));
+                                make_uint4(hmul2_bf16(l2, er4[half][0]), hmul2_bf16(l2, er4[half][1]), hmul2_bf16(l2, er4[half][2]),
+                                           hmul2_bf16(l2, er4[half][3]));
                         }
                     }
                     fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_full + wg * NSTA + st);
-                    ++n_stage[0];
+                    if (lane == 0) mbar_arrive(a_full + st);
                 }
+                n_stage += nch;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(vec_empty + vb);  // eL / eR of this tile are no longer read by this warp
             }
             // ---------------------------------------- epilogue: TMEM -> dwt ----------------------------------------
             mbar_wait_sticky(bar_done, items_done & 1, abort_flag);
-            {
-                fence_after_sync();
-                const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-                for (int ch = chunk_begin + wg; ch < chunk_end; ch += 2) {
-                    uint32_t v[NPAD];
+            fence_after_sync();
+            const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+            for (int ch = chunk_begin + (int)gsel; ch < chunk_end; ch += 2) {
+                uint32_t v[NPAD];
 #pragma unroll
-                    for (int q = 0; q < NPAD / 8; ++q) tmem_ld8(tmem_base + lane_base + (ch - chunk_begin) * NPAD + q * 8, v + q * 8);
-                    tmem_wait_ld();
-                    const int blk = 2 * ch + (row >> 6);
-                    if (blk < NBLK) {
-                        const int l = 8 * (blk / (C / 8)) + ((row & 63) >> 3);
-                        const int rp = 8 * (blk % (C / 8)) + (row & 7);
-                        float* dst = a.dwt + (((int64_t)s * a.R + r) * K + (l * C + rp)) * OC;
+                for (int q = 0; q < NPAD / 8; ++q) tmem_ld8(tmem_base + lane_base + (ch - chunk_begin) * NPAD + q * 8, v + q * 8);
+                tmem_wait_ld();
+                const int blk = 2 * ch + (row >> 6);
+                if (blk < NBLK) {
+                    const int l = 8 * (blk / CB) + ((row & 63) >> 3);
+                    const int rp = 8 * (blk % CB) + (row & 7);
+                    float* dst = a.dwt + (((int64_t)s * a.R + r) * K + (l * C + rp)) * OC;
 #pragma unroll
-                        for (int q = 0; q < OC / 4; ++q)
-                            reinterpret_cast<float4*>(dst)[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                                                            __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-                    }
+                    for (int q = 0; q < OC / 4; ++q)
+                        reinterpret_cast<float4*>(dst)[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                                        __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
                 }
-                fence_before_sync();
             }
+            fence_before_sync();
         }
     }
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     if (threadIdx.x == 0 && *abort_flag) atomicAdd(&g_tc_bwd_aborts, 1);
-    if (warp == 8) tmem_dealloc(tmem_base, 512);
+    if (warp == 9) tmem_dealloc(tmem_base, 512);
 }
 
 // csum[s][o][r] = sum over rows b with out > -inf of g[s][r][b][o].  For normalised weights lw = param - logz the
@@ -344,7 +318,7 @@ template <int C, int OC, int NPAD, int GC>
 static int launch_bwd_w(const TcBwdArgs& a, cudaStream_t st) {
     constexpr int NCHUNK = ((C / 8) * (C / 8) + 1) / 2;
     constexpr int NGROUPS = (NCHUNK + GC - 1) / GC;
-    constexpr int SMEM = 2 * 2 * 128 * 128 * 2 + 2 * 128 * NPAD * 2 + (4 * 2 + 3) * 8 + 16;
+    constexpr int SMEM = 4 * 128 * 128 * 2 + 2 * ((C / 2) * 512 + 1024) + 2 * 2 * (C / 2) * 512 + (2 * 4 + 7) * 8 + 16;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(sum_tc_bwd_w_kernel<C, OC, NPAD, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -355,20 +329,23 @@ static int launch_bwd_w(const TcBwdArgs& a, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int nitems = a.d_out * a.R * NGROUPS;
-    sum_tc_bwd_w_kernel<C, OC, NPAD, GC><<<nitems < sms ? nitems : sms, 288, SMEM, st>>>(a, NGROUPS);
+    sum_tc_bwd_w_kernel<C, OC, NPAD, GC><<<nitems < sms ? nitems : sms, 320, SMEM, st>>>(a, NGROUPS);
     return spn_launch_status();
 }
 
-extern "C" int spn_sum_tc_bwd_w(const float* x, const float* out, const float* g, const float* lw, const float* logz,
+extern "C" int spn_sum_tc_bwd_w(const void* hand, const float* out, const float* g, const float* lw, const float* logz,
                                 int B, int d_in, int d_out, int c, int oc, int R, float* dwt_workspace, float* dlw,
                                 void* stream) {
-    if (!x || !out || !g || !lw || !dwt_workspace || !dlw || B <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
+    if (!hand || !out || !g || !lw || !dwt_workspace || !dlw || B <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
     if (!spn_sum_tc_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
     TcBwdArgs a{};
-    a.x = x; a.out = out; a.g = g; a.dwt = dwt_workspace;
+    a.hand = (const uint8_t*)hand; a.dwt = dwt_workspace;
     a.B = B; a.d_in = d_in; a.d_out = d_out; a.R = R;
     a.ntiles = (B + 127) / 128;
-    a.nsplit = 1;
+    {
+        const char* dbg = getenv("SPN_TC_DEBUG");
+        a.debug = dbg ? atoi(dbg) : 0;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (c == 40) rc = launch_bwd_w<40, 40, 48, 7>(a, st);

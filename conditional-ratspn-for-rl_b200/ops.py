@@ -212,9 +212,12 @@ class SumTcFn(torch.autograd.Function):
         x, w, out, wimg, logz = ctx.saved_tensors
         logz = logz if ctx.raw else None
         g = _f32c(g)
-        dx = tc_sum_backward_x(x, out, g, wimg, w) if ctx.needs_input_grad[0] else None
-        dw = tc_sum_backward_w(x, out, g, w, logz) if ctx.needs_input_grad[1] else None
-        return dx, dw, None, None
+        # the dX kernel also hands its packed per-row vectors (exp(x - max), G) to the dW kernel, which recomputes nothing
+        need_dw = ctx.needs_input_grad[1]
+        hand = tc_hand_buffer(x, out) if need_dw else None
+        dx = tc_sum_backward_x(x, out, g, wimg, w, hand) if (ctx.needs_input_grad[0] or need_dw) else None
+        dw = tc_sum_backward_w(hand, x, out, g, w, logz) if need_dw else None
+        return (dx if ctx.needs_input_grad[0] else None), dw, None, None
 
 
 class RootSharedFn(torch.autograd.Function):
@@ -398,27 +401,36 @@ def tc_sum_forward(x: torch.Tensor, wimg: torch.Tensor, lw: torch.Tensor, logz: 
     return out
 
 
-def tc_sum_backward_x(x, out, g, wimg, lw):
-    """dL/dx of tc_sum_forward, [d_in, R, B, c] (tensor-core GEMM dE = G W^T + in-register reduction)."""
-    require_cuda(x, out, g, wimg)
+def tc_hand_buffer(x, out):
+    """Scratch through which tc_sum_backward_x hands the packed per-row vectors to tc_sum_backward_w."""
+    d_in, R, B, c = x.shape
+    return torch.empty(_abi.lib().spn_sum_tc_hand_bytes(B, out.shape[0], c, R), device=x.device, dtype=torch.uint8)
+
+
+def tc_sum_backward_x(x, out, g, wimg, lw, hand=None):
+    """dL/dx of tc_sum_forward, [d_in, R, B, c]: two forward-shaped tensor-core GEMMs (one per child).  ``hand``
+    (tc_hand_buffer) additionally receives the packed row vectors that tc_sum_backward_w consumes."""
+    require_cuda(x, out, g, wimg, hand)
     x, out, g = _f32c(x), _f32c(out), _f32c(g)
     d_in, R, B, c = x.shape
     d_out, oc = out.shape[0], out.shape[3]
     dx = torch.empty_like(x)
-    call("spn_sum_tc_bwd_x", ptr(x), ptr(out), ptr(g), ptr(wimg), B, d_in, d_out, c, oc, R, ptr(dx), stream_ptr(x.device))
+    call("spn_sum_tc_bwd_x", ptr(x), ptr(out), ptr(g), ptr(wimg), B, d_in, d_out, c, oc, R, ptr(dx), ptr(hand),
+         stream_ptr(x.device))
     return dx
 
 
-def tc_sum_backward_w(x, out, g, lw, logz=None):
+def tc_sum_backward_w(hand, x, out, g, lw, logz=None):
     """Gradient of tc_sum_forward w.r.t. the weight tensor it was given, [1, d_out, c*c, oc, R] (tensor-core GEMM over
-    the batch); with ``logz`` the tensor is the unnormalised parameter and the softmax backward is fused."""
-    require_cuda(x, out, g, lw, logz)
-    x, out, g, lw = _f32c(x), _f32c(out), _f32c(g), _f32c(lw)
+    the batch) from the hand-off buffer filled by tc_sum_backward_x(..., hand); with ``logz`` the tensor is the
+    unnormalised parameter and the softmax backward is fused."""
+    require_cuda(hand, x, out, g, lw, logz)
+    out, g, lw = _f32c(out), _f32c(g), _f32c(lw)
     d_in, R, B, c = x.shape
     d_out, oc = out.shape[0], out.shape[3]
     work = torch.empty(d_out * R * (c * c + 1) * oc, device=x.device, dtype=torch.float32)
     dlw = torch.empty_like(lw)
-    call("spn_sum_tc_bwd_w", ptr(x), ptr(out), ptr(g), ptr(lw), ptr(logz), B, d_in, d_out, c, oc, R, ptr(work), ptr(dlw),
+    call("spn_sum_tc_bwd_w", ptr(hand), ptr(out), ptr(g), ptr(lw), ptr(logz), B, d_in, d_out, c, oc, R, ptr(work), ptr(dlw),
          stream_ptr(x.device))
     return dlw
 

@@ -191,13 +191,18 @@ int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw, const floa
                    int c, int oc, int R, float* out, void* stream);
 /* Backward of spn_sum_tc_fwd (SURVEY A.5 as tensor-core GEMMs; layouts as in the forward).
  *   spn_sum_tc_bwd_x: dx [d_in, R, B, c] fully overwritten (two forward-shaped outer-product GEMMs, one per child).
- *   spn_sum_tc_bwd_w: dlw [1, d_out, c*c, oc, R] = gradient w.r.t. the tensor passed as lw, fully overwritten: the
+ *                     `hand` (optional, spn_sum_tc_hand_bytes() bytes): receives, per (scope, repetition, 128-row tile),
+ *                     the packed bf16 row vectors exp(xL - mL), exp(xR - mR) and G = g * exp(mL + mR - out) that
+ *                     spn_sum_tc_bwd_w consumes -- the weight-gradient kernel recomputes nothing.
+ *   spn_sum_tc_bwd_w: needs the `hand` buffer written by spn_sum_tc_bwd_x for the same (x, out, g) on the same stream.
+ *                     dlw [1, d_out, c*c, oc, R] = gradient w.r.t. the tensor passed as lw, fully overwritten: the
  *                     log-weights (logz == NULL) or the unnormalised parameters (logz from spn_sum_tc_prepare; the
  *                     softmax backward is fused); dwt_workspace: caller-provided scratch of
  *                     d_out * R * (c*c + 1) * oc floats. */
+int64_t spn_sum_tc_hand_bytes(int B, int d_out, int c, int R);
 int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g, const void* wimg, int B, int d_in, int d_out,
-                     int c, int oc, int R, float* dx, void* stream);
-int spn_sum_tc_bwd_w(const float* x, const float* out, const float* g, const float* lw, const float* logz, int B,
+                     int c, int oc, int R, float* dx, void* hand, void* stream);
+int spn_sum_tc_bwd_w(const void* hand, const float* out, const float* g, const float* lw, const float* logz, int B,
                      int d_in, int d_out, int c, int oc, int R, float* dwt_workspace, float* dlw, void* stream);
 /* ---------------------------------------------------------------------------------------------------------------
  * Root sum layer for SHARED weights on the internal layout: merges the repetitions into the channel axis and sums over

@@ -19,8 +19,9 @@ def timeit(name, fn, flops=None, n=5):
 fl = 2 * B * 16 * 1600 * 40 * R
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "fwd"): timeit("tc fwd S_1", lambda: ops.tc_sum_forward(x, wimg, lw), fl)
-if which in ("all", "bwdx"): timeit("tc bwd_x S_1", lambda: ops.tc_sum_backward_x(x, out, go, wimg, lw), fl)
-if which in ("all", "bwdw"): timeit("tc bwd_w S_1", lambda: ops.tc_sum_backward_w(x, out, go, lw), fl)
+hand = ops.tc_hand_buffer(x, out)
+if which in ("all", "bwdx", "bwdw"): timeit("tc bwd_x S_1", lambda: ops.tc_sum_backward_x(x, out, go, wimg, lw, hand), fl)
+if which in ("all", "bwdw"): timeit("tc bwd_w S_1", lambda: ops.tc_sum_backward_w(hand, x, out, go, lw), fl)
 if which in ("all",): timeit("prepare", lambda: ops.tc_prepare(lw))
 print("aborts", ops.tc_aborts())
 import os, ctypes
