@@ -281,12 +281,13 @@ def main():
             h0 = model._leaf(resident[0], perm32=model._perm32()[0], layout="drbc")
             w1 = model._inner_layers[1].weight_param.detach()
             wimg, logz = ops.tc_prepare(w1, True)
-            out1 = ops.tc_sum_forward(h0, wimg, w1, logz)
+            fhand = ops.tc_fhand_buffer(h0, w1)
+            out1 = ops.tc_sum_forward(h0, wimg, w1, logz, fhand)
             g1 = torch.randn_like(out1) / B
-            t_fwd = time_alone(lambda: ops.tc_sum_forward(h0, wimg, w1, logz))
+            t_fwd = time_alone(lambda: ops.tc_sum_forward(h0, wimg, w1, logz, fhand))
             hand = ops.tc_hand_buffer(h0, out1)
-            t_bx = time_alone(lambda: ops.tc_sum_backward_x(h0, out1, g1, wimg, w1, hand))
-            t_bw = time_alone(lambda: ops.tc_sum_backward_w(hand, h0, out1, g1, w1, logz))
+            t_bx = time_alone(lambda: ops.tc_sum_backward_x(h0, out1, g1, wimg, w1, fhand, hand))
+            t_bw = time_alone(lambda: ops.tc_sum_backward_w(fhand, hand, h0, out1, g1, w1, logz))
             t_prep = time_alone(lambda: ops.tc_prepare(w1, True))
         _, per_layer = contraction_flops_fwd(B)
         fl = per_layer[0]

@@ -60,7 +60,10 @@ struct OpgArgs {
     const float* out;      // [d_out][R][B][OC]  (DX: forward output)
     const float* g;        // [d_out][R][B][OC]  (DX: upstream gradient)
     float* y;              // FWD: out;  DX: dx [d_in][R][B][C]
-    uint8_t* hand;         // DXR, optional: per (s, r, tile) the packed eL / eR / G tiles for the dW kernel (see spn_sum_tc_bwd_w)
+    uint8_t* hand;         // optional hand-off written by this launch, per (s, r, row tile):
+                           //   FWD: packed eL, eR ([pair][128 rows] words) + row shifts mL, mR  -> read by the dX / dW kernels
+                           //   DXR: G tile in the dW kernel's B-operand layout                    -> read by the dW kernel
+    const uint8_t* fhand;  // DX, optional: the forward's hand-off (then no x rows are loaded and nothing is exponentiated)
     int B, d_in, d_out, R;
     int ntiles, nsplit, debug, dbg_n;
 };
@@ -207,8 +210,10 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
     uint8_t* wsm = smem;                                                       // W_BYTES + 1024 (aliased N-group overrun)
     uint32_t* Us = reinterpret_cast<uint32_t*>(smem + W_BYTES + 1024);         // [2 buf][NPAIR][128]  U vector (packed bf16)
     uint32_t* Vs = Us + 2 * NPAIR * 128;                                       // [2 buf][NPAIR][128]  V vector
-    uint32_t* Es = Vs + 2 * NPAIR * 128;                                       // [2 buf][NPAIR][128]  DX: epilogue scale vector
-    float* Ms = reinterpret_cast<float*>(Es + 2 * NPAIR * 128);                // [2 buf][2][128]      row shifts mL, mR
+    uint32_t* Es = Vs + 2 * NPAIR * 128;                                       // DX:  [2 buf][NPAIR][128] epilogue scale vector
+    float* Xs = reinterpret_cast<float*>(Es);                                  // FWD: [2 children][128][C] fp32 rows staged by TMA
+    constexpr int ES_WORDS = MODE == OPG_FWD ? 2 * 128 * C : 2 * NPAIR * 128;
+    float* Ms = reinterpret_cast<float*>(Es + ES_WORDS);                       // [2 buf][2][128]      row shifts mL, mR
     uint64_t* st_full = reinterpret_cast<uint64_t*>(Ms + 2 * 2 * 128);         // [NST]  generators -> MMA
     uint64_t* st_empty = st_full + NST;                                        // [NST]  MMA commit -> generators
     uint64_t* vec_full = st_empty + NST;                                       // [2]    loaders -> generators
@@ -216,7 +221,9 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
     uint64_t* acc_full = vec_empty + 2;                                        // [2]    MMA commit -> epilogue
     uint64_t* acc_empty = acc_full + 2;                                        // [2]    epilogue -> MMA
     uint64_t* bar_w = acc_empty + 2;                                           // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 1);
+    uint64_t* x_full = bar_w + 1;                                              // [1]    FWD: TMA (x rows) -> loaders
+    uint64_t* h_full = x_full + 1;                                             // [2]    DX: TMA (forward hand-off) -> loaders
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_full + 2);
     volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
     // warp index through a shuffle: the idiom that tells the compiler the value (and every branch on it) is warp-uniform
@@ -233,6 +240,9 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
             mbar_init(acc_empty + i, 8);
         }
         mbar_init(bar_w, 1);
+        mbar_init(x_full, 1);
+        mbar_init(h_full + 0, 1);
+        mbar_init(h_full + 1, 1);
         *abort_flag = 0;
         mbar_fence_init();
     }
@@ -409,14 +419,20 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
             const bool has_mine = half ? has_r : has_l;
             const float* xbase = a.x + ((int64_t)(2 * s + half) * a.R + r) * a.B * C;
             const int nt = tile_end - tile_begin;
-            // FWD: this thread's child row of the NEXT tile is loaded one tile ahead (registers).  DX: the loader also needs
-            // out / g slices, so everything of a tile is requested together at its start instead (register budget).
-            constexpr bool PREFETCH = MODE == OPG_FWD;
+            // FWD: the 128 rows of a child are contiguous (20 KB at C = 40), so the TMA engine stages them one tile ahead and
+            // every thread picks its row from shared memory: a per-thread 16-byte global load touches 32 cache lines per warp
+            // instruction (32 L1 wavefronts), which made these loads the most expensive part of the prologue.
+            // DX: the loader also needs out / g slices; everything of a tile is requested together at its start.
+            constexpr bool STAGED = MODE == OPG_FWD;
+            auto stage_x = [&](int tile) {  // whole warp 8 (one elected lane issues)
+                const int rows = min(128, a.B - tile * 128);
+                const uint32_t bytes = (uint32_t)rows * C * 4;
+                mbar_arrive_expect_tx_elect(x_full, (has_l ? bytes : 0u) + (has_r ? bytes : 0u));
+                if (has_l) bulk_g2s_elect(Xs, a.x + (((int64_t)(2 * s) * a.R + r) * a.B + (int64_t)tile * 128) * C, bytes, x_full);
+                if (has_r) bulk_g2s_elect(Xs + 128 * C, a.x + (((int64_t)(2 * s + 1) * a.R + r) * a.B + (int64_t)tile * 128) * C, bytes, x_full);
+            };
+            if (STAGED && warp == 8 && nt > 0) stage_x(tile_begin);
             float v[C];
-            if (PREFETCH) {
-                const int64_t b = (int64_t)tile_begin * 128 + row;
-                load_row<C>(xbase + (b < a.B ? b : 0) * C, b < a.B && has_mine && nt > 0, v);
-            }
             for (int i = 0; i <= nt; ++i) {
                 if (i < nt) {
                     // ---------------- prologue of tile i: half 0 owns the left child row, half 1 the right child row
@@ -430,33 +446,57 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
                     uint32_t* my_v = Vs + vb * NPAIR * 128 + row;
                     uint32_t* my_e = Es + vb * NPAIR * 128 + row;
                     float* my_m = Ms + vb * 2 * 128 + row;
-                    if (!PREFETCH) load_row<C>(xbase + bb * C, valid && has_mine, v);
+                    constexpr int FH_BYTES = 2 * NPAIR * 512 + 1024;   // forward hand-off per tile: eL, eR, shifts
+                    const bool from_fwd = MODE != OPG_FWD && a.fhand != nullptr;
+                    if (from_fwd) {
+                    } else if (STAGED) {
+                        mbar_wait_sticky(x_full, n_tile & 1, abort_flag);
+                        const float4* rowp = reinterpret_cast<const float4*>(Xs + (half * 128 + row) * C);
+#pragma unroll
+                        for (int q = 0; q < C / 4; ++q) {
+                            const float4 t4 = (valid && has_mine) ? rowp[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                            v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+                        }
+                    } else {
+                        load_row<C>(xbase + bb * C, valid && has_mine, v);
+                    }
                     uint32_t e[NPAIR];
                     float m = 0.f;
-                    if ((a.debug != 4 && a.debug < 7 || a.debug == 9)) m = exp_pack<C>(v, e);
+                    if (from_fwd) {
+                    } else if ((a.debug != 4 && a.debug < 7 || a.debug == 9)) m = exp_pack<C>(v, e);
                     else {
 #pragma unroll
                         for (int j = 0; j < NPAIR; ++j) e[j] = __float_as_uint(v[j]);
                     }
-                    {   // issue the loads of the next tile now; they complete while this tile is finished and stored
-                        const int64_t bn = b + 128;
-                        if (PREFETCH)
-                            load_row<C>(xbase + (bn < a.B ? bn : 0) * C, bn < a.B && has_mine && i + 1 < nt && (a.debug != 5 && a.debug < 7 || a.debug == 9), v);
-                        if (i + 2 < nt && b + 256 < a.B && has_mine) {
+                    {
+                        if (!STAGED && i + 2 < nt && b + 256 < a.B && has_mine) {
                             const char* nx = reinterpret_cast<const char*>(xbase + (b + 256) * C);
                             prefetch_l2(nx);
                             prefetch_l2(nx + C * 4 - 4);
                         }
                     }
                     mbar_wait_sticky(vec_empty + vb, ((n_tile >> 1) & 1) ^ 1, abort_flag);  // generators are done with tile n - 2
-                    if (MODE == OPG_DXR && a.hand && warp == 8 && lane == 0) bulk_wait_group_read<1>();  // ... and so is the TMA store
-                    // every loader thread has finished the epilogue that read this buffer (partner rows' shift / scale)
+                    if (MODE != OPG_DXL && a.hand && warp == 8) bulk_wait_group_read<1>();  // ... and so is the TMA store (issuing lane)
+                    // every loader thread has finished the epilogue that read this buffer (partner rows' shift / scale) -- and,
+                    // FWD, has taken its row out of the staging area, which the TMA engine may now refill with the next tile
                     named_bar_sync(1, 256);
-                    my_m[half * 128] = m;
-                    // FWD: U = eL, V = eR.  DXR: U = eL, scale = eR.  DXL: U = eR, scale = eL.
-                    uint32_t* dst = MODE == OPG_FWD ? (half ? my_v : my_u) : MODE == OPG_DXR ? (half ? my_e : my_u) : (half ? my_u : my_e);
+                    if (STAGED && warp == 8 && i + 1 < nt) stage_x(tile + 1);
+                    if (from_fwd) {
+                        // DXR: U = eL, scale = eR.  DXL: U = eR, scale = eL.  Straight from the forward's hand-off by TMA.
+                        if (warp == 8) {
+                            const uint8_t* src = a.fhand + ((size_t)sr * a.ntiles + tile) * FH_BYTES;
+                            mbar_arrive_expect_tx_elect(h_full + vb, FH_BYTES);
+                            bulk_g2s_elect(MODE == OPG_DXR ? Us + vb * NPAIR * 128 : Es + vb * NPAIR * 128, src, NPAIR * 512, h_full + vb);
+                            bulk_g2s_elect(MODE == OPG_DXR ? Es + vb * NPAIR * 128 : Us + vb * NPAIR * 128, src + NPAIR * 512, NPAIR * 512, h_full + vb);
+                            bulk_g2s_elect(Ms + vb * 2 * 128, src + 2 * NPAIR * 512, 1024, h_full + vb);
+                        }
+                    } else {
+                        my_m[half * 128] = m;
+                        // FWD: U = eL, V = eR.  DXR: U = eL, scale = eR.  DXL: U = eR, scale = eL.
+                        uint32_t* dst = MODE == OPG_FWD ? (half ? my_v : my_u) : MODE == OPG_DXR ? (half ? my_e : my_u) : (half ? my_u : my_e);
 #pragma unroll
-                    for (int j = 0; j < NPAIR; ++j) dst[j * 128] = e[j];
+                        for (int j = 0; j < NPAIR; ++j) dst[j * 128] = e[j];
+                    }
                     if (MODE != OPG_FWD) {
                         // G = g * exp(shift - out) = g / (linear-domain sum); out = -inf (impossible row): no gradient.  The
                         // exponent is capped so that rows whose sum underflowed in the forward (rescue path) stay finite.
@@ -477,7 +517,8 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
                             vo[4 * q] = t4.x; vo[4 * q + 1] = t4.y; vo[4 * q + 2] = t4.z; vo[4 * q + 3] = t4.w;
                             vg[4 * q] = u4.x; vg[4 * q + 1] = u4.y; vg[4 * q + 2] = u4.z; vg[4 * q + 3] = u4.w;
                         }
-                        named_bar_sync(2, 256);  // both shifts are in shared memory
+                        if (from_fwd) mbar_wait_sticky(h_full + vb, (n_tile >> 1) & 1, abort_flag);  // eL, eR and the shifts have landed
+                        else named_bar_sync(2, 256);  // both shifts are in shared memory
                         const float sh2 = (my_m[0] + my_m[128]) * 1.4426950408889634f;
                         uint4* gdst = reinterpret_cast<uint4*>(Vs + vb * NPAIR * 128 + (row >> 3) * (NVG * 32) + (row & 7) * 4);
 #pragma unroll
@@ -493,17 +534,21 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
                             if (og < nog) gdst[(og0 + og) * 8] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                         }
                     }
-                    if (MODE == OPG_DXR && a.hand) fence_proxy_async();  // the row vectors are also read by the TMA engine below
+                    if (MODE != OPG_DXL && a.hand) fence_proxy_async();  // the row vectors are also read by the TMA engine below
                     __syncwarp();
                     if (lane == 0) mbar_arrive(vec_full + vb);
-                    if (MODE == OPG_DXR && a.hand && warp == 8 && lane == 0) {
-                        // hand the packed eL / eR / G tiles of this row tile to the dW kernel: three bulk stores by the TMA
-                        // engine once all eight loader warps have written them (the barrier completes on the 8th arrival)
+                    if (MODE != OPG_DXL && a.hand && warp == 8) {
+                        // hand-off by TMA bulk stores once all eight loader warps have written the tiles (the barrier completes
+                        // on the 8th arrival).  FWD: eL, eR, shifts for the backward kernels.  DXR: the G tile for the dW kernel.
                         mbar_wait_sticky(vec_full + vb, (n_tile >> 1) & 1, abort_flag);
-                        uint8_t* dst = a.hand + ((size_t)sr * a.ntiles + tile) * (3 * NPAIR * 512);
-                        bulk_s2g(dst, Us + vb * NPAIR * 128, NPAIR * 512);
-                        bulk_s2g(dst + NPAIR * 512, Es + vb * NPAIR * 128, NPAIR * 512);
-                        bulk_s2g(dst + 2 * NPAIR * 512, Vs + vb * NPAIR * 128, NPAIR * 512);
+                        if (MODE == OPG_FWD) {
+                            uint8_t* dst = a.hand + ((size_t)sr * a.ntiles + tile) * FH_BYTES;
+                            bulk_s2g_elect(dst, Us + vb * NPAIR * 128, NPAIR * 512);
+                            bulk_s2g_elect(dst + NPAIR * 512, Vs + vb * NPAIR * 128, NPAIR * 512);
+                            bulk_s2g_elect(dst + 2 * NPAIR * 512, Ms + vb * 2 * 128, 1024);
+                        } else {
+                            bulk_s2g_elect(a.hand + ((size_t)sr * a.ntiles + tile) * (NPAIR * 512), Vs + vb * NPAIR * 128, NPAIR * 512);
+                        }
                         bulk_commit_group();
                     }
                     ++n_tile;
@@ -578,7 +623,7 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
         }
     }
     // teardown
-    if (MODE == OPG_DXR && warp == 8 && lane == 0) bulk_wait_group<0>();
+    if (MODE != OPG_DXL && warp == 8) bulk_wait_group<0>();
     if (warp == 0) TC2_FLUSH(0);
     if (warp == 8) TC2_FLUSH(6);
     if (warp == 16) TC2_FLUSH(12);
@@ -682,7 +727,8 @@ __global__ void __launch_bounds__(256) tc_wimage_t_kernel(const uint4* __restric
 template <int C, int MODE>
 static int launch_opg(const OpgArgs& a, cudaStream_t st) {
     constexpr int W_BYTES = C * C * C * 2;
-    constexpr int SMEM = W_BYTES + 1024 + 3 * 2 * (C / 2) * 128 * 4 + 2 * 2 * 128 * 4 + (2 * 4 + 9) * 8 + 16;
+    constexpr int SMEM = W_BYTES + 1024 + 2 * 2 * (C / 2) * 128 * 4 + (MODE == OPG_FWD ? 2 * 128 * C * 4 : 2 * (C / 2) * 128 * 4) +
+                         2 * 2 * 128 * 4 + (2 * 4 + 12) * 8 + 16;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(opg_kernel<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -753,26 +799,31 @@ extern "C" int spn_sum_tc_prepare(const float* lw, int d_out, int c, int oc, int
 }
 
 extern "C" int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw, const float* logz, int B, int d_in,
-                              int d_out, int c, int oc, int R, float* out, void* stream) {
+                              int d_out, int c, int oc, int R, float* out, void* fhand, void* stream) {
     if (!x || !wimg || !lw || !out || B <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
     if (!spn_sum_tc_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
     OpgArgs a{};
-    a.x = x; a.wimg = (const uint8_t*)wimg; a.lw = lw; a.logz = logz; a.y = out;
+    a.x = x; a.wimg = (const uint8_t*)wimg; a.lw = lw; a.logz = logz; a.y = out; a.hand = (uint8_t*)fhand;
     a.B = B; a.d_in = d_in; a.d_out = d_out; a.R = R;
     opg_split(a, B, d_out, R);
     return dispatch_opg<OPG_FWD>(c, a, (cudaStream_t)stream);
 }
 
+// hand-off buffers (see OpgArgs): forward -> backward (packed eL, eR, shifts) and dX -> dW (G tiles)
+extern "C" int64_t spn_sum_tc_fhand_bytes(int B, int d_out, int c, int R) {
+    return (int64_t)d_out * R * ((B + 127) / 128) * (2 * (c / 2) * 512 + 1024);
+}
 extern "C" int64_t spn_sum_tc_hand_bytes(int B, int d_out, int c, int R) {
-    return (int64_t)d_out * R * ((B + 127) / 128) * 3 * (c / 2) * 512;
+    return (int64_t)d_out * R * ((B + 127) / 128) * (c / 2) * 512;
 }
 
-extern "C" int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g, const void* wimg, int B, int d_in,
-                                int d_out, int c, int oc, int R, float* dx, void* hand, void* stream) {
+extern "C" int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g, const void* wimg, const void* fhand, int B,
+                                int d_in, int d_out, int c, int oc, int R, float* dx, void* hand, void* stream) {
     if (!x || !out || !g || !wimg || !dx || B <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
     if (!spn_sum_tc_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
     OpgArgs a{};
     a.x = x; a.wimg = (const uint8_t*)wimg; a.out = out; a.g = g; a.y = dx; a.hand = (uint8_t*)hand;
+    a.fhand = (const uint8_t*)fhand;
     a.B = B; a.d_in = d_in; a.d_out = d_out; a.R = R;
     opg_split(a, B, d_out, R);
     int rc = dispatch_opg<OPG_DXL>(c, a, (cudaStream_t)stream);

@@ -14,7 +14,8 @@ using namespace tc;
 __device__ int g_tc_bwd_aborts = 0;
 
 struct TcBwdArgs {
-    const uint8_t* hand;  // per (s, r, row tile): packed eL, eR ([pair][128 rows] words) and G (B-operand layout) from the dX kernel
+    const uint8_t* fhand; // per (s, r, row tile): packed eL, eR ([pair][128 rows] words) + shifts, written by the forward kernel
+    const uint8_t* hand;  // per (s, r, row tile): G tile (B-operand layout), written by the dX kernel
     float* dwt;           // [d_out][R][K][OC] linear-domain weight gradient
     int B, d_in, d_out, R;
     int ntiles, debug;    // debug (SPN_TC_DEBUG, timing experiments only): 1 no MMA issue, 3 generators idle
@@ -47,9 +48,9 @@ __device__ __forceinline__ void dw_issue_chunk(uint32_t dcol, uint64_t adesc, ui
 // into shared memory (MN-major core matrices: one 16-byte store per 8 elements); the kernel is bound by shared-memory
 // bandwidth (A is written once and read once by the tensor core: ~0.8 MB per 128-row tile), not by the tensor pipe.
 //
-// The per-row inputs are NOT recomputed here: the dX kernel that runs just before (sum_tc2.cu, mode DXR) hands over, per
-// (scope, repetition, row tile), the packed bf16 vectors eL, eR ([pair][row] words) and G = g * exp(shift - out) already in
-// the core-matrix layout of this kernel's B operand.  Three TMA bulk copies per tile bring them into shared memory, so
+// The per-row inputs are NOT recomputed here: the forward kernel (sum_tc2.cu, mode FWD) hands over, per (scope, repetition,
+// row tile), the packed bf16 vectors eL, eR ([pair][row] words), and the dX kernel (mode DXR) G = g * exp(shift - out) already
+// in the core-matrix layout of this kernel's B operand.  Three TMA bulk copies per tile bring them into shared memory, so
 // this kernel has no global-load instructions, no exp and no prologue at all (one row per thread with 16-byte loads of
 // four fp32 arrays cost ~5000 L1 wavefronts per tile and was the limiter of the previous version).
 // Thread organisation (10 warps):
@@ -152,11 +153,11 @@ __global__ void __launch_bounds__(320, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
                 mbar_wait_sticky(vec_empty + vb, ((n_tile >> 1) & 1) ^ 1, abort_flag);
                 mbar_wait_sticky(g_empty + vb, ((n_tile >> 1) & 1) ^ 1, abort_flag);
                 if (lane == 0) {
-                    const uint8_t* src = a.hand + ((size_t)sr * a.ntiles + tile) * (3 * V_BYTES);
+                    const uint8_t* src = a.fhand + ((size_t)sr * a.ntiles + tile) * (2 * V_BYTES + 1024);
                     mbar_arrive_expect_tx(vec_full + vb, 3 * V_BYTES);
                     bulk_g2s(Ls + vb * NPAIR * 128, src, V_BYTES, vec_full + vb);
                     bulk_g2s(Rs + vb * NPAIR * 128, src + V_BYTES, V_BYTES, vec_full + vb);
-                    bulk_g2s(gbuf + vb * G_BYTES, src + 2 * V_BYTES, V_BYTES, vec_full + vb);
+                    bulk_g2s(gbuf + vb * G_BYTES, a.hand + ((size_t)sr * a.ntiles + tile) * V_BYTES, V_BYTES, vec_full + vb);
                 }
                 __syncwarp();
             }
@@ -333,13 +334,13 @@ static int launch_bwd_w(const TcBwdArgs& a, cudaStream_t st) {
     return spn_launch_status();
 }
 
-extern "C" int spn_sum_tc_bwd_w(const void* hand, const float* out, const float* g, const float* lw, const float* logz,
+extern "C" int spn_sum_tc_bwd_w(const void* fhand, const void* hand, const float* out, const float* g, const float* lw, const float* logz,
                                 int B, int d_in, int d_out, int c, int oc, int R, float* dwt_workspace, float* dlw,
                                 void* stream) {
-    if (!hand || !out || !g || !lw || !dwt_workspace || !dlw || B <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
+    if (!fhand || !hand || !out || !g || !lw || !dwt_workspace || !dlw || B <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
     if (!spn_sum_tc_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
     TcBwdArgs a{};
-    a.hand = (const uint8_t*)hand; a.dwt = dwt_workspace;
+    a.fhand = (const uint8_t*)fhand; a.hand = (const uint8_t*)hand; a.dwt = dwt_workspace;
     a.B = B; a.d_in = d_in; a.d_out = d_out; a.R = R;
     a.ntiles = (B + 127) / 128;
     {

@@ -202,21 +202,28 @@ class SumTcFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, raw=False, cache=None):
         wimg, logz = tc_prepare_cached(w, raw, cache)
-        out = tc_sum_forward(x, wimg, w, logz)
-        ctx.save_for_backward(x, w, out, wimg, logz if raw else torch.empty(0, device=x.device))
-        ctx.raw = raw
+        # when a backward pass will follow, the forward kernel hands its packed per-row vectors (exp(x - max), shifts) over
+        fhand = tc_fhand_buffer(x, w) if (x.requires_grad or w.requires_grad) else None
+        out = tc_sum_forward(x, wimg, w, logz, fhand)
+        empty = torch.empty(0, device=x.device)
+        ctx.save_for_backward(x, w, out, wimg, logz if raw else empty, fhand if fhand is not None else empty)
+        ctx.raw, ctx.has_fhand = raw, fhand is not None
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x, w, out, wimg, logz = ctx.saved_tensors
+        x, w, out, wimg, logz, fhand = ctx.saved_tensors
         logz = logz if ctx.raw else None
+        fhand = fhand if ctx.has_fhand else None
         g = _f32c(g)
-        # the dX kernel also hands its packed per-row vectors (exp(x - max), G) to the dW kernel, which recomputes nothing
+        # forward -> dX -> dW hand-offs: the dX kernel takes exp(x - max) from the forward and passes G on to the dW
+        # kernel, which recomputes nothing
         need_dw = ctx.needs_input_grad[1]
+        if need_dw and fhand is None:
+            raise RuntimeError("the weight gradient needs the forward's hand-off buffer (forward ran without grad inputs)")
         hand = tc_hand_buffer(x, out) if need_dw else None
-        dx = tc_sum_backward_x(x, out, g, wimg, w, hand) if (ctx.needs_input_grad[0] or need_dw) else None
-        dw = tc_sum_backward_w(hand, x, out, g, w, logz) if need_dw else None
+        dx = tc_sum_backward_x(x, out, g, wimg, w, fhand, hand) if (ctx.needs_input_grad[0] or need_dw) else None
+        dw = tc_sum_backward_w(fhand, hand, x, out, g, w, logz) if need_dw else None
         return (dx if ctx.needs_input_grad[0] else None), dw, None, None
 
 
@@ -388,50 +395,58 @@ def tc_prepare_cached(w: torch.Tensor, raw: bool, cache):
     return wimg, logz
 
 
-def tc_sum_forward(x: torch.Tensor, wimg: torch.Tensor, lw: torch.Tensor, logz: torch.Tensor = None) -> torch.Tensor:
+def tc_fhand_buffer(x, lw):
+    """Scratch through which tc_sum_forward hands exp(x - max) (packed bf16) and the row shifts to the backward kernels."""
+    d_in, R, B, c = x.shape
+    return torch.empty(_abi.lib().spn_sum_tc_fhand_bytes(B, lw.shape[1], c, R), device=x.device, dtype=torch.uint8)
+
+
+def tc_sum_forward(x: torch.Tensor, wimg: torch.Tensor, lw: torch.Tensor, logz: torch.Tensor = None,
+                   fhand: torch.Tensor = None) -> torch.Tensor:
     """x [d_in, R, B, c] -> out [d_out, R, B, oc] (fused CrossProduct + Sum on tcgen05)."""
-    require_cuda(x, wimg, lw, logz)
+    require_cuda(x, wimg, lw, logz, fhand)
     x, lw = _f32c(x), _f32c(lw)
     d_in, R, B, c = x.shape
     _, d_out, ic, oc, Rw = lw.shape
     assert ic == c * c and Rw == R and _pow2_ceil(d_in) == 2 * d_out
     out = torch.empty(d_out, R, B, oc, device=x.device, dtype=torch.float32)
-    call("spn_sum_tc_fwd", ptr(x), ptr(wimg), ptr(lw), ptr(logz), B, d_in, d_out, c, oc, R, ptr(out),
+    call("spn_sum_tc_fwd", ptr(x), ptr(wimg), ptr(lw), ptr(logz), B, d_in, d_out, c, oc, R, ptr(out), ptr(fhand),
          stream_ptr(x.device))
     return out
 
 
 def tc_hand_buffer(x, out):
-    """Scratch through which tc_sum_backward_x hands the packed per-row vectors to tc_sum_backward_w."""
+    """Scratch through which tc_sum_backward_x hands the packed G tiles to tc_sum_backward_w."""
     d_in, R, B, c = x.shape
     return torch.empty(_abi.lib().spn_sum_tc_hand_bytes(B, out.shape[0], c, R), device=x.device, dtype=torch.uint8)
 
 
-def tc_sum_backward_x(x, out, g, wimg, lw, hand=None):
-    """dL/dx of tc_sum_forward, [d_in, R, B, c]: two forward-shaped tensor-core GEMMs (one per child).  ``hand``
-    (tc_hand_buffer) additionally receives the packed row vectors that tc_sum_backward_w consumes."""
-    require_cuda(x, out, g, wimg, hand)
+def tc_sum_backward_x(x, out, g, wimg, lw, fhand=None, hand=None):
+    """dL/dx of tc_sum_forward, [d_in, R, B, c]: two forward-shaped tensor-core GEMMs (one per child).  ``fhand``: the
+    forward's hand-off (optional; without it exp(x - max) is recomputed); ``hand`` (tc_hand_buffer) receives the packed
+    G tiles that tc_sum_backward_w consumes."""
+    require_cuda(x, out, g, wimg, fhand, hand)
     x, out, g = _f32c(x), _f32c(out), _f32c(g)
     d_in, R, B, c = x.shape
     d_out, oc = out.shape[0], out.shape[3]
     dx = torch.empty_like(x)
-    call("spn_sum_tc_bwd_x", ptr(x), ptr(out), ptr(g), ptr(wimg), B, d_in, d_out, c, oc, R, ptr(dx), ptr(hand),
+    call("spn_sum_tc_bwd_x", ptr(x), ptr(out), ptr(g), ptr(wimg), ptr(fhand), B, d_in, d_out, c, oc, R, ptr(dx), ptr(hand),
          stream_ptr(x.device))
     return dx
 
 
-def tc_sum_backward_w(hand, x, out, g, lw, logz=None):
+def tc_sum_backward_w(fhand, hand, x, out, g, lw, logz=None):
     """Gradient of tc_sum_forward w.r.t. the weight tensor it was given, [1, d_out, c*c, oc, R] (tensor-core GEMM over
-    the batch) from the hand-off buffer filled by tc_sum_backward_x(..., hand); with ``logz`` the tensor is the
-    unnormalised parameter and the softmax backward is fused."""
-    require_cuda(hand, x, out, g, lw, logz)
+    the batch) from the hand-off buffers filled by tc_sum_forward(..., fhand) and tc_sum_backward_x(..., hand); with
+    ``logz`` the tensor is the unnormalised parameter and the softmax backward is fused."""
+    require_cuda(fhand, hand, x, out, g, lw, logz)
     out, g, lw = _f32c(out), _f32c(g), _f32c(lw)
     d_in, R, B, c = x.shape
     d_out, oc = out.shape[0], out.shape[3]
     work = torch.empty(d_out * R * (c * c + 1) * oc, device=x.device, dtype=torch.float32)
     dlw = torch.empty_like(lw)
-    call("spn_sum_tc_bwd_w", ptr(hand), ptr(out), ptr(g), ptr(lw), ptr(logz), B, d_in, d_out, c, oc, R, ptr(work), ptr(dlw),
-         stream_ptr(x.device))
+    call("spn_sum_tc_bwd_w", ptr(fhand), ptr(hand), ptr(out), ptr(g), ptr(lw), ptr(logz), B, d_in, d_out, c, oc, R, ptr(work),
+         ptr(dlw), stream_ptr(x.device))
     return dlw
 
 

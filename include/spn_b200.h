@@ -187,23 +187,27 @@ int spn_sample_leaf(const float* mu, const float* sigma, int Wsets, int w, int Q
 int spn_sum_tc_supported(int c, int oc, int R);
 int64_t spn_sum_tc_image_bytes(int d_out, int c, int oc, int R);
 int spn_sum_tc_prepare(const float* lw, int d_out, int c, int oc, int R, float* logz, void* wimg, void* stream);
+/* `fhand` (optional, spn_sum_tc_fhand_bytes() bytes): receives, per (scope, repetition, 128-row tile), the packed bf16 row
+ * vectors exp(xL - mL), exp(xR - mR) and the shifts; the backward kernels then load no activations and exponentiate nothing. */
+int64_t spn_sum_tc_fhand_bytes(int B, int d_out, int c, int R);
 int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw, const float* logz, int B, int d_in, int d_out,
-                   int c, int oc, int R, float* out, void* stream);
+                   int c, int oc, int R, float* out, void* fhand, void* stream);
 /* Backward of spn_sum_tc_fwd (SURVEY A.5 as tensor-core GEMMs; layouts as in the forward).
  *   spn_sum_tc_bwd_x: dx [d_in, R, B, c] fully overwritten (two forward-shaped outer-product GEMMs, one per child).
+ *                     `fhand` (optional): the forward's hand-off; without it the row vectors are recomputed from x.
  *                     `hand` (optional, spn_sum_tc_hand_bytes() bytes): receives, per (scope, repetition, 128-row tile),
- *                     the packed bf16 row vectors exp(xL - mL), exp(xR - mR) and G = g * exp(mL + mR - out) that
- *                     spn_sum_tc_bwd_w consumes -- the weight-gradient kernel recomputes nothing.
- *   spn_sum_tc_bwd_w: needs the `hand` buffer written by spn_sum_tc_bwd_x for the same (x, out, g) on the same stream.
+ *                     G = g * exp(mL + mR - out) as a packed bf16 tile in the layout of spn_sum_tc_bwd_w's B operand.
+ *   spn_sum_tc_bwd_w: needs `fhand` (from spn_sum_tc_fwd) and `hand` (from spn_sum_tc_bwd_x) of the same (x, out, g), same
+ *                     stream; it recomputes nothing.
  *                     dlw [1, d_out, c*c, oc, R] = gradient w.r.t. the tensor passed as lw, fully overwritten: the
  *                     log-weights (logz == NULL) or the unnormalised parameters (logz from spn_sum_tc_prepare; the
  *                     softmax backward is fused); dwt_workspace: caller-provided scratch of
  *                     d_out * R * (c*c + 1) * oc floats. */
 int64_t spn_sum_tc_hand_bytes(int B, int d_out, int c, int R);
-int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g, const void* wimg, int B, int d_in, int d_out,
-                     int c, int oc, int R, float* dx, void* hand, void* stream);
-int spn_sum_tc_bwd_w(const void* hand, const float* out, const float* g, const float* lw, const float* logz, int B,
-                     int d_in, int d_out, int c, int oc, int R, float* dwt_workspace, float* dlw, void* stream);
+int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g, const void* wimg, const void* fhand, int B, int d_in,
+                     int d_out, int c, int oc, int R, float* dx, void* hand, void* stream);
+int spn_sum_tc_bwd_w(const void* fhand, const void* hand, const float* out, const float* g, const float* lw, const float* logz,
+                     int B, int d_in, int d_out, int c, int oc, int R, float* dwt_workspace, float* dlw, void* stream);
 /* ---------------------------------------------------------------------------------------------------------------
  * Root sum layer for SHARED weights on the internal layout: merges the repetitions into the channel axis and sums over
  * all of them, fused with the last CrossProduct.  Replaces rat_spn.py:230-236 + layers.py:110-128 for a RatSpn.

@@ -6,7 +6,8 @@ x = (torch.randn(d_in, R, B, c, device='cuda') * 3 - 20)
 lw = torch.log_softmax(torch.randn(1, 16, c*c, c, R, device='cuda'), dim=2)
 go = torch.randn(16, R, B, c, device='cuda')
 wimg = ops.tc_prepare(lw)
-out = ops.tc_sum_forward(x, wimg, lw)
+fhand = ops.tc_fhand_buffer(x, lw)
+out = ops.tc_sum_forward(x, wimg, lw, None, fhand)
 def timeit(name, fn, flops=None, n=5):
     for _ in range(2): fn()
     torch.cuda.synchronize()
@@ -19,9 +20,10 @@ def timeit(name, fn, flops=None, n=5):
 fl = 2 * B * 16 * 1600 * 40 * R
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "fwd"): timeit("tc fwd S_1", lambda: ops.tc_sum_forward(x, wimg, lw), fl)
+if which in ("all", "fwd"): timeit("tc fwd S_1 + hand-off", lambda: ops.tc_sum_forward(x, wimg, lw, None, fhand), fl)
 hand = ops.tc_hand_buffer(x, out)
-if which in ("all", "bwdx", "bwdw"): timeit("tc bwd_x S_1", lambda: ops.tc_sum_backward_x(x, out, go, wimg, lw, hand), fl)
-if which in ("all", "bwdw"): timeit("tc bwd_w S_1", lambda: ops.tc_sum_backward_w(hand, x, out, go, lw), fl)
+if which in ("all", "bwdx", "bwdw"): timeit("tc bwd_x S_1", lambda: ops.tc_sum_backward_x(x, out, go, wimg, lw, fhand, hand), 2 * fl)
+if which in ("all", "bwdw"): timeit("tc bwd_w S_1", lambda: ops.tc_sum_backward_w(fhand, hand, x, out, go, lw), fl)
 if which in ("all",): timeit("prepare", lambda: ops.tc_prepare(lw))
 print("aborts", ops.tc_aborts())
 import os, ctypes
