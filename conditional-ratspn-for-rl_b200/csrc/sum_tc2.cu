@@ -683,7 +683,9 @@ __global__ void __launch_bounds__(256) tc_logz_kernel(const float* __restrict__ 
 }
 
 // fp32 (log-)weights [1][d][K][OC][R]  ->  bf16 exp() core-matrix image [d][R][K/8][OC/8][8 (k)][8 (o)].
-// One block per (scope, group of 8 k-values).
+// One block per (scope, group of 8 k-values): the [8][OC][R] slab is read coalesced into shared memory, then every thread
+// assembles whole 16-byte image rows (8 outputs of one k): consecutive threads take consecutive repetitions, so the
+// shared-memory reads are conflict free and the stores are full 16-byte chunks.
 __global__ void __launch_bounds__(256) tc_wimage_kernel(const float* __restrict__ lw, const float* __restrict__ logz,
                                                        uint8_t* __restrict__ wimg, int d, int K, int OC, int R) {
     extern __shared__ float tile[];  // [8][OC][R]
@@ -695,13 +697,19 @@ __global__ void __launch_bounds__(256) tc_wimage_kernel(const float* __restrict_
     const float* zp = logz ? logz + (int64_t)s * ocr : nullptr;
     for (int i = threadIdx.x; i < n; i += blockDim.x) tile[i] = __expf(src[i] - (zp ? zp[i % ocr] : 0.f));
     __syncthreads();
-    const int per_r = OC * 8;  // bf16 elements per (r, kg)
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(wimg);
-    for (int i = threadIdx.x; i < R * per_r; i += blockDim.x) {
-        const int r = i / per_r, e = i % per_r;
-        const int og = e / 64, kk = (e / 8) % 8, oo = e % 8;
-        const int o = og * 8 + oo;
-        dst[(((int64_t)s * R + r) * (K / 8) + kg) * per_r + e] = __float2bfloat16(tile[(kk * OC + o) * R + r]);
+    const int NOG = OC / 8;
+    uint4* dst = reinterpret_cast<uint4*>(wimg);
+    // work item = (og, kk, r) with r fastest
+    for (int i = threadIdx.x; i < NOG * 8 * R; i += blockDim.x) {
+        const int r = i % R, kk = (i / R) % 8, og = i / (8 * R);
+        const float* t = tile + (kk * OC + og * 8) * R + r;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(t[0], t[R]), p1 = __floats2bfloat162_rn(t[2 * R], t[3 * R]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(t[4 * R], t[5 * R]), p3 = __floats2bfloat162_rn(t[6 * R], t[7 * R]);
+        uint4 v;
+        v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
+        v.z = *reinterpret_cast<uint32_t*>(&p2); v.w = *reinterpret_cast<uint32_t*>(&p3);
+        // chunk index inside (s, r): ((kg * NOG + og) * 8 + kk); one (s, r) image = K * NOG chunks
+        dst[(((int64_t)s * R + r) * (K / 8) + kg) * (NOG * 8) + og * 8 + kk] = v;
     }
 }
 
