@@ -203,7 +203,7 @@ class SumTcFn(torch.autograd.Function):
     def forward(ctx, x, w, raw=False, cache=None):
         wimg, logz = tc_prepare_cached(w, raw, cache)
         # when a backward pass will follow, the forward kernel hands its packed per-row vectors (exp(x - max), shifts) over
-        fhand = tc_fhand_buffer(x, w) if (x.requires_grad or w.requires_grad) else None
+        fhand = tc_fhand_buffer(x, w) if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) else None
         out = tc_sum_forward(x, wimg, w, logz, fhand)
         empty = torch.empty(0, device=x.device)
         ctx.save_for_backward(x, w, out, wimg, logz if raw else empty, fhand if fhand is not None else empty)
