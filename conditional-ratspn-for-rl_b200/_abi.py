@@ -59,6 +59,10 @@ SIGNATURES = {
     "spn_root_shared_bwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "spn_sample_leaf": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _P, _P, _I, _U, _U, _P, _P, _L, _L, _L,
                         _I, _I, _P, _P, _P],
+    "spn_sample_sum_bwd": [_P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _I, _P, _P, _L, _L, _L,
+                           _L, _I, _I, _I, _I, _I, _P, _U, _U, _P, _I, _I, _P, _P, _P, _P],
+    "spn_sample_leaf_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _U, _U, _P, _P, _L, _L, _L, _I,
+                            _I, _P, _I, _P, _P, _P, _P, _P],
 }
 
 _RETURNS_INT64 = {"spn_leaf_workspace_floats", "spn_sum_tc_image_bytes", "spn_sum_tc_hand_bytes", "spn_sum_tc_fhand_bytes"}

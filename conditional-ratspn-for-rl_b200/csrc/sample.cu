@@ -16,12 +16,15 @@ struct SampleSumArgs {
     int32_t* out;
 };
 
-// One warp per item (q, s, rs); lanes stride over the in-channels and keep (best value, first index).
+// One group of G lanes (G = 4..32, the power of two covering ic) per item (q, s, rs); lanes stride over the in-channels
+// and keep (best value, first index).  Out-of-range groups run on the last item with the write masked.
+template <int G>
 __global__ void __launch_bounds__(256) sample_sum_kernel(SampleSumArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & (G - 1);
     const int64_t items = (int64_t)a.Q * a.d * a.Rs;
-    if (item >= items) return;
+    int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool live = item < items;
+    if (!live) item = items - 1;
     const int rs = (int)(item % a.Rs);
     const int s = (int)((item / a.Rs) % a.d);
     const int64_t q = item / ((int64_t)a.Rs * a.d);
@@ -48,7 +51,7 @@ __global__ void __launch_bounds__(256) sample_sum_kernel(SampleSumArgs a) {
 
     float best = -CUDART_INF_F;
     int besti = 0x7fffffff;
-    for (int i = lane; i < a.ic; i += 32) {
+    for (int i = lane; i < a.ic; i += G) {
         int r = rsel, ii = i;
         if (a.root) { r = i / a.ic_top; ii = i - r * a.ic_top; }
         float v = lwp[(int64_t)ii * a.sw_i + (int64_t)r * a.sw_r];
@@ -70,12 +73,12 @@ __global__ void __launch_bounds__(256) sample_sum_kernel(SampleSumArgs a) {
         if (v > best || besti == 0x7fffffff) { best = v; besti = i; }
     }
 #pragma unroll
-    for (int sh = 16; sh > 0; sh >>= 1) {
+    for (int sh = G / 2; sh > 0; sh >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best, sh);
         const int oi = __shfl_xor_sync(0xffffffffu, besti, sh);
         if (oi != 0x7fffffff && (besti == 0x7fffffff || ov > best || (ov == best && oi < besti))) { best = ov; besti = oi; }
     }
-    if (lane == 0) a.out[item] = besti;
+    if (lane == 0 && live) a.out[item] = besti;
 }
 
 struct SampleLeafArgs {
@@ -139,8 +142,16 @@ extern "C" int spn_sample_sum(const float* lw, int64_t sw_w, int64_t sw_d, int64
     a.pa = pa; a.sp_q = sp_q; a.sp_s = sp_s; a.sp_r = sp_r; a.unravel = unravel; a.rep = rep;
     a.xc = xc; a.sxc_b = sxc_b; a.sxc_d = sxc_d; a.sxc_c = sxc_c; a.sxc_r = sxc_r; a.xc_din = xc_din; a.c = c; a.Qe = Qe;
     a.root = root; a.ic_top = ic_top; a.gumbel = gumbel; a.mpe = mpe; a.seed = seed; a.q_offset = q_offset; a.out = out;
-    const int64_t threads = (int64_t)Q * d * Rs * 32;
-    sample_sum_kernel<<<spn_blocks(threads, 256), 256, 0, (cudaStream_t)stream>>>(a);
+    int G = 4;
+    while (G < 32 && G < ic) G <<= 1;
+    const unsigned blocks = spn_blocks((int64_t)Q * d * Rs * G, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (G) {
+        case 4: sample_sum_kernel<4><<<blocks, 256, 0, st>>>(a); break;
+        case 8: sample_sum_kernel<8><<<blocks, 256, 0, st>>>(a); break;
+        case 16: sample_sum_kernel<16><<<blocks, 256, 0, st>>>(a); break;
+        default: sample_sum_kernel<32><<<blocks, 256, 0, st>>>(a); break;
+    }
     return spn_launch_status();
 }
 

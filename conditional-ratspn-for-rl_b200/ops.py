@@ -357,6 +357,57 @@ def sample_leaf(mu, sigma, Q, card, Rs, pa, pa_strides, rep, eps, mpe, inv_perm3
     return out, ch
 
 
+def _sum_sample_geometry(lw, root, xc):
+    Wsets = lw.shape[0]
+    if root:
+        _, _, KR, oc, _ = lw.shape
+        ic, ic_top = KR, KR // root
+        sw = (KR * oc, 0, oc, 1, ic_top * oc)
+        c = int(round(math.sqrt(ic_top)))
+    else:
+        _, dl, ic, oc, R = lw.shape
+        ic_top = 0
+        sw = (dl * ic * oc * R, ic * oc * R, oc * R, R, 1)
+        c = int(round(math.sqrt(ic)))
+    xc_din, sxc = 0, (0, 0, 0, 0)
+    if xc is not None:
+        xc_din, cx, Rx = xc.shape[-3:]
+        assert cx == c
+        sxc = (xc_din * cx * Rx, cx * Rx, Rx, 1)
+    return Wsets, ic, oc, ic_top, c, sw, xc_din, sxc
+
+
+def sample_sum_backward(lw, root, Q, d, Rs, pa, pa_strides, unravel, rep, xc, Qe, gumbel, seed, gc, gc_d, dlw, dxc,
+                        want_parent, gc_allreps=False, q_offset=0):
+    """Straight-through gradient of one Sum layer of the onehot sampling pass (spn_sample_sum_bwd); accumulates into
+    dlw / dxc and returns the gradient w.r.t. the parent one-hots [Q, d, oc, Rs] (None at the top layer)."""
+    require_cuda(lw, pa, rep, xc, gumbel, gc, dlw, dxc)
+    assert lw.is_contiguous() and dlw.is_contiguous() and gc.is_contiguous()
+    Wsets, ic, oc, ic_top, c, sw, xc_din, sxc = _sum_sample_geometry(lw, root, xc)
+    w = Wsets if Wsets != 1 else 1
+    gp = torch.empty(Q, d, oc, Rs, device=lw.device, dtype=torch.float32) if want_parent and not root else None
+    call("spn_sample_sum_bwd", ptr(lw), *sw, Wsets, w, Q, d, ic, oc, Rs, ptr(pa), *pa_strides, int(unravel), ptr(rep),
+         ptr(xc), *sxc, xc_din, c, Qe, 1 if root else 0, ic_top, ptr(gumbel), seed, q_offset, ptr(gc), gc_d,
+         int(gc_allreps), ptr(dlw), ptr(dxc), ptr(gp), stream_ptr(lw.device))
+    return gp
+
+
+def sample_leaf_backward(mu, sigma, Q, card, Rs, ch, rep, eps, mpe, seed, perm32, evidence, ev_strides, Qe, squash, y,
+                         gy, want_g0, g0_allreps=False, q_offset=0):
+    """Leaf step of the onehot sampling backward (spn_sample_leaf_bwd): returns (dmu, dsigma, g0 [Q, dP, I, Rs])."""
+    require_cuda(mu, sigma, ch, rep, eps, perm32, evidence, y, gy)
+    assert mu.is_contiguous() and sigma.is_contiguous() and gy.is_contiguous()
+    Wsets, F, I, R = mu.shape
+    w = Wsets if Wsets != 1 else 1
+    dP = -(-F // card)
+    dmu, dsigma = torch.zeros_like(mu), torch.zeros_like(sigma)
+    g0 = torch.empty(Q, dP, I, R if g0_allreps else Rs, device=mu.device, dtype=torch.float32) if want_g0 else None
+    call("spn_sample_leaf_bwd", ptr(mu), ptr(sigma), Wsets, w, Q, F, I, R, card, Rs, dP, ptr(ch), ptr(rep), ptr(eps),
+         int(mpe), seed, q_offset, ptr(perm32), ptr(evidence), *ev_strides, Qe, int(squash), ptr(y), int(g0_allreps), ptr(gy),
+         ptr(dmu), ptr(dsigma), ptr(g0), stream_ptr(mu.device))
+    return dmu, dsigma, g0
+
+
 def launches() -> int:
     return _abi.LAUNCHES
 

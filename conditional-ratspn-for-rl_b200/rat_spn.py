@@ -329,8 +329,7 @@ class RatSpn(nn.Module):
                 ctx, fused = self._sample_index(ctx, class_index, evidence, layer_index, fuse_post, noise)
             elif mode == 'onehot':
                 from .diffsample import sample_onehot
-                ctx = sample_onehot(self, ctx, class_index, evidence, layer_index, noise)
-                fused = False
+                ctx, fused = sample_onehot(self, ctx, class_index, evidence, layer_index, noise, fuse_post)
             else:
                 raise ValueError(f"unknown sampling mode {mode}")
         if do_sample_postprocessing and not fused:
@@ -490,6 +489,8 @@ class RatSpn(nn.Module):
             inv = self.inv_permutation
             if ctx.repetition_indices is not None:
                 sel = inv.t()[ctx.repetition_indices]
+            elif ctx.onehot_repetition is not None:
+                sel = inv.t()[ctx.onehot_repetition]
             elif ctx.sampling_mode == 'onehot' and ctx.parent_indices is not None and not ctx.has_rep_dim:
                 sel = (inv * ctx.parent_indices.detach().sum(-2).long()).sum(-1)
             else:

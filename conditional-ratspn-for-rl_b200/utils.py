@@ -32,6 +32,7 @@ class Sample:
     scopes: int = None                            # number of scopes of the layer sampling started at
     parent_indices: th.Tensor = None              # channel choice handed to the next (lower) layer
     repetition_indices: th.Tensor = None          # chosen repetition per sample (root sampling, index mode)
+    onehot_repetition: th.Tensor = None           # onehot mode: index of the repetition whose one-hots are non-zero
     is_mpe: bool = False
     sample: th.Tensor = None
     has_rep_dim: bool = True

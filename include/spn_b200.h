@@ -171,6 +171,34 @@ int spn_sample_leaf(const float* mu, const float* sigma, int Wsets, int w, int Q
                     float* out, int32_t* ch_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Backward of the differentiable ('onehot') sampling mode: straight-through Gumbel-softmax estimator, tau = 1.
+ * Replaces autograd through layers.py:181-186, :206-234 (hard - soft.detach() + soft), :495-503 (CrossProduct one-hot
+ * split), distributions.py:281-301 (one-hot selection of (mu, sigma)) and rat_spn.py:437-468 (root / repetition
+ * one-hots).  The forward values are the ones of spn_sample_sum / spn_sample_leaf (same noise: the supplied tensors
+ * or the same Philox seed); the backward runs bottom-up, one call per layer:
+ *   spn_sample_leaf_bwd: gy [Q, F, Rs] = dL/d(out of spn_sample_leaf) (perm/evidence/squash as in that call; perm is
+ *     the FORWARD permutation [F, R], y the forward output) -> dmu, dsigma [Wsets, F, I, R] (accumulated, atomics)
+ *     and g0 [Q, dP, I, Rs] = dL/d(leaf-channel one-hot of every Product scope), dP = ceil(F / card).
+ *   spn_sample_sum_bwd: gc [Q, gc_d, c, Rs] = gradient w.r.t. the one-hots of the gc_d child scopes (at the root it
+ *     applies to the selected repetition only) -> dlw (same strides as lw, accumulated), dxc (same strides as xc,
+ *     accumulated, NULL iff xc NULL), gparent [Q, d, oc, Rs] = gradient w.r.t. the parent one-hots (NULL at the top).
+ *   D = 1 (the root sits directly on the leaf CrossProduct, no Sum layer clears the unselected repetitions): pass
+ *     g0_allreps = gc_allreps = 1; g0 / gc are then [Q, dP, I, R], evaluated with every repetition's leaf parameters.
+ * All other arguments as in the forward calls.  Accumulating outputs must be zero-initialised by the caller.
+ * ------------------------------------------------------------------------------------------------------------- */
+int spn_sample_sum_bwd(const float* lw, int64_t sw_w, int64_t sw_d, int64_t sw_i, int64_t sw_o, int64_t sw_r,
+                       int Wsets, int w, int Q, int d, int ic, int oc, int Rs, const int32_t* pa, int64_t sp_q,
+                       int64_t sp_s, int64_t sp_r, int unravel, const int32_t* rep, const float* xc, int64_t sxc_b,
+                       int64_t sxc_d, int64_t sxc_c, int64_t sxc_r, int xc_din, int c, int Qe, int root, int ic_top,
+                       const float* gumbel, uint64_t seed, uint64_t q_offset, const float* gc, int gc_d, int gc_allreps,
+                       float* dlw, float* dxc, float* gparent, void* stream);
+int spn_sample_leaf_bwd(const float* mu, const float* sigma, int Wsets, int w, int Q, int F, int I, int R, int card,
+                        int Rs, int dP, const int32_t* ch, const int32_t* rep, const float* eps, int mpe, uint64_t seed,
+                        uint64_t q_offset, const int32_t* perm, const float* evidence, int64_t se_q, int64_t se_f,
+                        int64_t se_r, int Qe, int squash, const float* y, int g0_allreps, const float* gy, float* dmu,
+                        float* dsigma, float* g0, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Tensor-core path (tcgen05 + TMEM) for SHARED-weight layers: fused CrossProduct + Sum forward as a bf16 GEMM with
  * fp32 accumulation; replaces the same reference lines as spn_sum_fwd(xprod = 1) for RatSpn models whose channel
  * counts are supported (spn_sum_tc_supported).  Activations use the internal layout [scope][repetition][batch][channel]:
