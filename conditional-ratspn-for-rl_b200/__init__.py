@@ -12,7 +12,8 @@ The directory name contains hyphens, so import it through the alias module at th
 import sys
 
 from . import _abi, ops  # noqa: F401
-from . import type_checks, utils, layers, distributions, rat_spn, cspn, diffsample, parallel  # noqa: F401
+from . import type_checks, utils, layers, distributions, rat_spn, cspn, diffsample, parallel, graphs  # noqa: F401
+from .graphs import GraphedCall  # noqa: F401
 from .cspn import CSPN, CspnConfig, print_cspn_params  # noqa: F401
 from .distributions import IndependentMultivariate, Leaf, RatNormal, truncated_normal_  # noqa: F401
 from .layers import CrossProduct, Product, Sum  # noqa: F401

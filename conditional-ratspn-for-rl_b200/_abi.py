@@ -43,7 +43,7 @@ SIGNATURES = {
     "spn_xprod_fwd": [_P, _I, _I, _I, _I, _P, _P],
     "spn_xprod_bwd": [_P, _I, _I, _I, _I, _P, _P],
     "spn_sample_sum": [_P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _I, _P, _P, _L, _L, _L, _L,
-                       _I, _I, _I, _I, _I, _P, _I, _U, _U, _P, _P],
+                       _I, _I, _I, _I, _I, _P, _I, _U, _U, _P, _P, _P],
     "spn_sum_tc_supported": [_I, _I, _I],
     "spn_sum_tc_image_bytes": [_I, _I, _I, _I],
     "spn_sum_tc_prepare": [_P, _I, _I, _I, _I, _P, _P, _P],
@@ -57,11 +57,11 @@ SIGNATURES = {
     "spn_root_shared_supported": [_I, _I, _I],
     "spn_root_shared_fwd": [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P],
     "spn_root_shared_bwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
-    "spn_sample_leaf": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _P, _P, _I, _U, _U, _P, _P, _L, _L, _L,
+    "spn_sample_leaf": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _P, _P, _I, _U, _U, _P, _P, _P, _L, _L, _L,
                         _I, _I, _P, _P, _P],
     "spn_sample_sum_bwd": [_P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _I, _P, _P, _L, _L, _L,
-                           _L, _I, _I, _I, _I, _I, _P, _U, _U, _P, _I, _I, _P, _P, _P, _P],
-    "spn_sample_leaf_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _U, _U, _P, _P, _L, _L, _L, _I,
+                           _L, _I, _I, _I, _I, _I, _P, _U, _U, _P, _P, _I, _I, _P, _P, _P, _P],
+    "spn_sample_leaf_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _U, _U, _P, _P, _P, _L, _L, _L, _I,
                             _I, _P, _I, _P, _P, _P, _P, _P],
 }
 

@@ -126,6 +126,7 @@ class CSPN(RatSpn):
         """Evaluate the gating network on ``feat_inp`` [B, *F_cond] and install, per conditional, log-normalised sum
         weights [B, d, ic, oc, r] and sigmoid-bounded leaf parameters [B, F, I, R]   (cspn.py:254-301)."""
         B = feat_inp.shape[0]
+        self._release_param_graph()
         features = self.feat_layers(feat_inp).flatten(start_dim=1)
         hidden = self.sum_layers(features)
         head = iter(self.sum_param_heads)
@@ -144,6 +145,17 @@ class CSPN(RatSpn):
         hidden = self.dist_layers(features)
         base.mean_param = base.bounded_means(self.dist_mean_head(hidden).view(shape))
         base.std_param = base.bounded_stds(self.dist_std_head(hidden).view(shape))
+
+    def _release_param_graph(self):
+        """Drop the autograd graph of the previous ``set_params`` before building the next one.  The installed
+        parameters are the only long-lived references to it; keeping it alive across calls would make the new graph
+        share the old AccumulateGrad nodes (and their stream), which breaks CUDA-graph capture of an update."""
+        base = self._leaf.base_leaf
+        for owner, name in [(l, "weight_param") for l in list(self._inner_layers) + [self.root] if isinstance(l, Sum)] \
+                + [(base, "mean_param"), (base, "std_param")]:
+            t = getattr(owner, name, None)
+            if isinstance(t, th.Tensor) and t.grad_fn is not None:
+                setattr(owner, name, t.detach())
 
     def clear_params(self):
         dev = self.device

@@ -12,7 +12,7 @@ struct SampleSumArgs {
     const int32_t* rep;
     const float* xc; int64_t sxc_b, sxc_d, sxc_c, sxc_r; int xc_din, c, Qe;
     int root, ic_top;
-    const float* gumbel; int mpe; uint64_t seed, q_offset;
+    const float* gumbel; int mpe; uint64_t seed, q_offset; const uint64_t* seed_dev;
     int32_t* out;
 };
 
@@ -21,6 +21,7 @@ struct SampleSumArgs {
 template <int G>
 __global__ void __launch_bounds__(256) sample_sum_kernel(SampleSumArgs a) {
     const int lane = threadIdx.x & (G - 1);
+    const uint64_t seed_v = a.seed_dev ? *a.seed_dev : a.seed;  // device seed: fresh noise on CUDA-graph replays
     const int64_t items = (int64_t)a.Q * a.d * a.Rs;
     int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const bool live = item < items;
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(256) sample_sum_kernel(SampleSumArgs a) {
                 v += a.gumbel[((q * a.d + s) * (int64_t)a.ic + i) * a.Rs + rs];
             } else {
                 const uint64_t elem = ((((uint64_t)q + a.q_offset) * a.d + s) * (uint64_t)a.ic + i) * a.Rs + rs;
-                v += spn_gumbel(elem, stream_id, a.seed);
+                v += spn_gumbel(elem, stream_id, seed_v);
             }
         }
         if (v > best || besti == 0x7fffffff) { best = v; besti = i; }
@@ -86,7 +87,7 @@ struct SampleLeafArgs {
     int Wsets, w, Q, F, I, R, card, Rs;
     const int32_t* pa; int64_t sp_q, sp_s, sp_r;
     const int32_t* rep;
-    const float* eps; int mpe; uint64_t seed, q_offset;
+    const float* eps; int mpe; uint64_t seed, q_offset; const uint64_t* seed_dev;
     const int32_t* inv_perm;
     const float* evidence; int64_t se_q, se_f, se_r; int Qe;
     int squash;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256) sample_leaf_kernel(SampleLeafArgs a) {
     const int64_t total = (int64_t)a.Q * a.F * a.Rs;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= total) return;
+    const uint64_t seed_v = a.seed_dev ? *a.seed_dev : a.seed;
     const int rs = (int)(tid % a.Rs);
     const int fo = (int)((tid / a.Rs) % a.F);
     const int64_t q = tid / ((int64_t)a.Rs * a.F);
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(256) sample_leaf_kernel(SampleLeafArgs a) {
         const int64_t ne = (q * a.F + slot) * (int64_t)a.Rs + rs;
         float e;
         if (a.eps) e = a.eps[ne];
-        else e = spn_normal((((uint64_t)q + a.q_offset) * a.F + slot) * (uint64_t)a.Rs + rs, 0x1eafULL, a.seed);
+        else e = spn_normal((((uint64_t)q + a.q_offset) * a.F + slot) * (uint64_t)a.Rs + rs, 0x1eafULL, seed_v);
         y += a.sigma[pi] * e;
     }
     if (a.evidence) {
@@ -130,7 +132,7 @@ extern "C" int spn_sample_sum(const float* lw, int64_t sw_w, int64_t sw_d, int64
                               int64_t sp_s, int64_t sp_r, int unravel, const int32_t* rep, const float* xc,
                               int64_t sxc_b, int64_t sxc_d, int64_t sxc_c, int64_t sxc_r, int xc_din, int c, int Qe,
                               int root, int ic_top, const float* gumbel, int mpe, uint64_t seed, uint64_t q_offset,
-                              int32_t* out, void* stream) {
+                              const uint64_t* seed_dev, int32_t* out, void* stream) {
     if (!lw || !pa || !out || Q < 0 || d <= 0 || ic <= 0 || oc <= 0 || Rs <= 0) return SPN_ERR_ARG;
     if (Wsets != 1 && (Wsets != w || Q % w != 0)) return SPN_ERR_ARG;
     if (xc && (Qe <= 0 || c <= 0 || Q % Qe != 0)) return SPN_ERR_ARG;
@@ -141,7 +143,7 @@ extern "C" int spn_sample_sum(const float* lw, int64_t sw_w, int64_t sw_d, int64
     a.Wsets = Wsets; a.w = w; a.Q = Q; a.d = d; a.ic = ic; a.oc = oc; a.Rs = Rs;
     a.pa = pa; a.sp_q = sp_q; a.sp_s = sp_s; a.sp_r = sp_r; a.unravel = unravel; a.rep = rep;
     a.xc = xc; a.sxc_b = sxc_b; a.sxc_d = sxc_d; a.sxc_c = sxc_c; a.sxc_r = sxc_r; a.xc_din = xc_din; a.c = c; a.Qe = Qe;
-    a.root = root; a.ic_top = ic_top; a.gumbel = gumbel; a.mpe = mpe; a.seed = seed; a.q_offset = q_offset; a.out = out;
+    a.root = root; a.ic_top = ic_top; a.gumbel = gumbel; a.mpe = mpe; a.seed = seed; a.q_offset = q_offset; a.seed_dev = seed_dev; a.out = out;
     int G = 4;
     while (G < 32 && G < ic) G <<= 1;
     const unsigned blocks = spn_blocks((int64_t)Q * d * Rs * G, 256);
@@ -158,7 +160,7 @@ extern "C" int spn_sample_sum(const float* lw, int64_t sw_w, int64_t sw_d, int64
 extern "C" int spn_sample_leaf(const float* mu, const float* sigma, int Wsets, int w, int Q, int F, int I, int R,
                                int card, int Rs, const int32_t* pa, int64_t sp_q, int64_t sp_s, int64_t sp_r,
                                const int32_t* rep, const float* eps, int mpe, uint64_t seed, uint64_t q_offset,
-                               const int32_t* inv_perm, const float* evidence, int64_t se_q, int64_t se_f,
+                               const uint64_t* seed_dev, const int32_t* inv_perm, const float* evidence, int64_t se_q, int64_t se_f,
                                int64_t se_r, int Qe, int squash, float* out, int32_t* ch_out, void* stream) {
     if (!mu || !sigma || !pa || !out || Q < 0 || F <= 0 || I <= 0 || R <= 0 || card <= 0 || Rs <= 0) return SPN_ERR_ARG;
     if (Wsets != 1 && (Wsets != w || Q % w != 0)) return SPN_ERR_ARG;
@@ -167,7 +169,7 @@ extern "C" int spn_sample_leaf(const float* mu, const float* sigma, int Wsets, i
     SampleLeafArgs a{};
     a.mu = mu; a.sigma = sigma; a.Wsets = Wsets; a.w = w; a.Q = Q; a.F = F; a.I = I; a.R = R; a.card = card; a.Rs = Rs;
     a.pa = pa; a.sp_q = sp_q; a.sp_s = sp_s; a.sp_r = sp_r; a.rep = rep; a.eps = eps; a.mpe = mpe; a.seed = seed;
-    a.q_offset = q_offset; a.inv_perm = inv_perm; a.evidence = evidence; a.se_q = se_q; a.se_f = se_f; a.se_r = se_r;
+    a.seed_dev = seed_dev; a.q_offset = q_offset; a.inv_perm = inv_perm; a.evidence = evidence; a.se_q = se_q; a.se_f = se_f; a.se_r = se_r;
     a.Qe = Qe; a.squash = squash; a.out = out; a.ch_out = ch_out;
     const int64_t total = (int64_t)Q * F * Rs;
     sample_leaf_kernel<<<spn_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(a);

@@ -19,7 +19,7 @@ struct SampleSumBwdArgs {
     const int32_t* rep;
     const float* xc; int64_t sxc_b, sxc_d, sxc_c, sxc_r; int xc_din, c, Qe;
     int root, ic_top;
-    const float* gumbel; uint64_t seed, q_offset;
+    const float* gumbel; uint64_t seed, q_offset; const uint64_t* seed_dev;
     int gc_allreps;              // root directly above the leaves (D = 1): gc is [Q, gc_d, c, R], every repetition
     const float* gc; int gc_d;   // upstream gradient w.r.t. the one-hots of the gc_d child scopes [Q, gc_d, c, Rs]
     float* dlw; float* dxc; float* gparent;  // gparent [Q, d, oc, Rs] or null
@@ -44,6 +44,7 @@ template <int G>
 __global__ void __launch_bounds__(256) sample_sum_bwd_kernel(SampleSumBwdArgs a) {
     extern __shared__ float dz_all[];
     const int lane = threadIdx.x & (G - 1);
+    const uint64_t seed_v = a.seed_dev ? *a.seed_dev : a.seed;  // device seed: fresh noise on CUDA-graph replays
     const int wib = threadIdx.x / G;
     const int64_t items = (int64_t)a.Q * a.d * a.Rs;
     int64_t item = (int64_t)blockIdx.x * (blockDim.x / G) + wib;
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(256) sample_sum_bwd_kernel(SampleSumBwdArgs a)
             v += xoff;
         }
         if (a.gumbel) v += a.gumbel[((q * a.d + s) * (int64_t)a.ic + i) * a.Rs + rs];
-        else v += spn_gumbel(((((uint64_t)q + a.q_offset) * a.d + s) * (uint64_t)a.ic + i) * a.Rs + rs, stream_id, a.seed);
+        else v += spn_gumbel(((((uint64_t)q + a.q_offset) * a.d + s) * (uint64_t)a.ic + i) * a.Rs + rs, stream_id, seed_v);
         return v;
     };
     auto upstream = [&](int i) -> float {
@@ -181,7 +182,7 @@ struct SampleLeafBwdArgs {
     const float* mu; const float* sigma;
     int Wsets, w, Q, F, I, R, card, Rs, dP;
     const int32_t* ch; const int32_t* rep;
-    const float* eps; int mpe; uint64_t seed, q_offset;
+    const float* eps; int mpe; uint64_t seed, q_offset; const uint64_t* seed_dev;
     const int32_t* perm;   // [F, R] slot -> output feature (null: identity / un-post-processed samples)
     const float* evidence; int64_t se_q, se_f, se_r; int Qe;
     int squash; const float* y;
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(256) sample_leaf_bwd_kernel(SampleLeafBwdArgs 
     const int64_t total = (int64_t)a.Q * a.dP * a.I * Rg;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= total) return;
+    const uint64_t seed_v = a.seed_dev ? *a.seed_dev : a.seed;
     const int rg = (int)(tid % Rg);
     const int i = (int)((tid / Rg) % a.I);
     const int s = (int)((tid / ((int64_t)Rg * a.I)) % a.dP);
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(256) sample_leaf_bwd_kernel(SampleLeafBwdArgs 
         float e = 0.f;
         if (!a.mpe) {
             if (a.eps) e = a.eps[ne];
-            else e = spn_normal((((uint64_t)q + a.q_offset) * a.F + f) * (uint64_t)a.Rs + rs, 0x1eafULL, a.seed);
+            else e = spn_normal((((uint64_t)q + a.q_offset) * a.F + f) * (uint64_t)a.Rs + rs, 0x1eafULL, seed_v);
         }
         acc += g * (a.mu[pi] + a.sigma[pi] * e);
         if (a.ch[ne] == i && r == rsel && g != 0.f) {
@@ -240,7 +242,7 @@ extern "C" int spn_sample_sum_bwd(const float* lw, int64_t sw_w, int64_t sw_d, i
                                   int64_t sp_q, int64_t sp_s, int64_t sp_r, int unravel, const int32_t* rep,
                                   const float* xc, int64_t sxc_b, int64_t sxc_d, int64_t sxc_c, int64_t sxc_r,
                                   int xc_din, int c, int Qe, int root, int ic_top, const float* gumbel, uint64_t seed,
-                                  uint64_t q_offset, const float* gc, int gc_d, int gc_allreps, float* dlw, float* dxc,
+                                  uint64_t q_offset, const uint64_t* seed_dev, const float* gc, int gc_d, int gc_allreps, float* dlw, float* dxc,
                                   float* gparent, void* stream) {
     if (!lw || !pa || !gc || !dlw || Q < 0 || d <= 0 || ic <= 0 || oc <= 0 || Rs <= 0 || c <= 0) return SPN_ERR_ARG;
     if (Wsets != 1 && (Wsets != w || Q % w != 0)) return SPN_ERR_ARG;
@@ -253,7 +255,7 @@ extern "C" int spn_sample_sum_bwd(const float* lw, int64_t sw_w, int64_t sw_d, i
     a.Wsets = Wsets; a.w = w; a.Q = Q; a.d = d; a.ic = ic; a.oc = oc; a.Rs = Rs;
     a.pa = pa; a.sp_q = sp_q; a.sp_s = sp_s; a.sp_r = sp_r; a.unravel = unravel; a.rep = rep;
     a.xc = xc; a.sxc_b = sxc_b; a.sxc_d = sxc_d; a.sxc_c = sxc_c; a.sxc_r = sxc_r; a.xc_din = xc_din; a.c = c; a.Qe = Qe;
-    a.root = root; a.ic_top = ic_top; a.gumbel = gumbel; a.seed = seed; a.q_offset = q_offset;
+    a.root = root; a.ic_top = ic_top; a.gumbel = gumbel; a.seed = seed; a.q_offset = q_offset; a.seed_dev = seed_dev;
     a.gc = gc; a.gc_d = gc_d; a.gc_allreps = (root && gc_allreps) ? 1 : 0; a.dlw = dlw; a.dxc = xc ? dxc : nullptr; a.gparent = root ? nullptr : gparent;
     int G = 4;
     while (G < 32 && G < ic) G <<= 1;
@@ -278,7 +280,8 @@ extern "C" int spn_sample_sum_bwd(const float* lw, int64_t sw_w, int64_t sw_d, i
 
 extern "C" int spn_sample_leaf_bwd(const float* mu, const float* sigma, int Wsets, int w, int Q, int F, int I, int R,
                                    int card, int Rs, int dP, const int32_t* ch, const int32_t* rep, const float* eps,
-                                   int mpe, uint64_t seed, uint64_t q_offset, const int32_t* perm, const float* evidence,
+                                   int mpe, uint64_t seed, uint64_t q_offset, const uint64_t* seed_dev, const int32_t* perm,
+                                   const float* evidence,
                                    int64_t se_q, int64_t se_f, int64_t se_r, int Qe, int squash, const float* y,
                                    int g0_allreps, const float* gy, float* dmu, float* dsigma, float* g0, void* stream) {
     if (!mu || !sigma || !ch || !gy || !dmu || !dsigma || Q < 0 || F <= 0 || I <= 0 || R <= 0 || card <= 0 || Rs <= 0)
@@ -291,7 +294,8 @@ extern "C" int spn_sample_leaf_bwd(const float* mu, const float* sigma, int Wset
     if (Q == 0) return SPN_OK;
     SampleLeafBwdArgs a{};
     a.mu = mu; a.sigma = sigma; a.Wsets = Wsets; a.w = w; a.Q = Q; a.F = F; a.I = I; a.R = R; a.card = card; a.Rs = Rs;
-    a.dP = dP; a.ch = ch; a.rep = rep; a.eps = eps; a.mpe = mpe; a.seed = seed; a.q_offset = q_offset; a.perm = perm;
+    a.dP = dP; a.ch = ch; a.rep = rep; a.eps = eps; a.mpe = mpe; a.seed = seed; a.q_offset = q_offset; a.seed_dev = seed_dev;
+    a.perm = perm;
     a.evidence = evidence; a.se_q = se_q; a.se_f = se_f; a.se_r = se_r; a.Qe = Qe; a.squash = squash; a.y = y;
     a.g0_allreps = g0_allreps ? 1 : 0; a.gy = gy; a.dmu = dmu; a.dsigma = dsigma; a.g0 = g0;
     const int64_t total = (int64_t)Q * dP * I * (g0_allreps ? R : Rs);

@@ -221,9 +221,7 @@ def sample_onehot(spn, ctx: Sample, class_index, evidence, layer_index: int, noi
     plan = _Plan()
     plan.mpe, plan.R, plan.card = bool(ctx.is_mpe), cfg.R, spn._leaf.cardinality
     plan.Qe = int(np.prod(evidence.shape[:-3])) if evidence is not None else 1
-    plan.seed = 0
-    if noise is None and not plan.mpe:
-        plan.seed = int(th.randint(0, 2 ** 62, (1,)).item())  # host RNG: reproducible under th.manual_seed, no sync
+    plan.seed = ops.new_seed(dev, plan.mpe or noise is not None)
 
     def take(shape):
         if plan.mpe or noise is None:

@@ -336,9 +336,10 @@ def sample_sum(lw, root, Q, d, Rs, pa, pa_strides, unravel, rep, xc, Qe, gumbel,
         if xc is None:
             c = int(round(math.sqrt(ic_top)))
     out = torch.empty(Q, d, Rs, device=lw.device, dtype=torch.int32)
+    hseed, dseed = _seed_args(seed)
     call("spn_sample_sum", ptr(lw), *sw, Wsets, w, Q, d, ic, oc, Rs, ptr(pa), *pa_strides, int(unravel), ptr(rep),
-         ptr(xc), *sxc, xc_din, c, Qe, 1 if root else 0, ic_top, ptr(gumbel), int(mpe), seed, q_offset, ptr(out),
-         stream_ptr(lw.device))
+         ptr(xc), *sxc, xc_din, c, Qe, 1 if root else 0, ic_top, ptr(gumbel), int(mpe), hseed, q_offset, dseed,
+         ptr(out), stream_ptr(lw.device))
     return out
 
 
@@ -351,8 +352,9 @@ def sample_leaf(mu, sigma, Q, card, Rs, pa, pa_strides, rep, eps, mpe, inv_perm3
     w = Wsets if Wsets != 1 else 1
     out = torch.empty(Q, F, Rs, device=mu.device, dtype=torch.float32)
     ch = torch.empty(Q, F, Rs, device=mu.device, dtype=torch.int32) if want_channels else None
+    hseed, dseed = _seed_args(seed)
     call("spn_sample_leaf", ptr(mu), ptr(sigma), Wsets, w, Q, F, I, R, card, Rs, ptr(pa), *pa_strides, ptr(rep),
-         ptr(eps), int(mpe), seed, q_offset, ptr(inv_perm32), ptr(evidence), *ev_strides, Qe, int(squash), ptr(out),
+         ptr(eps), int(mpe), hseed, q_offset, dseed, ptr(inv_perm32), ptr(evidence), *ev_strides, Qe, int(squash), ptr(out),
          ptr(ch), stream_ptr(mu.device))
     return out, ch
 
@@ -386,8 +388,9 @@ def sample_sum_backward(lw, root, Q, d, Rs, pa, pa_strides, unravel, rep, xc, Qe
     Wsets, ic, oc, ic_top, c, sw, xc_din, sxc = _sum_sample_geometry(lw, root, xc)
     w = Wsets if Wsets != 1 else 1
     gp = torch.empty(Q, d, oc, Rs, device=lw.device, dtype=torch.float32) if want_parent and not root else None
+    hseed, dseed = _seed_args(seed)
     call("spn_sample_sum_bwd", ptr(lw), *sw, Wsets, w, Q, d, ic, oc, Rs, ptr(pa), *pa_strides, int(unravel), ptr(rep),
-         ptr(xc), *sxc, xc_din, c, Qe, 1 if root else 0, ic_top, ptr(gumbel), seed, q_offset, ptr(gc), gc_d,
+         ptr(xc), *sxc, xc_din, c, Qe, 1 if root else 0, ic_top, ptr(gumbel), hseed, q_offset, dseed, ptr(gc), gc_d,
          int(gc_allreps), ptr(dlw), ptr(dxc), ptr(gp), stream_ptr(lw.device))
     return gp
 
@@ -402,10 +405,30 @@ def sample_leaf_backward(mu, sigma, Q, card, Rs, ch, rep, eps, mpe, seed, perm32
     dP = -(-F // card)
     dmu, dsigma = torch.zeros_like(mu), torch.zeros_like(sigma)
     g0 = torch.empty(Q, dP, I, R if g0_allreps else Rs, device=mu.device, dtype=torch.float32) if want_g0 else None
+    hseed, dseed = _seed_args(seed)
     call("spn_sample_leaf_bwd", ptr(mu), ptr(sigma), Wsets, w, Q, F, I, R, card, Rs, dP, ptr(ch), ptr(rep), ptr(eps),
-         int(mpe), seed, q_offset, ptr(perm32), ptr(evidence), *ev_strides, Qe, int(squash), ptr(y), int(g0_allreps), ptr(gy),
+         int(mpe), hseed, q_offset, dseed, ptr(perm32), ptr(evidence), *ev_strides, Qe, int(squash), ptr(y), int(g0_allreps), ptr(gy),
          ptr(dmu), ptr(dsigma), ptr(g0), stream_ptr(mu.device))
     return dmu, dsigma, g0
+
+
+def _seed_args(seed):
+    """(host seed, device seed pointer): ``seed`` is an int, or a one-element int64 CUDA tensor read by the kernels."""
+    if isinstance(seed, torch.Tensor):
+        assert seed.is_cuda and seed.dtype == torch.int64 and seed.numel() == 1
+        return 0, ptr(seed)
+    return int(seed), None
+
+
+def new_seed(device, mpe: bool = False):
+    """Seed for the in-kernel noise of one sampling pass.  Eager: a host integer from torch's CPU generator
+    (reproducible under torch.manual_seed, no device work).  While a CUDA graph is being captured: a device word drawn
+    with torch's graph-safe CUDA generator, so every replay of the graph samples fresh noise."""
+    if mpe:
+        return 0
+    if torch.device(device).type == "cuda" and torch.cuda.is_current_stream_capturing():
+        return torch.randint(0, 2 ** 62, (1,), device=device, dtype=torch.int64)
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
 
 
 def launches() -> int:
@@ -436,6 +459,8 @@ def tc_prepare(w: torch.Tensor, raw: bool = False):
 
 def tc_prepare_cached(w: torch.Tensor, raw: bool, cache):
     """(wimg, logz) for ``w``; re-used from ``cache`` while the tensor (storage, version) is unchanged."""
+    if torch.cuda.is_current_stream_capturing():
+        cache = None  # a captured graph must rebuild the image on every replay (the weights change between replays)
     key = (w.data_ptr(), w._version, tuple(w.shape), bool(raw))
     if cache is not None and cache.get("key") == key:
         return cache["wimg"], cache["logz"]

@@ -351,9 +351,7 @@ class RatSpn(nn.Module):
             w = class_index.shape[0] if class_index is not None else W
             Qe = 1
         is_mpe = ctx.is_mpe
-        seed = 0
-        if noise is None and not is_mpe:
-            seed = int(th.randint(0, 2 ** 62, (1,)).item())  # host RNG: reproducible under th.manual_seed, no sync
+        seed = ops.new_seed(dev, is_mpe or noise is not None)  # host integer; a device word under graph capture
 
         def take(shape):
             if is_mpe or noise is None:

@@ -146,14 +146,17 @@ int spn_xprod_bwd(const float* g, int B, int d_in, int c, int R, float* dx, void
  *           strides; the posterior logit offset is xc[qe, 2s, l, r] + xc[qe, 2s+1, r', r], qe = q % Qe
  *   root    1: this is the root Sum over R*ic_top channels (d = 1, Rs = 1); the repetition is i / ic_top
  *   gumbel  [Q, d, ic, Rs] contiguous noise, or NULL with mpe = 1 (argmax) or mpe = 0 (in-kernel Philox, keyed by
- *           seed and the global element index q_offset-shifted so results do not depend on the GPU count)
+ *           seed and the global element index q_offset-shifted so results do not depend on the GPU count);
+ *           seed_dev != NULL: the seed is read from device memory instead (one uint64), so that a captured CUDA
+ *           graph draws fresh noise on every replay when the caller refreshes that word inside the graph)
  *   out     int32 [Q, d, Rs] chosen in-channel (first maximal index)
  * ------------------------------------------------------------------------------------------------------------- */
 int spn_sample_sum(const float* lw, int64_t sw_w, int64_t sw_d, int64_t sw_i, int64_t sw_o, int64_t sw_r, int Wsets,
                    int w, int Q, int d, int ic, int oc, int Rs, const int32_t* pa, int64_t sp_q, int64_t sp_s,
                    int64_t sp_r, int unravel, const int32_t* rep, const float* xc, int64_t sxc_b, int64_t sxc_d,
                    int64_t sxc_c, int64_t sxc_r, int xc_din, int c, int Qe, int root, int ic_top,
-                   const float* gumbel, int mpe, uint64_t seed, uint64_t q_offset, int32_t* out, void* stream);
+                   const float* gumbel, int mpe, uint64_t seed, uint64_t q_offset, const uint64_t* seed_dev,
+                   int32_t* out, void* stream);
 
 /* Leaf step of sampling fused with the post-processing: channel fan-out to features, (mu, sigma) gather, Gaussian
  * draw, inverse permutation of the selected repetition, evidence fill-in, clamp+tanh.
@@ -166,7 +169,8 @@ int spn_sample_sum(const float* lw, int64_t sw_w, int64_t sw_d, int64_t sw_i, in
  * ------------------------------------------------------------------------------------------------------------- */
 int spn_sample_leaf(const float* mu, const float* sigma, int Wsets, int w, int Q, int F, int I, int R, int card,
                     int Rs, const int32_t* pa, int64_t sp_q, int64_t sp_s, int64_t sp_r, const int32_t* rep,
-                    const float* eps, int mpe, uint64_t seed, uint64_t q_offset, const int32_t* inv_perm,
+                    const float* eps, int mpe, uint64_t seed, uint64_t q_offset, const uint64_t* seed_dev,
+                    const int32_t* inv_perm,
                     const float* evidence, int64_t se_q, int64_t se_f, int64_t se_r, int Qe, int squash,
                     float* out, int32_t* ch_out, void* stream);
 
@@ -190,11 +194,13 @@ int spn_sample_sum_bwd(const float* lw, int64_t sw_w, int64_t sw_d, int64_t sw_i
                        int Wsets, int w, int Q, int d, int ic, int oc, int Rs, const int32_t* pa, int64_t sp_q,
                        int64_t sp_s, int64_t sp_r, int unravel, const int32_t* rep, const float* xc, int64_t sxc_b,
                        int64_t sxc_d, int64_t sxc_c, int64_t sxc_r, int xc_din, int c, int Qe, int root, int ic_top,
-                       const float* gumbel, uint64_t seed, uint64_t q_offset, const float* gc, int gc_d, int gc_allreps,
+                       const float* gumbel, uint64_t seed, uint64_t q_offset, const uint64_t* seed_dev, const float* gc,
+                       int gc_d, int gc_allreps,
                        float* dlw, float* dxc, float* gparent, void* stream);
 int spn_sample_leaf_bwd(const float* mu, const float* sigma, int Wsets, int w, int Q, int F, int I, int R, int card,
                         int Rs, int dP, const int32_t* ch, const int32_t* rep, const float* eps, int mpe, uint64_t seed,
-                        uint64_t q_offset, const int32_t* perm, const float* evidence, int64_t se_q, int64_t se_f,
+                        uint64_t q_offset, const uint64_t* seed_dev, const int32_t* perm, const float* evidence, int64_t se_q,
+                        int64_t se_f,
                         int64_t se_r, int Qe, int squash, const float* y, int g0_allreps, const float* gy, float* dmu,
                         float* dsigma, float* g0, void* stream);
 

@@ -89,8 +89,32 @@ def cfg3():
 
     ms, launches = timed(update, reps=5)
     ms_r, launches_r = timed(rollout, reps=20)
+    # the same update captured into one CUDA graph (graphs.GraphedCall): grads pre-allocated and zeroed in place
+    params = [p for p in m.parameters() if p.requires_grad]
+    for p in params:
+        p.grad = torch.zeros_like(p)
+
+    def update_static():
+        for p in params:
+            p.grad.zero_()
+        ctx = m.sample(mode="onehot", condition=obs, evidence=ev)
+        H, _ = m.recursive_entropy_approx(condition=obs, sample_size=5, marginal_mask=failed)
+        act = ctx.sample.reshape(B, 17)
+        (-(0.1 * H + act.sum(-1)).mean()).backward()
+        (-m(xs, condition=obs).mean()).backward()
+        return act
+    g = rb.GraphedCall(update_static)
+    ms_g, _ = timed(g, reps=20)
+    obs1, ev1 = obs[:1].clone(), ev[:, :1].clone()
+
+    def rollout_static():
+        with torch.no_grad():
+            return m.sample(mode="index", condition=obs1, evidence=ev1).sample
+    gr = rb.GraphedCall(rollout_static)
+    ms_gr, _ = timed(gr, reps=50)
     return {"config": "cfg3 CSPN SAC update obs 376 / act 17, R=I=S=3 D=4, B=256: onehot sample + evidence, recursive "
-                      "entropy (n=5, mask) fwd+bwd, LL fwd+bwd", "us_per_update": ms * 1e3, "abi_calls_per_update": launches,
+                      "entropy (n=5, mask) fwd+bwd, LL fwd+bwd", "us_per_update": ms * 1e3, "us_per_update_cuda_graph": ms_g * 1e3,
+            "rollout_index_sample_with_evidence_B1_us_cuda_graph": ms_gr * 1e3, "abi_calls_per_update": launches,
             "rollout_index_sample_with_evidence_B1_us": ms_r * 1e3, "abi_calls_per_rollout": launches_r,
             "reference_cpu_ms (SURVEY 6, 8 cores)": 2700.0,
             "note": "latency bound: 1467 circuit parameters per conditional; roofline fractions are meaningless here"}
