@@ -195,6 +195,12 @@ class CSPN(RatSpn):
             self.set_params(condition)
         return super().naive_entropy_approx(**kwargs)
 
+    def huber_entropy_lb(self, condition: th.Tensor = None, **kwargs):
+        """Huber et al. entropy lower bound of p(. | condition)   (cspn.py:112-115)."""
+        if condition is not None:
+            self.set_params(condition)
+        return super().huber_entropy_lb(**kwargs)
+
     def sample(self, mode: str = None, condition: th.Tensor = None, class_index=None, evidence: th.Tensor = None,
                **kwargs):
         """Sample x ~ p(. | condition)   (cspn.py:125-145)."""

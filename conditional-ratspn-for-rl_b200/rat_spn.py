@@ -612,10 +612,12 @@ class RatSpn(nn.Module):
         """{"lay{L}/rep{r}/{metric}/{min,max,mean,std}": float}; the statistics of all repetitions are reduced on the
         device and fetched with one transfer per metric (the reference issues 4*R .item() syncs, rat_spn.py:752-774)."""
         log_dict = {}
+        # the number of repetitions reported is that of the FIRST metric, for every metric (rat_spn.py:754)
+        n_rep = list(metrics.values())[0].size(rep_dim)
         for key, metric in metrics.items():
             if metric is None:
                 continue
-            m = metric.to(self.device).movedim(rep_dim, 0)
+            m = metric.to(self.device).movedim(rep_dim, 0)[:n_rep]
             R = m.shape[0]
             flat = m.reshape(R, -1)
             stats = [flat.min(dim=1).values, flat.max(dim=1).values, flat.mean(dim=1)]
@@ -663,6 +665,78 @@ class RatSpn(nn.Module):
             samples = th.where(marginal_mask.expand_as(samples), th.full_like(samples, float('nan')), samples)
         samples = samples.movedim(0, -1).unsqueeze(-1)  # 'o...d -> ...do' then a repetition dim
         return -self.forward(samples, layer_index=layer_index).mean()
+
+    def huber_entropy_lb(self, layer_index: int = None, verbose=True, detach_weights: bool = False,
+                         add_sub_weight_ent: bool = False, marginal_mask: th.Tensor = None):
+        """Entropy lower bound for mixtures of Huber et al. (2008), evaluated layer by layer (rat_spn.py:825-951):
+        H(sum_k w_k p_k) >= -sum_k w_k log sum_j w_j z_kj with the pairwise overlaps z_kj = int p_k p_j dx.
+
+        The pass carries the log-overlaps L[w, scope, a, b, ra, rb] between node a of repetition ra and node b of
+        repetition rb.  Leaves: int N(x; m1, v1) N(x; m2, v2) dx = N(m1; m2, v1 + v2); overlaps multiply across the
+        scopes joined by a Product / CrossProduct (logs add) and mix linearly through Sum weights.  Returns
+        (bound for the nodes of ``layer_index`` -- [w, d, oc, R], or [w, 1, C] at the root -- , logging dict).
+        Like the reference, the leaf Product requires F to be a multiple of its cardinality and the pairing of
+        repetitions uses the permutation of the second repetition index.
+        """
+        logging = {}
+        entropy_lb = None
+        if layer_index is None:
+            layer_index = self.max_layer_index
+        assert 1 <= layer_index <= self.max_layer_index, "layer_index must address an inner layer or the root"
+        base = self._leaf.base_leaf
+        if marginal_mask is not None:
+            shape_should = tuple(base.mean_param.shape[:2])
+            assert tuple(marginal_mask.shape) == shape_should, \
+                f"marginal_mask is of shape {tuple(marginal_mask.shape)} but needs to have shape {shape_should}"
+            marginal_mask = marginal_mask.clone().bool()
+
+        # leaf overlaps in the original feature order, [w, F, a, b, ra, rb]
+        mu = self.apply_inv_permutation(self.means)
+        var = self.apply_inv_permutation(self.var)
+        v = var[:, :, :, None, :, None] + var[:, :, None, :, None, :]
+        diff = mu[:, :, :, None, :, None] - mu[:, :, None, :, None, :]
+        L = -0.5 * diff * diff / v - 0.5 * v.log() - 0.5 * np.log(2.0 * np.pi)
+        if marginal_mask is not None:
+            L = L.masked_fill(marginal_mask.view(*marginal_mask.shape, 1, 1, 1, 1), 0.0)
+        L = th.gather(L, dim=1, index=self.permutation.view(1, -1, 1, 1, 1, self.config.R).expand_as(L))
+        w, F_, I_, _, R, _ = L.shape
+        card = self._leaf.prod.cardinality
+        assert F_ % card == 0, "huber_entropy_lb needs F to be a multiple of the leaf cardinality"
+        L = L.view(w, F_ // card, card, I_, I_, R, R).sum(2)
+
+        for i in range(1, layer_index + 1):
+            layer = self.layer_index_to_obj(i)
+            if isinstance(layer, CrossProduct):
+                left, right = layer.split_shuffled_scopes(L, 1)  # each [w, d, o, o, R, R]
+                w, d, o = left.shape[:3]
+                # pair channel (a', a) of the new node = (right child a', left child a), likewise (b', b)
+                L = (right[:, :, :, None, :, None] + left[:, :, None, :, None, :]).reshape(w, d, o * o, o * o, R, R)
+                continue
+            log_w = layer.weights
+            weight_entropy = -(log_w * log_w.exp()).sum(dim=2)
+            is_root = i == self.max_layer_index
+            weights = self.root_weights_split_by_rep if is_root else log_w
+            if detach_weights:
+                weights = weights.detach()
+            # M[w, d, a, o, ra, rb] = log sum_b w[b, o, rb] z[a, b, ra, rb]
+            M = (L.unsqueeze(-3) + weights.unsqueeze(2).unsqueeze(-2)).logsumexp(3)
+            if add_sub_weight_ent:
+                we = weight_entropy.unsqueeze(2).unsqueeze(-1)
+                M = M - we + we.detach()
+            if is_root:
+                M = M.logsumexp(-1)  # the root mixes over repetitions as well
+            if verbose or i == layer_index:
+                own = M if is_root else th.diagonal(M, dim1=-2, dim2=-1)
+                entropy_lb = -(weights.exp() * own).sum(dim=-3)
+                if is_root:
+                    entropy_lb = entropy_lb.sum(-1)
+            if i < layer_index:
+                # L'[w, d, o1, o2, ra, rb] = log sum_a w[a, o2, ra] exp(M[a, o1, ra, rb])
+                L = (M.unsqueeze(-3) + weights.unsqueeze(-3).unsqueeze(-1)).logsumexp(2)
+            if verbose:
+                metrics = {'weight_entropy': weight_entropy.detach(), 'huber_entropy_LB': entropy_lb.detach()}
+                logging.update(self.log_dict_from_metric(i, metrics, batch_dim=None))
+        return entropy_lb, logging
 
     # ------------------------------------------------------------------------------------------ misc API
     def debug__set_weights_dirac(self, layer_index):

@@ -1,7 +1,8 @@
 """Sampling context and evidence context manager (API of the reference's utils.py:52-145)."""
+import os
 from contextlib import contextmanager, nullcontext
 from dataclasses import dataclass, fields
-from typing import Tuple, Union
+from typing import List, Tuple, Union
 
 import torch as th
 from torch import nn
@@ -65,3 +66,35 @@ class Sample:
             k = len(self.n) + 1
             assert self.parent_indices is None or tuple(self.parent_indices.shape[1:k]) == tuple(self.n)
             assert self.repetition_indices is None or tuple(self.repetition_indices.shape[1:k]) == tuple(self.n)
+
+
+def non_existing_folder_name(base_dir: str, folder_name: str, create_path: bool = True) -> str:
+    """``folder_name``, or ``folder_name__<k>`` with the smallest k >= 1 that does not exist under ``base_dir`` yet
+    (utils.py:12-25); optionally creates it."""
+    candidate, k = folder_name, 0
+    while os.path.exists(os.path.join(base_dir, candidate)):
+        k += 1
+        candidate = f"{folder_name}__{k}"
+    if create_path:
+        os.makedirs(os.path.join(base_dir, candidate), exist_ok=False)
+    return candidate
+
+
+def flat_index_to_tensor_index(index: int, tensor_shape) -> List[int]:
+    """Row-major flat offset -> per-dimension indices (utils.py:28-39)."""
+    if isinstance(index, th.Tensor):
+        index = index.item()
+    out = []
+    for size in reversed(tuple(tensor_shape)[1:]):
+        index, rem = divmod(int(index), int(size))
+        out.append(rem)
+    out.append(int(index))
+    return out[::-1]
+
+
+def tensor_index_to_flat_index(index: List[int], tensor_shape) -> int:
+    """Per-dimension indices -> row-major flat offset (utils.py:42-49)."""
+    flat = 0
+    for ind, size in zip(index, tuple(tensor_shape)):
+        flat = flat * int(size) + int(ind)
+    return flat
