@@ -188,7 +188,8 @@ def main():
     B = args.batch
     model = build_model(dev)
     broadcast_parameters(model)
-    reducer = FlatGradAllReducer(model.parameters(), overlap=True)
+    overlap = os.environ.get("SPN_DP_OVERLAP", "1") != "0"
+    reducer = FlatGradAllReducer(model.parameters(), overlap=overlap)
     nbuf = 4
     gen = torch.Generator().manual_seed(1234 + rank)
     host = [torch.rand(B, 1, CFG["F"], 1, 1, generator=gen).pin_memory() for _ in range(nbuf)]
@@ -240,11 +241,18 @@ def main():
         def run(x, non_blocking=False):
             xin.copy_(x, non_blocking=non_blocking)
             return step(xin)
-    launches_per_step = None
+    # kernels of libspn_b200.so launched by one step, counted by CUPTI (torch.profiler) on one eager step: everything
+    # that is not an ATen / optimizer / NCCL / memset kernel.  (_abi.LAUNCHES counts ABI calls, several kernels each.)
     sync_all()
     l0 = _abi.LAUNCHES
-    step(resident[0])  # one eager step to count the launches a step consists of (graph replays do not pass the ABI)
-    launches_per_step = _abi.LAUNCHES - l0
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step(resident[0])
+        torch.cuda.synchronize()
+    abi_calls_per_step = _abi.LAUNCHES - l0
+    foreign = ("at::", "nccl", "multi_tensor", "cub::", "Memset", "Memcpy", "cutlass", "cublas", "elementwise")
+    launches_per_step = sum(e.count for e in prof.key_averages()
+                            if e.device_type.name == "CUDA" and not any(t in e.key for t in foreign))
     for i in range(2):
         run(resident[i % nbuf])
     sync_all()
@@ -359,7 +367,7 @@ def main():
                 "clocks": clk.summary(),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * CFG["F"] * 4,
                         "d2h_bytes_per_step": 4},
-                "gpu_launches": launches, "roofline": roof, "tc_kernels": kernels, "cpu_baseline": cb, "loss": loss_host}
+                "gpu_launches": launches, "abi_calls_per_step": abi_calls_per_step, "roofline": roof, "tc_kernels": kernels, "cpu_baseline": cb, "loss": loss_host}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
