@@ -348,7 +348,7 @@ def main():
         roof = {"bound": "tensor", "kernel": f"{dom}, layer S_1 (d=16, K=1600, N=40, R=40), "
                                              f"{kernels[dom]['flops']:.3e} flop per call (2*N*d*c^2*S*R per GEMM)",
                 "achieved": kernels[dom]["achieved_tflops"], "peak": peak, "unit": "TFLOP/s",
-                "frac": kernels[dom]["frac"], "traffic": ncu.get(dom), "kernel_ms": kernels[dom]["ms"],
+                "frac": kernels[dom]["frac"], "traffic": kernels[dom]["traffic"], "kernel_ms": kernels[dom]["ms"],
                 "peak_source": src}
 
     if rank == 0:

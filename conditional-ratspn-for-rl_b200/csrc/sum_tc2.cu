@@ -638,77 +638,106 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
 // Weight operand preparation
 // ---------------------------------------------------------------------------------------------------------------
 // Log-normaliser of the unnormalised weights: logz[s][o][r] = logsumexp_k param[s][k][o][r]  (F.log_softmax(dim=2) of
-// layers.py:85 is then lw = param - logz, applied by the consumers).  Block = 64 consecutive (o, r) columns x 4 k-phases;
-// every warp load is one 128-byte line; online max/sum so the parameters are read once.
+// layers.py:85 is then lw = param - logz, applied by the consumers).  Block = 64 consecutive (o, r) columns (16 threads
+// x float4 = one 256-byte segment per row) x 16 k-phases, four rows in flight per thread (16 KB per block); online
+// max / sum per column so the parameters are read once.  Requires ocr % 4 == 0.
+__device__ __forceinline__ void logz_update(float& m, float& acc, float v0, float v1, float v2, float v3) {
+    const float mn = fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), m);
+    if (mn != -CUDART_INF_F) {
+        acc = acc * __expf(m - mn) + __expf(v0 - mn) + __expf(v1 - mn) + __expf(v2 - mn) + __expf(v3 - mn);
+        m = mn;
+    }
+}
+
 __global__ void __launch_bounds__(256) tc_logz_kernel(const float* __restrict__ param, float* __restrict__ logz, int K,
                                                      int ocr, int tiles_per_s) {
-    __shared__ float sm_m[4][64], sm_s[4][64];
+    __shared__ float sm_m[16][64], sm_s[16][64];
     const int s = blockIdx.x / tiles_per_s;
-    const int col = (blockIdx.x % tiles_per_s) * 64 + (threadIdx.x & 63);
-    const int ph = threadIdx.x >> 6;
-    float m = -CUDART_INF_F, acc = 0.f;
+    const int cq = threadIdx.x & 15, ph = threadIdx.x >> 4;
+    const int col = (blockIdx.x % tiles_per_s) * 64 + cq * 4;
+    float m[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (col < ocr) {
-        const float* p = param + (int64_t)s * K * ocr + col;
+        const float4* p = reinterpret_cast<const float4*>(param + (int64_t)s * K * ocr + col);
+        const int64_t rs = ocr / 4;
         int k = ph;
-        for (; k + 12 < K; k += 16) {  // four independent loads in flight per thread
-            const float v0 = p[(int64_t)k * ocr], v1 = p[(int64_t)(k + 4) * ocr], v2 = p[(int64_t)(k + 8) * ocr],
-                        v3 = p[(int64_t)(k + 12) * ocr];
-            const float mn = fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), m);
-            if (mn != -CUDART_INF_F) {
-                acc = acc * __expf(m - mn) + __expf(v0 - mn) + __expf(v1 - mn) + __expf(v2 - mn) + __expf(v3 - mn);
-                m = mn;
-            }
+        for (; k + 48 < K; k += 64) {
+            const float4 a0 = __ldg(p + (int64_t)k * rs), a1 = __ldg(p + (int64_t)(k + 16) * rs),
+                         a2 = __ldg(p + (int64_t)(k + 32) * rs), a3 = __ldg(p + (int64_t)(k + 48) * rs);
+            logz_update(m[0], acc[0], a0.x, a1.x, a2.x, a3.x);
+            logz_update(m[1], acc[1], a0.y, a1.y, a2.y, a3.y);
+            logz_update(m[2], acc[2], a0.z, a1.z, a2.z, a3.z);
+            logz_update(m[3], acc[3], a0.w, a1.w, a2.w, a3.w);
         }
-        for (; k < K; k += 4) {
-            const float v = p[(int64_t)k * ocr];
-            const float mn = fmaxf(m, v);
-            if (mn != -CUDART_INF_F) {
-                acc = acc * __expf(m - mn) + __expf(v - mn);
-                m = mn;
-            }
+        for (; k < K; k += 16) {
+            const float4 a0 = __ldg(p + (int64_t)k * rs);
+            const float ninf = -CUDART_INF_F;
+            logz_update(m[0], acc[0], a0.x, ninf, ninf, ninf);
+            logz_update(m[1], acc[1], a0.y, ninf, ninf, ninf);
+            logz_update(m[2], acc[2], a0.z, ninf, ninf, ninf);
+            logz_update(m[3], acc[3], a0.w, ninf, ninf, ninf);
         }
     }
-    sm_m[ph][threadIdx.x & 63] = m;
-    sm_s[ph][threadIdx.x & 63] = acc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        sm_m[ph][cq * 4 + j] = m[j];
+        sm_s[ph][cq * 4 + j] = acc[j];
+    }
     __syncthreads();
-    if (ph == 0 && col < ocr) {
-        float mm = fmaxf(fmaxf(sm_m[0][threadIdx.x], sm_m[1][threadIdx.x]), fmaxf(sm_m[2][threadIdx.x], sm_m[3][threadIdx.x]));
+    const int c = threadIdx.x;
+    const int ocol = (blockIdx.x % tiles_per_s) * 64 + c;
+    if (c < 64 && ocol < ocr) {
+        float mm = -CUDART_INF_F;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) mm = fmaxf(mm, sm_m[q][c]);
         float tot = 0.f;
         if (mm != -CUDART_INF_F) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) tot += sm_s[q][threadIdx.x] * __expf(sm_m[q][threadIdx.x] - mm);
+            for (int q = 0; q < 16; ++q) tot += sm_s[q][c] * __expf(sm_m[q][c] - mm);
         }
-        logz[(int64_t)s * ocr + col] = mm == -CUDART_INF_F ? -CUDART_INF_F : mm + logf(tot);
+        logz[(int64_t)s * ocr + ocol] = mm == -CUDART_INF_F ? -CUDART_INF_F : mm + logf(tot);
     }
 }
 
 // fp32 (log-)weights [1][d][K][OC][R]  ->  bf16 exp() core-matrix image [d][R][K/8][OC/8][8 (k)][8 (o)].
-// One block per (scope, group of 8 k-values): the [8][OC][R] slab is read coalesced into shared memory, then every thread
-// assembles whole 16-byte image rows (8 outputs of one k): consecutive threads take consecutive repetitions, so the
-// shared-memory reads are conflict free and the stores are full 16-byte chunks.
+// One block per (scope, group of 8 k-values): the [8][OC][R] slab is read with coalesced float4 loads into a padded
+// shared-memory tile [8][OC][R|1] (+ pad so that the k-stride is 9 mod 32 banks); then every thread assembles one
+// 16-byte image row (8 outputs of one k), consecutive threads taking consecutive rows of one repetition so that both
+// the shared-memory reads (conflict free) and the global stores (640 contiguous bytes per repetition) are efficient.
 __global__ void __launch_bounds__(256) tc_wimage_kernel(const float* __restrict__ lw, const float* __restrict__ logz,
-                                                       uint8_t* __restrict__ wimg, int d, int K, int OC, int R) {
-    extern __shared__ float tile[];  // [8][OC][R]
+                                                       uint8_t* __restrict__ wimg, int d, int K, int OC, int R, int RP,
+                                                       int KS) {
+    extern __shared__ float tile[];  // [8][KS], row (kk, o) at kk * KS + o * RP
     const int kg = blockIdx.x % (K / 8);
     const int s = blockIdx.x / (K / 8);
-    const int n = 8 * OC * R;
-    const float* src = lw + ((int64_t)s * K + (int64_t)kg * 8) * OC * R;
     const int ocr = OC * R;
-    const float* zp = logz ? logz + (int64_t)s * ocr : nullptr;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) tile[i] = __expf(src[i] - (zp ? zp[i % ocr] : 0.f));
+    const float4* src = reinterpret_cast<const float4*>(lw + ((int64_t)s * K + (int64_t)kg * 8) * ocr);
+    const float4* zp = logz ? reinterpret_cast<const float4*>(logz + (int64_t)s * ocr) : nullptr;
+    const int n4 = 2 * ocr;  // 8 * ocr / 4
+    for (int i4 = threadIdx.x; i4 < n4; i4 += blockDim.x) {
+        const int i = i4 * 4;
+        const int kk = i / ocr, rem = i - kk * ocr;
+        const float4 v = __ldg(src + i4);
+        const float4 z = zp ? __ldg(zp + rem / 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float e[4] = {__expf(v.x - z.x), __expf(v.y - z.y), __expf(v.z - z.z), __expf(v.w - z.w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // (OC * R) % 4 == 0, so the four values share kk; R itself may be odd
+            const int o = (rem + j) / R, r = rem + j - o * R;
+            tile[kk * KS + o * RP + r] = e[j];
+        }
+    }
     __syncthreads();
     const int NOG = OC / 8;
     uint4* dst = reinterpret_cast<uint4*>(wimg);
-    // work item = (og, kk, r) with r fastest
+    // work item = (r, og, kk) with kk fastest: chunk index inside (s, r) is (kg * NOG + og) * 8 + kk
     for (int i = threadIdx.x; i < NOG * 8 * R; i += blockDim.x) {
-        const int r = i % R, kk = (i / R) % 8, og = i / (8 * R);
-        const float* t = tile + (kk * OC + og * 8) * R + r;
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(t[0], t[R]), p1 = __floats2bfloat162_rn(t[2 * R], t[3 * R]);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(t[4 * R], t[5 * R]), p3 = __floats2bfloat162_rn(t[6 * R], t[7 * R]);
+        const int kk = i & 7, og = (i >> 3) % NOG, r = i / (8 * NOG);
+        const float* t = tile + kk * KS + og * 8 * RP + r;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(t[0], t[RP]), p1 = __floats2bfloat162_rn(t[2 * RP], t[3 * RP]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(t[4 * RP], t[5 * RP]), p3 = __floats2bfloat162_rn(t[6 * RP], t[7 * RP]);
         uint4 v;
         v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
         v.z = *reinterpret_cast<uint32_t*>(&p2); v.w = *reinterpret_cast<uint32_t*>(&p3);
-        // chunk index inside (s, r): ((kg * NOG + og) * 8 + kk); one (s, r) image = K * NOG chunks
         dst[(((int64_t)s * R + r) * (K / 8) + kg) * (NOG * 8) + og * 8 + kk] = v;
     }
 }
@@ -792,12 +821,15 @@ extern "C" int spn_sum_tc_prepare(const float* lw, int d_out, int c, int oc, int
         int rc = spn_launch_status();
         if (rc != SPN_OK) return rc;
     }
-    const size_t smem = (size_t)8 * oc * R * sizeof(float);
+    const int RP = R | 1;
+    const int KS = oc * RP + ((9 - (oc * RP) % 32) + 32) % 32;
+    const size_t smem = (size_t)8 * KS * sizeof(float);
+    if (smem > 200 * 1024) return SPN_ERR_UNSUPPORTED;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(tc_wimage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return spn_cuda_status(e);
     }
-    tc_wimage_kernel<<<d_out * (K / 8), 256, smem, st>>>(lw, logz, (uint8_t*)wimg, d_out, K, oc, R);
+    tc_wimage_kernel<<<d_out * (K / 8), 256, smem, st>>>(lw, logz, (uint8_t*)wimg, d_out, K, oc, R, RP, KS);
     int rc = spn_launch_status();
     if (rc != SPN_OK) return rc;
     const int64_t img_bytes = (int64_t)d_out * R * K * oc * 2;

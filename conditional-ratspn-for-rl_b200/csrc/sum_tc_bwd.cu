@@ -313,6 +313,48 @@ __global__ void __launch_bounds__(256) tc_dw_finish_kernel(const float* __restri
     }
 }
 
+// Same, vectorised for R % 4 == 0 and OC % 4 == 0: float4 on both sides (dwt rows of KT*OC floats; parameter rows with r
+// innermost), index arithmetic once per four values.
+__global__ void __launch_bounds__(256) tc_dw_finish_vec_kernel(const float* __restrict__ lw, const float* __restrict__ logz,
+                                                              const float* __restrict__ csum, const float* __restrict__ dwt,
+                                                              float* __restrict__ dlw, int d, int K, int OC, int R) {
+    extern __shared__ float tile[];  // [R][KT*OC + 1]
+    constexpr int KT = 4;
+    const int kt = blockIdx.x % (K / KT);
+    const int s = blockIdx.x / (K / KT);
+    const int n = KT * OC, n4 = n / 4;
+    {
+        const int rows_per_pass = blockDim.x / n4;
+        const int rr = threadIdx.x / n4, e4 = threadIdx.x - rr * n4;
+        if (rr < rows_per_pass) {
+            for (int r = rr; r < R; r += rows_per_pass) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(dwt + (((int64_t)s * R + r) * K + (int64_t)kt * KT) * OC) + e4);
+                float* t = tile + r * (n + 1) + 4 * e4;
+                t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t base = ((int64_t)s * K + (int64_t)kt * KT) * OC * R;
+    const int ocr = OC * R, R4 = R / 4;
+    const float4* lw4 = reinterpret_cast<const float4*>(lw + base);
+    float4* out4 = reinterpret_cast<float4*>(dlw + base);
+    for (int i4 = threadIdx.x; i4 < n * R4; i4 += blockDim.x) {
+        const int e = i4 / R4, r = 4 * (i4 - e * R4);
+        float4 w = __ldg(lw4 + i4);
+        const float* t = tile + r * (n + 1) + e;
+        float4 dv = make_float4(t[0], t[n + 1], t[2 * (n + 1)], t[3 * (n + 1)]);
+        if (logz) {
+            const int zc = s * ocr + (e % OC) * R + r;
+            const float4 z = __ldg(reinterpret_cast<const float4*>(logz + zc));
+            const float4 c = __ldg(reinterpret_cast<const float4*>(csum + zc));
+            w.x -= z.x; w.y -= z.y; w.z -= z.z; w.w -= z.w;
+            dv.x -= c.x; dv.y -= c.y; dv.z -= c.z; dv.w -= c.w;
+        }
+        out4[i4] = make_float4(__expf(w.x) * dv.x, __expf(w.y) * dv.y, __expf(w.z) * dv.z, __expf(w.w) * dv.w);
+    }
+}
+
 extern "C" int spn_sum_tc_supported(int c, int oc, int R);
 
 template <int C, int OC, int NPAD, int GC>
@@ -368,7 +410,10 @@ extern "C" int spn_sum_tc_bwd_w(const void* fhand, const void* hand, const float
         if (rc != SPN_OK) return rc;
     }
     const size_t smem = (size_t)R * (4 * oc + 1) * sizeof(float);
-    tc_dw_finish_kernel<<<d_out * (K / 4), 256, smem, st>>>(lw, logz, csum, dwt_workspace, dlw, d_out, K, oc, R);
+    if (R % 4 == 0 && oc % 4 == 0 && oc <= 256)
+        tc_dw_finish_vec_kernel<<<d_out * (K / 4), 256, smem, st>>>(lw, logz, csum, dwt_workspace, dlw, d_out, K, oc, R);
+    else
+        tc_dw_finish_kernel<<<d_out * (K / 4), 256, smem, st>>>(lw, logz, csum, dwt_workspace, dlw, d_out, K, oc, R);
     return spn_launch_status();
 }
 
