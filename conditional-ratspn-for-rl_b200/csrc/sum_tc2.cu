@@ -49,6 +49,16 @@ __device__ unsigned long long g_tc2_prof[24];
 #define TC2_COUNT(slot) do { } while (0)
 #define TC2_FLUSH(base) do { } while (0)
 #endif
+// The experiment switches (SPN_TC_DEBUG: skip the MMAs / the TMEM stores / the multiplies ..., SPN_TC_N: MMA width) exist
+// only in the profiling build.  In the product build they are the constant 0: a run-time switch on them became a jump
+// table (LDC + BRX) on the MMA warp's per-stage critical path, ~150 clk per stage while the tensor pipe drained.
+#ifdef SPN_TC_PROFILE
+#define OPG_DEBUG(a) ((a).debug)
+#define OPG_DBGN(a) ((a).dbg_n)
+#else
+#define OPG_DEBUG(a) 0
+#define OPG_DBGN(a) 0
+#endif
 
 enum { OPG_FWD = 0, OPG_DXR = 1, OPG_DXL = 2 };
 
@@ -312,12 +322,12 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
                         if (step == STEPS - 1) acc_ready = mbar_probe_uniform(acc_empty + (ab ^ 1), (((m_tile + 1) >> 1) & 1) ^ 1);
                     }
                     const uint32_t abase = tmem_base + A_BASE + st * A_COLS;
-                    if (a.debug != 1 && a.debug != 8) {
+                    if (OPG_DEBUG(a) != 1 && OPG_DEBUG(a) != 8) {
                         // base descriptor of the stage (see opg_desc_delta): FWD advances 4*NVG K groups of NVG*128 bytes per
                         // stage; DX advances four u's = 4*NVG*NVG blocks of 128 bytes
                         const uint32_t sbytes = (uint32_t)step * (4 * NVG * NVG * 128);
                         const uint64_t dbase = MODE == OPG_FWD ? smem_desc(wsm_addr + sbytes, NVG * 128, 128) : smem_desc(wsm_addr + sbytes, 0, NVG * 128);
-                        opg_issue_stage<C, MODE>(acc, abase, dbase, a.dbg_n ? instr_desc_bf16(128, a.dbg_n, 0, MODE == OPG_FWD ? 1 : 0) : IDESC,
+                        opg_issue_stage<C, MODE>(acc, abase, dbase, OPG_DBGN(a) ? instr_desc_bf16(128, OPG_DBGN(a), 0, MODE == OPG_FWD ? 1 : 0) : IDESC,
                                                  step ? 1u : 0u);
                     }
                     mma_commit_uniform(st_empty + st);
@@ -365,7 +375,7 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
                 if (i < STEPS) {
                     e0 = my_u[(2 * i) * 128];
                     e1 = my_u[(2 * i + 1) * 128];
-                    if ((a.debug != 3 && a.debug < 7 || a.debug == 9)) {
+                    if ((OPG_DEBUG(a) != 3 && OPG_DEBUG(a) < 7 || OPG_DEBUG(a) == 9)) {
                         const uint32_t u0 = bcast_lo(e0), u1 = bcast_hi(e0);
 #pragma unroll
                         for (int q = 0; q < NPAIR; ++q) { p[q] = hmul2_bf16(u0, V[q]); p[NPAIR + q] = hmul2_bf16(u1, V[q]); }
@@ -382,15 +392,15 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
                     fence_after_sync();
                     TC2_T(t_w1);
                     TC2_ADD(1, t_w0, t_w1);
-                    if (a.debug != 2 && (a.debug != 3 && a.debug < 7 || a.debug == 9)) tmem_store_cols<C>(cols, p);
-                    if ((a.debug != 3 && a.debug < 7 || a.debug == 9)) {
+                    if (OPG_DEBUG(a) != 2 && (OPG_DEBUG(a) != 3 && OPG_DEBUG(a) < 7 || OPG_DEBUG(a) == 9)) tmem_store_cols<C>(cols, p);
+                    if ((OPG_DEBUG(a) != 3 && OPG_DEBUG(a) < 7 || OPG_DEBUG(a) == 9)) {
                         const uint32_t u0 = bcast_lo(e1), u1 = bcast_hi(e1);
 #pragma unroll
                         for (int q = 0; q < NPAIR; ++q) { p[q] = hmul2_bf16(u0, V[q]); p[NPAIR + q] = hmul2_bf16(u1, V[q]); }
                     }
                     if (more) e1 = my_u[(2 * (i + 2) + 1) * 128];
-                    if (a.debug != 2 && (a.debug != 3 && a.debug < 7 || a.debug == 9)) tmem_store_cols<C>(cols + C, p);
-                    if (more && (a.debug != 3 && a.debug < 7 || a.debug == 9)) {
+                    if (OPG_DEBUG(a) != 2 && (OPG_DEBUG(a) != 3 && OPG_DEBUG(a) < 7 || OPG_DEBUG(a) == 9)) tmem_store_cols<C>(cols + C, p);
+                    if (more && (OPG_DEBUG(a) != 3 && OPG_DEBUG(a) < 7 || OPG_DEBUG(a) == 9)) {
                         const uint32_t u0 = bcast_lo(e0n), u1 = bcast_hi(e0n);
 #pragma unroll
                         for (int q = 0; q < NPAIR; ++q) { p[q] = hmul2_bf16(u0, V[q]); p[NPAIR + q] = hmul2_bf16(u1, V[q]); }
@@ -463,7 +473,7 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
                     uint32_t e[NPAIR];
                     float m = 0.f;
                     if (from_fwd) {
-                    } else if ((a.debug != 4 && a.debug < 7 || a.debug == 9)) m = exp_pack<C>(v, e);
+                    } else if ((OPG_DEBUG(a) != 4 && OPG_DEBUG(a) < 7 || OPG_DEBUG(a) == 9)) m = exp_pack<C>(v, e);
                     else {
 #pragma unroll
                         for (int j = 0; j < NPAIR; ++j) e[j] = __float_as_uint(v[j]);
@@ -584,7 +594,7 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
 #pragma unroll
                     for (int q = 0; q < HC; ++q) av[q] = __uint_as_float(half ? accv[q + OFF1] : accv[q]);
                     const float* my_m = Ms + ab * 2 * 128 + row;
-                    if ((a.debug == 4 || a.debug == 7 || a.debug == 8)) {
+                    if ((OPG_DEBUG(a) == 4 || OPG_DEBUG(a) == 7 || OPG_DEBUG(a) == 8)) {
                     } else if (MODE == OPG_FWD) {
                         const float shift = my_m[0] + my_m[128];
                         float* op = a.y + (((int64_t)s * a.R + r) * a.B + bb) * C + half * HC;
@@ -600,7 +610,7 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
                             }
                             if (valid) *reinterpret_cast<float4*>(op + o4) = make_float4(res[0], res[1], res[2], res[3]);
                         }
-                        if (bad && valid && !a.debug) opg_exact_row<C, HC>(a, s, r, b, half * HC, op);
+                        if (bad && valid && !OPG_DEBUG(a)) opg_exact_row<C, HC>(a, s, r, b, half * HC, op);
                     } else {
                         const uint32_t* my_e = Es + ab * NPAIR * 128 + row;
                         const int sc = MODE == OPG_DXR ? 2 * s + 1 : 2 * s;

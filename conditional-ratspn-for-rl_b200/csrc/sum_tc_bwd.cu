@@ -13,6 +13,12 @@ using namespace tc;
 
 __device__ int g_tc_bwd_aborts = 0;
 
+#ifdef SPN_TC_PROFILE
+#define BWD_DEBUG(a) ((a).debug)
+#else
+#define BWD_DEBUG(a) 0   // experiment switches exist only in the profiling build
+#endif
+
 struct TcBwdArgs {
     const uint8_t* fhand; // per (s, r, row tile): packed eL, eR ([pair][128 rows] words) + shifts, written by the forward kernel
     const uint8_t* hand;  // per (s, r, row tile): G tile (B-operand layout), written by the dX kernel
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(320, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
                     fence_after_sync();
                     // A[M = k, K = row] MN-major: 8-element groups along M are 128 B apart, 8-row groups along K 2048 B
                     const uint64_t adesc = smem_desc(abuf_addr + st * A_BYTES, 2048, 128);
-                    if (a.debug != 1) dw_issue_chunk(tmem_base + ch * NPAD, adesc, bdesc, IDESC, tile ? 1u : 0u, (2 * CB * 128) >> 4);
+                    if (BWD_DEBUG(a) != 1) dw_issue_chunk(tmem_base + ch * NPAD, adesc, bdesc, IDESC, tile ? 1u : 0u, (2 * CB * 128) >> 4);
                     mma_commit_uniform(a_empty + st);
                 }
                 mma_commit_uniform(g_empty + vb);
@@ -191,7 +197,7 @@ __global__ void __launch_bounds__(320, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
                     uint8_t* my_a = abuf + st * A_BYTES + ((row >> 3) * 16) * 128 + (row & 7) * 16;
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        if (a.debug == 3) continue;
+                        if (BWD_DEBUG(a) == 3) continue;
 #pragma unroll
                         for (int li = 0; li < 8; ++li) {
                             const uint32_t e = el4[half][li >> 1];

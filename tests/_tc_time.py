@@ -27,7 +27,7 @@ if which in ("all", "bwdw"): timeit("tc bwd_w S_1", lambda: ops.tc_sum_backward_
 if which in ("all",): timeit("prepare", lambda: ops.tc_prepare(lw))
 print("aborts", ops.tc_aborts())
 import os, ctypes
-if os.environ.get("SPN_TC_DEBUG") in ("9", "3"):
+if os.environ.get("SPN_TC_DEBUG"):
     from ratspn_b200 import _abi
     buf = (ctypes.c_ulonglong * 24)()
     _abi.lib().spn_debug_tc_prof(buf, 1)

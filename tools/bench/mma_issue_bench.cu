@@ -7,14 +7,37 @@ using namespace tc;
 constexpr int NM = 1000;  // MMAs per measurement (100 stages of 10)
 constexpr uint32_t IDESC = instr_desc_bf16(128, 48, 0, 1);
 
+__device__ __forceinline__ void issue10(uint32_t a0, uint64_t d0, uint32_t s) {
+    asm volatile(
+        "{\n\t.reg .pred q, p;\n\t.reg .b64 d;\n\t.reg .b32 ta;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 d, %1;\n\tmov.b32 ta, %0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
+        "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
+        "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
+        "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
+        "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
+        "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
+        "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
+        "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
+        "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
+        "}" ::"r"(a0), "l"(d0), "r"(IDESC), "r"(0u), "r"(s ? 1u : 0u), "r"(0u)
+        : "memory");
+}
+
 template <int STYLE>
 __global__ void __launch_bounds__(160, 1) bench(long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
+    __shared__ uint64_t bars[6];
+    __shared__ int slot2;
     __shared__ uint32_t slot;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 32768 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1); slot2 = 0; mbar_fence_init(); }
     if (warp == 4) tmem_alloc(&slot, 512);
     fence_before_sync();
     __syncthreads();
@@ -54,24 +77,22 @@ __global__ void __launch_bounds__(160, 1) bench(long long* out) {
             for (int s = 0; s < NM / 10; ++s) {
                 const uint64_t d0 = smem_desc(wsm + (uint32_t)((s % 10) * 10) * 640, 640, 128);
                 const uint32_t a0 = 128 + (s & 3) * 80;
-                asm volatile(
-                    "{\n\t.reg .pred q, p;\n\t.reg .b64 d;\n\t.reg .b32 ta;\n\t"
-                    "elect.sync _|q, 0xffffffff;\n\t"
-                    "setp.ne.b32 p, %4, 0;\n\t"
-                    "mov.b64 d, %1;\n\tmov.b32 ta, %0;\n\t"
-                    "@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
-                    "setp.ne.b32 p, 1, 0;\n\t"
-                    "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
-                    "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
-                    "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
-                    "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
-                    "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
-                    "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
-                    "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
-                    "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
-                    "add.s64 d, d, 80;\n\tadd.s32 ta, ta, 8;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%5], [ta], d, %2, {%3, %3, %3, %3}, p;\n\t"
-                    "}" ::"r"(a0), "l"(d0), "r"(IDESC), "r"(0u), "r"(s ? 1u : 0u), "r"(0u)
-                    : "memory");
+                issue10(a0, d0, (uint32_t)s);
+            }
+        }
+        else if (STYLE >= 4) {
+            // 4: + one tcgen05.commit per stage; 5: + a probe (try_wait) before every stage; 6: two commits per stage;
+            // 7: commit + probe + a blocking wait on an already completed barrier
+#pragma unroll 1
+            for (int s = 0; s < NM / 10; ++s) {
+                const uint64_t d0 = smem_desc(wsm + (uint32_t)((s % 10) * 10) * 640, 640, 128);
+                const uint32_t a0 = 128 + (s & 3) * 80;
+                bool rdy = false;
+                if (STYLE == 5 || STYLE == 7) rdy = mbar_probe_uniform(&bars[4], 1);
+                issue10(a0, d0, (uint32_t)s);
+                mma_commit_uniform(&bars[s & 3]);
+                if (STYLE == 6) mma_commit_uniform(&bars[5]);
+                if (STYLE == 7 && !rdy) mbar_wait_sticky(&bars[4], 1, (volatile int*)&slot2);
             }
         }
         long long t1 = clock64();
@@ -102,6 +123,6 @@ void run(long long* d) {
 int main() {
     long long* d;
     cudaMalloc(&d, 16);
-    run<0>(d); run<1>(d); run<2>(d); run<3>(d);
+    run<0>(d); run<1>(d); run<2>(d); run<3>(d); run<4>(d); run<5>(d); run<6>(d); run<7>(d);
     return 0;
 }
