@@ -29,6 +29,8 @@ def build(force=False, verbose=False):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     extra = ["-DSPN_TC_PROFILE"] if os.environ.get("SPN_TC_PROFILE") else []  # per-phase clock64 hooks (perturbs timing)
+    if os.environ.get("SPN_TC_DEBUGSW"):
+        extra.append("-DSPN_TC_DEBUGSW")  # SPN_TC_DEBUG / SPN_TC_N experiment switches inside the tensor-core kernels
     cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:

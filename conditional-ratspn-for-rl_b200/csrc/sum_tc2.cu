@@ -50,9 +50,9 @@ __device__ unsigned long long g_tc2_prof[24];
 #define TC2_FLUSH(base) do { } while (0)
 #endif
 // The experiment switches (SPN_TC_DEBUG: skip the MMAs / the TMEM stores / the multiplies ..., SPN_TC_N: MMA width) exist
-// only in the profiling build.  In the product build they are the constant 0: a run-time switch on them became a jump
+// only in builds with -DSPN_TC_DEBUGSW.  In the product build they are the constant 0: a run-time switch on them became a jump
 // table (LDC + BRX) on the MMA warp's per-stage critical path, ~150 clk per stage while the tensor pipe drained.
-#ifdef SPN_TC_PROFILE
+#ifdef SPN_TC_DEBUGSW
 #define OPG_DEBUG(a) ((a).debug)
 #define OPG_DBGN(a) ((a).dbg_n)
 #else
@@ -805,6 +805,8 @@ static void opg_split(OpgArgs& a, int B, int d_out, int R) {
     int nsplit = (8 * 148 + d_out * R - 1) / (d_out * R);
     if (nsplit > a.ntiles / 4) nsplit = a.ntiles / 4;
     if (nsplit < 1) nsplit = 1;
+    const char* ns = getenv("SPN_TC_NSPLIT");  // tuning experiments
+    if (ns && atoi(ns) > 0 && atoi(ns) <= a.ntiles) nsplit = atoi(ns);
     a.nsplit = nsplit;
     const char* dbg = getenv("SPN_TC_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;

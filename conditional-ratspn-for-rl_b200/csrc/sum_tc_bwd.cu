@@ -13,7 +13,7 @@ using namespace tc;
 
 __device__ int g_tc_bwd_aborts = 0;
 
-#ifdef SPN_TC_PROFILE
+#ifdef SPN_TC_DEBUGSW
 #define BWD_DEBUG(a) ((a).debug)
 #else
 #define BWD_DEBUG(a) 0   // experiment switches exist only in the profiling build
