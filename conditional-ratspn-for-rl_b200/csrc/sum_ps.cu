@@ -114,6 +114,145 @@ __global__ void __launch_bounds__(1024) sum_ps_fwd_kernel(PsArgs a) {
     a.out[(b * a.d_out + s) * ocr + t] = res;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused backward for one row per weight set (B == w: the CSPN log-likelihood training step).  The slab of a
+// (conditional, scope) is read ONCE (TMA ring, as in the forward) and its gradient written ONCE (staged in shared memory,
+// TMA bulk store); the activation gradients of the two children fall out of the same pass:
+//     dlw[i,o,r] = g[o,r] * exp(xL[l,r] + xR[r',r] + lw[i,o,r] - out[o,r]),   i = l*c + r'
+//     dxL[l,r]   = sum_{r',o} dlw[(l,r'),o,r],      dxR[r',r] = sum_{l,o} dlw[(l,r'),o,r]
+// One thread per (o, r).  Per-thread partial sums (one for the current l, C for the r') are reduced over o with two
+// shuffles inside the warp and shared-memory atomics across warps.  Autograd of layers.py:110-128 + :419-440 for
+// per-sample weights.
+struct PsBwdArgs {
+    const float* x; int64_t sx_b, sx_d;
+    const float* lw; const float* out; const float* g;
+    float* dlw; float* dx; int64_t sdx_b, sdx_d;
+    int w, d_in, d_out, oc, R, rows_per_stage;
+};
+
+constexpr int PSB_NIN = 3;   // slab stages in flight (loads)
+constexpr int PSB_NOUT = 2;  // gradient stages (stores)
+
+template <int C>
+__global__ void __launch_bounds__(1024) sum_ps_bwd_kernel(PsBwdArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int ocr = a.oc * a.R, R = a.R;
+    constexpr int ic = C * C;
+    const int rps = a.rows_per_stage;                    // multiple of C
+    float* in_ring = reinterpret_cast<float*>(smem);                              // [PSB_NIN][rps][ocr]
+    float* out_ring = in_ring + PSB_NIN * rps * ocr;                              // [PSB_NOUT][rps][ocr]
+    float* xl = out_ring + PSB_NOUT * rps * ocr;                                  // [C][R]
+    float* xr = xl + C * R;                                                       // [C][R]
+    float* dxl = xr + C * R;                                                      // [C][R]
+    float* dxr = dxl + C * R;                                                     // [C][R]
+    uint64_t* full = reinterpret_cast<uint64_t*>(dxr + C * R);                    // [PSB_NIN]
+    const int s = blockIdx.x;
+    const int64_t b = blockIdx.y;
+    const int t = threadIdx.x, lane = t & 31;
+    const int r = t % R;
+    const int64_t slab_off = ((b * a.d_out + s) * (int64_t)ic) * ocr;
+    const float* slab = a.lw + slab_off;
+    float* gslab = a.dlw + slab_off;
+    const int nstage = ic / rps;
+
+    if (t == 0) {
+        for (int i = 0; i < PSB_NIN; ++i) mbar_init(full + i, 1);
+        mbar_fence_init();
+    }
+    const bool has_l = 2 * s < a.d_in, has_r = 2 * s + 1 < a.d_in;
+    for (int e = t; e < C * R; e += blockDim.x) {
+        xl[e] = has_l ? a.x[b * a.sx_b + (int64_t)(2 * s) * a.sx_d + e] : 0.f;
+        xr[e] = has_r ? a.x[b * a.sx_b + (int64_t)(2 * s + 1) * a.sx_d + e] : 0.f;
+        dxl[e] = 0.f;
+        dxr[e] = 0.f;
+    }
+    __syncthreads();
+    auto issue = [&](int k) {  // thread 0 only
+        const uint32_t bytes = (uint32_t)rps * ocr * 4;
+        uint64_t* bar = full + k % PSB_NIN;
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_g2s(in_ring + (k % PSB_NIN) * rps * ocr, slab + (int64_t)k * rps * ocr, bytes, bar);
+    };
+    if (t == 0)
+        for (int k = 0; k < min(PSB_NIN, nstage); ++k) issue(k);
+
+    constexpr float L2E = 1.4426950408889634f;
+    const float ov = a.out[(b * a.d_out + s) * ocr + t];
+    float gv = a.g[(b * a.d_out + s) * ocr + t];
+    const bool dead = ov == -CUDART_INF_F;   // impossible output: no gradient (th.logsumexp backward gives 0 * nan -> we give 0)
+    if (dead) gv = 0.f;
+    const float os = dead ? 0.f : ov * L2E;
+    float xrs[C];                            // right-child terms of this repetition, pre-scaled
+#pragma unroll
+    for (int q = 0; q < C; ++q) xrs[q] = xr[q * R + r] * L2E;
+    float acc_r[C];
+#pragma unroll
+    for (int q = 0; q < C; ++q) acc_r[q] = 0.f;
+    // reduction over o of a per-thread value: lanes with the same r inside a warp are `R` apart
+    const int same_r_in_warp = 32 / R;       // R divides 32 (checked on the host)
+    auto reduce_o_and_add = [&](float v, float* dst) {
+        for (int sh = R; sh < 32; sh <<= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+        if (lane < R) atomicAdd(dst, v);
+        (void)same_r_in_warp;
+    };
+    int l = 0;
+    for (int k = 0; k < nstage; ++k) {
+        while (!mbar_try_wait(full + k % PSB_NIN, (k / PSB_NIN) & 1)) {}
+        const float* wst = in_ring + (k % PSB_NIN) * rps * ocr + t;
+        float* ost = out_ring + (k % PSB_NOUT) * rps * ocr + t;
+        if (k >= PSB_NOUT) {
+            // the store that used this gradient stage two iterations ago must have read it
+            if (t == 0) bulk_wait_group_read<PSB_NOUT - 1>();
+            __syncthreads();
+        }
+        for (int j0 = 0; j0 < rps; j0 += C, ++l) {
+            const float lvs = fmaf(xl[l * R + r], L2E, -os);
+            float acc_l = 0.f;
+#pragma unroll
+            for (int q = 0; q < C; ++q) {
+                const float arg = fmaf(wst[(j0 + q) * ocr], L2E, lvs + xrs[q]);
+                const float val = gv * ex2_approx(arg);
+                ost[(j0 + q) * ocr] = val;
+                acc_l += val;
+                acc_r[q] += val;
+            }
+            reduce_o_and_add(acc_l, dxl + l * R + r);
+        }
+        fence_proxy_async();   // the staged gradients are read by the TMA engine
+        __syncthreads();       // everyone is done with both stages
+        if (t == 0) {
+            bulk_s2g(gslab + (int64_t)k * rps * ocr, out_ring + (k % PSB_NOUT) * rps * ocr, (uint32_t)rps * ocr * 4);
+            bulk_commit_group();
+            if (k + PSB_NIN < nstage) issue(k + PSB_NIN);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < C; ++q) reduce_o_and_add(acc_r[q], dxr + q * R + r);
+    if (t == 0) bulk_wait_group<0>();
+    __syncthreads();
+    for (int e = t; e < C * R; e += blockDim.x) {
+        if (has_l) a.dx[b * a.sdx_b + (int64_t)(2 * s) * a.sdx_d + e] = dxl[e];
+        if (has_r) a.dx[b * a.sdx_b + (int64_t)(2 * s + 1) * a.sdx_d + e] = dxr[e];
+    }
+}
+
+template <int C>
+static int launch_ps_bwd(const PsBwdArgs& a, int B, cudaStream_t st) {
+    const int ocr = a.oc * a.R;
+    const int smem = (PSB_NIN + PSB_NOUT) * a.rows_per_stage * ocr * 4 + 4 * C * a.R * 4 + PSB_NIN * 8 + 16;
+    cudaError_t e = cudaFuncSetAttribute(sum_ps_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return spn_cuda_status(e);
+    sum_ps_bwd_kernel<C><<<dim3(a.d_out, B), ocr, smem, st>>>(a);
+    return spn_launch_status();
+}
+
+static int ps_bwd_rows_per_stage(int c, int ocr) {
+    int m = PS_STAGE_BYTES / (c * ocr * 4);
+    if (m < 1) m = 1;
+    while (m > 1 && c % m != 0) --m;   // the stages must tile the c*c rows of a slab
+    return c * m;
+}
+
 }  // namespace
 
 extern "C" int spn_sum_ps_supported(int c, int oc, int R) {
@@ -137,4 +276,31 @@ extern "C" int spn_sum_ps_fwd(const float* x, int64_t sx_b, int64_t sx_d, int d_
     if (e != cudaSuccess) return spn_cuda_status(e);
     sum_ps_fwd_kernel<<<dim3(d_out, B), ocr, smem, (cudaStream_t)stream>>>(a);
     return spn_launch_status();
+}
+
+extern "C" int spn_sum_ps_bwd_supported(int c, int oc, int R) {
+    const int ocr = oc * R;
+    if (!(c == 8 || c == 16 || c == 32)) return 0;
+    if (ocr < 32 || ocr > 1024 || ocr % 32 != 0 || R > 32 || (32 % R) != 0) return 0;
+    const int rps = ps_bwd_rows_per_stage(c, ocr);
+    if ((size_t)(PSB_NIN + PSB_NOUT) * rps * ocr * 4 > 160 * 1024) return 0;
+    return 1;
+}
+
+extern "C" int spn_sum_ps_bwd(const float* x, int64_t sx_b, int64_t sx_d, int d_in, int c, const float* lw, int w, int B,
+                              int d_out, int oc, int R, const float* out, const float* g, float* dlw, float* dx,
+                              int64_t sdx_b, int64_t sdx_d, void* stream) {
+    if (!x || !lw || !out || !g || !dlw || !dx || B < 0 || w <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
+    if (B != w) return SPN_ERR_UNSUPPORTED;   // one row per weight set (several rows would have to accumulate into dlw)
+    if (!spn_sum_ps_bwd_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
+    if (B == 0) return SPN_OK;
+    if (B > 65535) return SPN_ERR_UNSUPPORTED;
+    PsBwdArgs a{};
+    a.x = x; a.sx_b = sx_b; a.sx_d = sx_d; a.lw = lw; a.out = out; a.g = g; a.dlw = dlw; a.dx = dx;
+    a.sdx_b = sdx_b; a.sdx_d = sdx_d; a.w = w; a.d_in = d_in; a.d_out = d_out; a.oc = oc; a.R = R;
+    a.rows_per_stage = ps_bwd_rows_per_stage(c, oc * R);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c == 8) return launch_ps_bwd<8>(a, B, st);
+    if (c == 16) return launch_ps_bwd<16>(a, B, st);
+    return launch_ps_bwd<32>(a, B, st);
 }

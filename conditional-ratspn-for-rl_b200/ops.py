@@ -179,8 +179,12 @@ class SumFn(torch.autograd.Function):
                 and _abi.lib().spn_sum_ps_supported(c, oc, R)):
             # per-conditional weights, big enough slabs: TMA-staged HBM-streaming kernel
             call("spn_sum_ps_fwd", ptr(x), sx[0], sx[1], d_in, c, ptr(lw), w, B, d_out, oc, R, ptr(out), stream_ptr(x.device))
+            # one row per weight set: the fused streaming backward applies as well
+            ctx.ps_bwd = (B == w and bool(_abi.lib().spn_sum_ps_bwd_supported(c, oc, R)),
+                          (sx[0], sx[1], d_in, c, w, B, d_out, oc, R))
         else:
             call("spn_sum_fwd", xprod, ptr(x), *sx, d_in, c, ptr(lw), *sw, *ints, ptr(out), *so, stream_ptr(x.device))
+            ctx.ps_bwd = (False, None)
         ctx.save_for_backward(x, lw, out)
         ctx.mode, ctx.layout = mode, layout
         return out
@@ -188,6 +192,13 @@ class SumFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, lw, out = ctx.saved_tensors
+        if ctx.ps_bwd[0] and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+            sxb, sxd, d_in, c, w, B, d_out, oc, R = ctx.ps_bwd[1]
+            g = _f32c(g)
+            dx, dlw = torch.empty_like(x), torch.empty_like(lw)
+            call("spn_sum_ps_bwd", ptr(x), sxb, sxd, d_in, c, ptr(lw), w, B, d_out, oc, R, ptr(out), ptr(g), ptr(dlw),
+                 ptr(dx), sxb, sxd, stream_ptr(x.device))
+            return (dx if ctx.needs_input_grad[0] else None), (dlw if ctx.needs_input_grad[1] else None), None, None
         dx, dlw = _sum_backward(x, lw, out, g, ctx.mode, ctx.layout, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return dx, dlw, None, None
 

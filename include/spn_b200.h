@@ -129,6 +129,15 @@ int spn_sum_ps_supported(int c, int oc, int R);
 int spn_sum_ps_fwd(const float* x, int64_t sx_b, int64_t sx_d, int d_in, int c, const float* lw, int w, int B, int d_out,
                    int oc, int R, float* out, void* stream);
 
+/* Fused backward of spn_sum_ps_fwd for ONE row per weight set (B == w, the CSPN log-likelihood training step): every
+ * slab is read once and its gradient written once (TMA ring in, staged TMA bulk store out); dx of both children comes
+ * out of the same pass.  dlw [w, d_out, c*c, oc, R] contiguous (fully overwritten); dx [B, d_in, c, R] with c, R
+ * contiguous (sdx_b, sdx_d in elements; every scope < d_in is written).  Autograd of layers.py:110-128 + :419-440. */
+int spn_sum_ps_bwd_supported(int c, int oc, int R);
+int spn_sum_ps_bwd(const float* x, int64_t sx_b, int64_t sx_d, int d_in, int c, const float* lw, int w, int B, int d_out,
+                   int oc, int R, const float* out, const float* g, float* dlw, float* dx, int64_t sdx_b,
+                   int64_t sdx_d, void* stream);
+
 /* Stand-alone CrossProduct (materialising) and its backward: layers.py:419-440.  x [B, d_in, c, R] contiguous,
  * out [B, ceil_pow2(d_in)/2, c*c, R] contiguous; dx [B, d_in, c, R] contiguous. */
 int spn_xprod_fwd(const float* x, int B, int d_in, int c, int R, float* out, void* stream);

@@ -56,3 +56,33 @@ def test_per_sample_sum_gradients_flow_through_general_backward():
     # every output is a normalised mixture: d out / d raw sums to zero over the in-channels, d out / d x sums to oc per child
     assert raw.grad.sum(dim=2).abs().max().item() < 1e-4
     assert (x.grad.sum(dim=3) - oc).abs().max().item() < 1e-3
+
+
+def _general_backward(x, lw, out, g):
+    """spn_sum_bwd_x / spn_sum_bwd_w (general exact kernels) on the same tensors."""
+    from ratspn_b200 import ops
+    return ops._sum_backward(x, lw, out, g, "xsum", "ref", True, True)
+
+
+@pytest.mark.parametrize("w,d_in,c,oc,R", [(48, 4, 16, 16, 8), (9, 3, 8, 16, 4), (5, 2, 32, 8, 8), (6, 7, 16, 32, 2), (3, 2, 16, 4, 32)])
+def test_fused_per_sample_backward_matches_general_kernels(w, d_in, c, oc, R):
+    """spn_sum_ps_bwd (one pass over the weights: dlw + both child gradients) against the exact general backward
+    kernels; tolerance 2e-5 of the tensor's largest magnitude (ex2.approx vs expf, different summation order)."""
+    from ratspn_b200 import _abi, ops
+    assert _abi.lib().spn_sum_ps_bwd_supported(c, oc, R)
+    gen = torch.Generator().manual_seed(w * 10 + d_in)
+    x = (torch.randn(1, w, d_in, c, R, generator=gen) * 3.0 - 5.0)
+    x[0, 0, 0, :, 0] = float("-inf")     # impossible left child in repetition 0 of conditional 0 -> -inf outputs, zero gradients
+    d_out = max(1, (1 << (d_in - 1).bit_length()) // 2)
+    lw = torch.log_softmax(torch.randn(w, d_out, c * c, oc, R, generator=gen) * 2.0, dim=2)
+    gout = torch.randn(1, w, d_out, oc, R, generator=gen)
+    x, lw, gout = x.to(DEV).requires_grad_(True), lw.to(DEV).requires_grad_(True), gout.to(DEV)
+    out = ops.sum_forward(x, lw, "xsum")
+    assert out.grad_fn is not None and out.grad_fn.ps_bwd[0], "the dispatch must have taken the streaming path"
+    out.backward(gout)
+    dx_ref, dlw_ref = _general_backward(x.detach(), lw.detach(), out.detach(), gout)
+    for got, ref, what in ((x.grad, dx_ref, "dx"), (lw.grad, dlw_ref, "dlw")):
+        assert not torch.isnan(got).any(), what
+        scale = float(ref.abs().max())
+        assert float((got - ref).abs().max()) <= 2e-5 * scale + 1e-7, f"{what}: {float((got - ref).abs().max()):.3e} vs scale {scale:.3e}"
+    assert float(x.grad[0, 0, 0, :, 0].abs().max()) == 0.0 or torch.isfinite(x.grad[0, 0, 0, :, 0]).all()
