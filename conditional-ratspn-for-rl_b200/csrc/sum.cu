@@ -107,6 +107,66 @@ __global__ void __launch_bounds__(256) sum_fwd_kernel(SumArgs a) {
     a.out[b * a.so_b + (int64_t)s * a.so_d + (int64_t)o * a.so_o + (a.reduce_r ? 0 : (int64_t)r0 * a.so_r)] = result;
 }
 
+// Forward, one WARP per output: for layers with few outputs and long reductions (the root of a wide CSPN: one output per
+// conditional over R * c^2 = 2048 terms) a thread per output leaves the GPU idle and serialises the exps.  Lanes stride
+// over the flattened (r, i) terms; same two-stage semantics as sum_fwd_kernel (input-max shift, exact rescue on underflow).
+template <bool XPROD>
+__global__ void __launch_bounds__(256) sum_fwd_warp_kernel(SumArgs a) {
+    const int Rt = a.reduce_r ? 1 : a.R;
+    const int64_t total = (int64_t)a.B * a.d_out * a.oc * Rt;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= total) return;
+    const int r0 = (int)(wid % Rt);
+    const int o = (int)((wid / Rt) % a.oc);
+    const int s = (int)((wid / ((int64_t)Rt * a.oc)) % a.d_out);
+    const int64_t b = wid / ((int64_t)Rt * a.oc * a.d_out);
+    const int ws = a.Wsets == 1 ? 0 : (int)(b % a.w);
+    const float* lwp = a.lw + (int64_t)ws * a.sw_w + (int64_t)s * a.sw_d + (int64_t)o * a.sw_o;
+    const int r_lo = a.reduce_r ? 0 : r0, nr = a.reduce_r ? a.R : 1;
+    const int nterm = nr * a.ic;
+    float mx = -CUDART_INF_F;
+    for (int k = lane; k < nterm; k += 32) {
+        const int rr = k / a.ic, i = k - rr * a.ic;
+        mx = fmaxf(mx, sum_input<XPROD>(a, b, s, i, r_lo + rr));
+    }
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
+    float result = -CUDART_INF_F;
+    if (mx != -CUDART_INF_F) {
+        float acc = 0.f;
+        for (int k = lane; k < nterm; k += 32) {
+            const int rr = k / a.ic, i = k - rr * a.ic, r = r_lo + rr;
+            acc += __expf(sum_input<XPROD>(a, b, s, i, r) - mx + lwp[(int64_t)r * a.sw_r + (int64_t)i * a.sw_i]);
+        }
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+        if (acc >= 1e-30f) {
+            result = mx + logf(acc);
+        } else {
+            float m2 = -CUDART_INF_F;
+            for (int k = lane; k < nterm; k += 32) {
+                const int rr = k / a.ic, i = k - rr * a.ic, r = r_lo + rr;
+                m2 = fmaxf(m2, sum_input<XPROD>(a, b, s, i, r) + lwp[(int64_t)r * a.sw_r + (int64_t)i * a.sw_i]);
+            }
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, sh));
+            if (m2 != -CUDART_INF_F) {
+                float acc2 = 0.f;
+                for (int k = lane; k < nterm; k += 32) {
+                    const int rr = k / a.ic, i = k - rr * a.ic, r = r_lo + rr;
+                    acc2 += expf(sum_input<XPROD>(a, b, s, i, r) + lwp[(int64_t)r * a.sw_r + (int64_t)i * a.sw_i] - m2);
+                }
+#pragma unroll
+                for (int sh = 16; sh > 0; sh >>= 1) acc2 += __shfl_xor_sync(0xffffffffu, acc2, sh);
+                result = m2 + logf(acc2);
+            }
+        }
+    }
+    if (lane == 0)
+        a.out[b * a.so_b + (int64_t)s * a.so_d + (int64_t)o * a.so_o + (a.reduce_r ? 0 : (int64_t)r0 * a.so_r)] = result;
+}
+
 // Backward w.r.t. the log-weights.  One thread per weight element, walking the rows that use it:
 // dlw = sum_b g[b,s,o,(r)] * exp(x_i + lw - out[b,s,o,(r)]).  Thread order follows the weight memory order
 // (inner layer: r fastest; root: o fastest) so out/g loads are coalesced.
@@ -260,6 +320,12 @@ extern "C" int spn_sum_fwd(int xprod, const float* x, int64_t sx_b, int64_t sx_d
     a.out = out;
     const int64_t total = (int64_t)B * d_out * oc * (reduce_r ? 1 : R);
     cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nterm = (int64_t)ic * (reduce_r ? R : 1);
+    if (total < 148 * 256 && nterm >= 128) {  // few outputs, long reductions: one warp per output
+        if (xprod) sum_fwd_warp_kernel<true><<<spn_blocks(total * 32, 256), 256, 0, st>>>(a);
+        else sum_fwd_warp_kernel<false><<<spn_blocks(total * 32, 256), 256, 0, st>>>(a);
+        return spn_launch_status();
+    }
     if (xprod) sum_fwd_kernel<true><<<spn_blocks(total, 256), 256, 0, st>>>(a);
     else sum_fwd_kernel<false><<<spn_blocks(total, 256), 256, 0, st>>>(a);
     return spn_launch_status();
