@@ -138,6 +138,98 @@ __global__ void __launch_bounds__(256) leaf_bwd_x_kernel(LeafArgs a) {
     atomicAdd(a.dx + xo, gv * v);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Per-conditional parameters (CSPN: Wsets == w), x without leaf-channel / repetition dims, R % 4 == 0, contiguous
+// [.., I, R] outputs: every parameter is read by exactly one row per n-sample, so both directions are HBM streams.  Each
+// thread handles FOUR consecutive repetitions of one (row, scope / feature, channel): 16-byte loads of mu / sigma /
+// permutation / gradient and 16-byte stores, four times the bytes in flight of the scalar kernels above.
+__global__ void __launch_bounds__(256) leaf_ps_fwd_kernel(LeafArgs a) {
+    const int IR4 = a.I * a.R / 4;
+    const int64_t total = (int64_t)a.B * a.d0 * IR4;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= total) return;
+    const int j = (int)(tid % IR4) * 4;
+    const int s = (int)((tid / IR4) % a.d0);
+    const int64_t b = tid / ((int64_t)IR4 * a.d0);
+    const int i = j / a.R, r0 = j % a.R;
+    const int64_t pbase = (((int64_t)(b % a.w)) * a.F * a.I + i) * a.R + r0;
+    const float* xb = a.x + b * a.sx_b;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int f_begin = s * a.card;
+    const int f_end = min(a.F, f_begin + a.card);
+#pragma unroll 4
+    for (int f = f_begin; f < f_end; ++f) {
+        int src[4] = {f, f, f, f};
+        if (a.perm) {
+            const int4 p4 = __ldg(reinterpret_cast<const int4*>(a.perm + (int64_t)f * a.R + r0));
+            src[0] = p4.x; src[1] = p4.y; src[2] = p4.z; src[3] = p4.w;
+        }
+        const int64_t p = pbase + (int64_t)f * a.I * a.R;
+        const float4 m4 = __ldg(reinterpret_cast<const float4*>(a.mu + p));
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.sigma + p));
+        const float mu_v[4] = {m4.x, m4.y, m4.z, m4.w}, sg_v[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float xv = xb[(int64_t)src[q] * a.sx_f];
+            if (!isnan(xv)) {
+                const float d = xv - mu_v[q];
+                float lp = -(d * d) * (1.f / (2.f * sg_v[q] * sg_v[q])) - (logf(sg_v[q]) + SPN_LOG_SQRT_2PI);
+                if (a.tanh_corr) lp -= spn_tanh_correction(xv);
+                acc[q] += lp;
+            }
+        }
+    }
+    *reinterpret_cast<float4*>(a.out + b * a.so_b + (int64_t)s * a.so_d + (int64_t)i * a.so_c + r0) =
+        make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+// thread = (weight set, feature, channel, 4 repetitions); walks the n rows that use this weight set
+__global__ void __launch_bounds__(256) leaf_ps_bwd_param_kernel(LeafArgs a) {
+    const int IR4 = a.I * a.R / 4;
+    const int64_t total = (int64_t)a.Wsets * a.F * IR4;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= total) return;
+    const int j = (int)(tid % IR4) * 4;
+    const int f = (int)((tid / IR4) % a.F);
+    const int ws = (int)(tid / ((int64_t)IR4 * a.F));
+    const int i = j / a.R, r0 = j % a.R;
+    const int s = f / a.card;
+    int src[4] = {f, f, f, f};
+    if (a.perm) {
+        const int4 p4 = __ldg(reinterpret_cast<const int4*>(a.perm + (int64_t)f * a.R + r0));
+        src[0] = p4.x; src[1] = p4.y; src[2] = p4.z; src[3] = p4.w;
+    }
+    const int64_t p = (((int64_t)ws * a.F + f) * a.I + i) * a.R + r0;
+    const float4 m4 = __ldg(reinterpret_cast<const float4*>(a.mu + p));
+    const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.sigma + p));
+    const float mu_v[4] = {m4.x, m4.y, m4.z, m4.w}, sg_v[4] = {s4.x, s4.y, s4.z, s4.w};
+    float inv_sg[4], inv_var[4], dmu[4] = {0.f, 0.f, 0.f, 0.f}, dsg[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { inv_sg[q] = 1.f / sg_v[q]; inv_var[q] = inv_sg[q] * inv_sg[q]; }
+    const int64_t goff = (int64_t)s * a.so_d + (int64_t)i * a.so_c + r0;
+    for (int64_t b = ws; b < a.B; b += a.w) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.g + b * a.so_b + goff));
+        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+        const float* xb = a.x + b * a.sx_b;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float xv = xb[(int64_t)src[q] * a.sx_f];
+            if (!isnan(xv)) {
+                const float d = xv - mu_v[q];
+                dmu[q] += gv[q] * d * inv_var[q];
+                dsg[q] += gv[q] * (d * d * inv_var[q] * inv_sg[q] - inv_sg[q]);
+            }
+        }
+    }
+    *reinterpret_cast<float4*>(a.dmu + p) = make_float4(dmu[0], dmu[1], dmu[2], dmu[3]);
+    *reinterpret_cast<float4*>(a.dsigma + p) = make_float4(dsg[0], dsg[1], dsg[2], dsg[3]);
+}
+
+static bool leaf_ps_vec_ok(const LeafArgs& a) {
+    return a.Wsets != 1 && a.Wsets == a.w && a.R % 4 == 0 && a.sx_i == 0 && a.sx_r == 0 && a.so_r == 1 &&
+           a.so_c % 4 == 0 && a.so_d % 4 == 0 && a.so_b % 4 == 0;
+}
+
 extern "C" int spn_leaf_fwd(const float* x, int64_t sx_b, int64_t sx_f, int64_t sx_i, int64_t sx_r,
                             const int32_t* perm, const float* mu, const float* sigma, int Wsets, int w, int B, int F,
                             int I, int R, int card, int d0, int tanh_corr, float* out, int64_t so_b, int64_t so_d,
@@ -151,7 +243,11 @@ extern "C" int spn_leaf_fwd(const float* x, int64_t sx_b, int64_t sx_f, int64_t 
     a.out = out; a.so_b = so_b; a.so_d = so_d; a.so_c = so_c; a.so_r = so_r;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t IR = (int64_t)I * R;
-    if (Wsets == 1 && B >= 8) {
+    if (leaf_ps_vec_ok(a) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(mu) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(sigma) & 15) == 0) {
+        const int64_t total = (int64_t)B * d0 * (IR / 4);
+        leaf_ps_fwd_kernel<<<spn_blocks(total, 256), 256, 0, st>>>(a);
+    } else if (Wsets == 1 && B >= 8) {
         const int64_t total = ((int64_t)(B + 7) / 8) * d0 * IR;
         leaf_fwd_kernel<8><<<spn_blocks(total, 256), 256, 0, st>>>(a);
     } else {
@@ -174,6 +270,12 @@ extern "C" int spn_leaf_bwd_params(const float* g, int64_t sg_b, int64_t sg_d, i
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total = (int64_t)Wsets * F * I * R;
     const int64_t rows = Wsets == 1 ? B : B / w;
+    if (leaf_ps_vec_ok(a) && total / 4 >= 296 * 256 && rows <= 64 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(mu) & 15) == 0 && (reinterpret_cast<uintptr_t>(sigma) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(dmu) & 15) == 0 && (reinterpret_cast<uintptr_t>(dsigma) & 15) == 0) {
+        leaf_ps_bwd_param_kernel<<<spn_blocks(total / 4, 256), 256, 0, st>>>(a);
+        return spn_launch_status();
+    }
     // split the row loop when there are few parameters but many rows, so the grid still fills 148 SMs
     int nsplit = 1;
     const int64_t blocks = (total + 255) / 256;

@@ -63,3 +63,38 @@ def test_tiled_leaf_all_nan_rows_are_fully_marginalised():
     sigma = torch.rand(1, F, I, R, device=DEV) + 0.1
     out = ops.leaf_forward(x, mu, sigma, None, card, False, "ref")
     assert torch.equal(out, torch.zeros_like(out))
+
+
+@pytest.mark.parametrize("n,w,F,D,I,R,tanh,nan", [
+    (1, 600, 64, 3, 16, 8, False, False),   # vectorised forward and backward (enough parameters to fill the GPU)
+    (3, 300, 40, 2, 8, 4, True, True),      # several rows per weight set, tanh correction, NaN marginalisation
+    (2, 5, 17, 4, 3, 4, True, True),        # small: vectorised forward, scalar backward; leaf padding
+])
+def test_per_conditional_leaf_vectorised_kernels_vs_oracle(n, w, F, D, I, R, tanh, nan):
+    """CSPN leaf (one parameter set per conditional, R % 4 == 0): the 16-byte-vectorised streaming kernels against
+    the fp64 oracle; x [n, w, F, 1, 1]."""
+    from oracle import spn_oracle as O
+    from ratspn_b200 import ops
+    g = torch.Generator().manual_seed(F * 3 + w)
+    arch = O.Arch(F=F, D=D, R=R, S=2, I=I, C=1, tanh_squash=tanh)
+    card, d0 = arch.card, arch.d0
+    x = torch.randn(n, w, F, 1, 1, generator=g)
+    if nan:
+        x[0, 1, ::3] = float("nan")
+        x[n - 1, w - 1, :] = float("nan")
+    perm = torch.stack([torch.randperm(F, generator=g) for _ in range(R)], dim=-1)
+    mu = torch.randn(w, F, I, R, generator=g)
+    sigma = torch.rand(w, F, I, R, generator=g) * 0.9 + 0.05
+    go = torch.randn(n, w, d0, I, R, generator=g)
+    mu_o, sg_o = mu.double().requires_grad_(True), sigma.double().requires_grad_(True)
+    ref = _oracle_leaf(x, perm, mu_o, sg_o, arch)
+    (ref * go.double()).sum().backward()
+    mu_t, sg_t = mu.to(DEV).requires_grad_(True), sigma.to(DEV).requires_grad_(True)
+    out = ops.leaf_forward(x.to(DEV), mu_t, sg_t, perm.to(torch.int32).to(DEV), card, tanh, "ref")
+    assert out.shape == ref.shape
+    (out * go.to(DEV)).sum().backward()
+    scale = ref.abs().max().item()
+    assert (out.cpu().double() - ref).abs().max().item() <= 2e-6 * scale + 1e-5
+    for name, a, b in (("dmu", mu_t.grad, mu_o.grad), ("dsigma", sg_t.grad, sg_o.grad)):
+        err = (a.cpu().double() - b).abs().max().item()
+        assert err <= 2e-5 * b.abs().max().item() + 1e-6, f"{name}: {err} vs scale {b.abs().max().item()}"

@@ -172,10 +172,55 @@ def cfg5_narrow(w=2048):
             "abi_calls": launches}
 
 
+def cfg5_narrow_train(w=512):
+    """Same per-sample-weight regime, LL forward + backward w.r.t. every per-conditional parameter (the CSPN training step
+    minus the gating MLP): weights read in the forward, read again and their gradient written in the backward."""
+    torch.manual_seed(0); np.random.seed(0)
+    cfg = rb.CspnConfig()
+    cfg.F_cond = (4,)
+    cfg.F, cfg.R, cfg.D, cfg.I, cfg.S, cfg.C = 1024, 8, 6, 16, 16, 1
+    cfg.dropout = 0.0
+    cfg.leaf_base_class = rb.RatNormal
+    cfg.leaf_base_kwargs = {"min_sigma": 0.001, "max_sigma": 1.0}
+    cfg.tanh_squash = False
+    cfg.feat_layers, cfg.sum_param_layers, cfg.dist_param_layers = [4], [4], [4]
+    m = rb.RatSpn.__new__(rb.CSPN)
+    rb.RatSpn.__init__(m, cfg)
+    m.replace_layer_params()
+    m = m.to(DEV)
+    params, nbytes = [], 0
+    for layer in list(m._inner_layers) + [m.root]:
+        if isinstance(layer, rb.Sum):
+            shape = (w, layer.in_features, layer.in_channels, layer.out_channels, layer.num_repetitions)
+            layer.weight_param = torch.log_softmax(torch.randn(shape, device=DEV), dim=2).requires_grad_(True)
+            params.append(layer.weight_param)
+            nbytes += layer.weight_param.numel() * 4
+        else:
+            layer.num_conditionals = w
+    base = m._leaf.base_leaf
+    base.mean_param = torch.randn(w, 1024, 16, 8, device=DEV).requires_grad_(True)
+    base.std_param = (torch.rand(w, 1024, 16, 8, device=DEV) * 0.9 + 0.05).requires_grad_(True)
+    params += [base.mean_param, base.std_param]
+    nbytes += 2 * base.mean_param.numel() * 4
+    x = torch.randn(1, w, 1024, 1, 1, device=DEV)
+
+    def step():
+        for p in params:
+            p.grad = None
+        (-rb.RatSpn.forward(m, x).mean()).backward()
+    ms, launches = timed(step, reps=5)
+    return {"config": f"cfg5-narrow per-sample weights R=8 S=I=16 D=6 F=1024, w={w} conditionals, n=1: LL forward + backward",
+            "ms": ms, "conditionals_per_s": w / ms * 1e3, "parameter_bytes": nbytes,
+            "algorithmic_bytes (3 x parameters: read, read, write gradient)": 3 * nbytes,
+            "achieved_GB_per_s": 3 * nbytes / ms / 1e6, "hbm_peak_GB_per_s": 6548.2, "frac": 3 * nbytes / ms / 1e6 / 6548.2,
+            "abi_calls": launches}
+
+
 def main():
     out_path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "configs.json")
     res = {"device": torch.cuda.get_device_name(0), "lib": _abi.version()}
-    for name, fn in (("cfg1", cfg1), ("cfg3", cfg3), ("cfg4", cfg4), ("cfg5_narrow", cfg5_narrow)):
+    for name, fn in (("cfg1", cfg1), ("cfg3", cfg3), ("cfg4", cfg4), ("cfg5_narrow", cfg5_narrow),
+                     ("cfg5_narrow_train", cfg5_narrow_train)):
         t0 = time.time()
         try:
             res[name] = fn()
