@@ -174,7 +174,7 @@ def main():
     import torch.distributed as dist
     import ratspn_b200 as rb
     from ratspn_b200 import _abi
-    from ratspn_b200.parallel import FlatGradAllReducer, broadcast_parameters
+    from ratspn_b200.parallel import FlatAdam, FlatGradAllReducer, broadcast_parameters
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -197,7 +197,11 @@ def main():
 
     sum_layers = [m for m in model.modules() if hasattr(m, "invalidate_weight_cache")]
 
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
+    # Adam as in mnist_gen_train.py:599, as one launch over flat buffers (spn_adam_step); SPN_TORCH_ADAM=1 -> torch's fused Adam
+    if os.environ.get("SPN_TORCH_ADAM"):
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
+    else:
+        opt = FlatAdam(reducer, lr=1e-3, module=model)
 
     def step(x):
         """One training step: LL forward, backward, gradient all-reduce, Adam update (mnist_gen_train.py:173-205)."""
@@ -360,7 +364,7 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_name(), "global_batch": world * B, "parallelism": f"dp{world}",
-                           "step": "LL forward + backward + gradient all-reduce + Adam (fused) update",
+                           "step": "LL forward + backward + gradient all-reduce + Adam update (one flat kernel)",
                            "cuda_graph": bool(use_graph and graph_err is None),
                            "l2": "per-step working set (leaf activations 839 MB + 317 MB weights) exceeds the 126 MB "
                                  "L2; 4 rotating input batches"},

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libspn_b200.so")
 _c_int, _c_i64, _c_u64, _c_ptr = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_void_p
 
 # name -> argtypes, in the order of include/spn_b200.h
-_P, _I, _L, _U = _c_ptr, _c_int, _c_i64, _c_u64
+_P, _I, _L, _U, _F = _c_ptr, _c_int, _c_i64, _c_u64, ctypes.c_float
 SIGNATURES = {
     "spn_version": [ctypes.c_char_p, _I],
     "spn_leaf_fwd": [_P, _L, _L, _L, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _L, _P],
@@ -40,6 +40,7 @@ SIGNATURES = {
                       _L, _L, _L, _L, _P, _L, _L, _L, _L, _P],
     "spn_sum_ps_supported": [_I, _I, _I],
     "spn_sum_ps_fwd": [_P, _L, _L, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P],
+    "spn_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _P],
     "spn_sum_ps_bwd_supported": [_I, _I, _I],
     "spn_sum_ps_bwd": [_P, _L, _L, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _L, _L, _P],
     "spn_xprod_fwd": [_P, _I, _I, _I, _I, _P, _P],

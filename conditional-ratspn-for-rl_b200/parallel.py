@@ -38,15 +38,18 @@ class FlatGradAllReducer:
         assert self.params, "no trainable parameters"
         dev, dt = self.params[0].device, self.params[0].dtype
         assert all(p.device == dev and p.dtype == dt for p in self.params)
-        self.numel = sum(p.numel() for p in self.params)
+        # every slice starts on a 256-byte boundary (the kernels use 16-byte vector / TMA accesses on whole tensors)
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 63) // 64 * 64
+        self.numel = off
         self.flat = torch.zeros(self.numel, device=dev, dtype=dt)
         self.average = average
         self.overlap = overlap
         self._handles = []
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
         if overlap and self._distributed():
             for p in self.params:
                 p.register_post_accumulate_grad_hook(self._hook)
@@ -67,15 +70,13 @@ class FlatGradAllReducer:
 
     def rebind(self):
         """Re-attach the views if something replaced ``.grad`` (e.g. ``zero_grad(set_to_none=True)``)."""
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             view = self.flat[off:off + p.numel()].view_as(p)
             if p.grad is None:
                 p.grad = view
             elif p.grad.data_ptr() != view.data_ptr():
                 view.copy_(p.grad)
                 p.grad = view
-            off += p.numel()
 
     def all_reduce(self, async_op: bool = False):
         if not self._distributed():
@@ -88,6 +89,40 @@ class FlatGradAllReducer:
         if self.average:
             self.flat.mul_(1.0 / dist.get_world_size())
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
+
+
+class FlatAdam:
+    """Adam (``torch.optim.Adam`` semantics: no amsgrad, no weight decay) as ONE kernel over flat buffers
+    (``spn_adam_step``): the parameters are re-homed as views into one flat fp32 buffer next to the reducer's flat
+    gradient buffer, so the update of the whole model is a single 28-byte-per-parameter HBM stream.
+
+    ``module``: the model whose tensor-core operand-image caches must be invalidated after every step (the kernel
+    writes the parameters behind autograd's version counters)."""
+
+    def __init__(self, reducer: FlatGradAllReducer, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 module: torch.nn.Module = None):
+        self.reducer = reducer
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.flat_p = torch.zeros_like(reducer.flat)
+        for p, off in zip(reducer.params, reducer.offsets):
+            n = p.numel()
+            self.flat_p[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[off:off + n].view_as(p)
+        self.exp_avg = torch.zeros_like(reducer.flat)
+        self.exp_avg_sq = torch.zeros_like(reducer.flat)
+        self.t = 0
+        self._cached = [m for m in module.modules() if hasattr(m, "invalidate_weight_cache")] if module is not None else []
+
+    def step(self):
+        from . import _abi
+        self.t += 1
+        b1, b2 = self.betas
+        bc1, bc2 = 1.0 - b1 ** self.t, 1.0 - b2 ** self.t
+        _abi.call("spn_adam_step", _abi.ptr(self.flat_p), _abi.ptr(self.reducer.flat), _abi.ptr(self.exp_avg),
+                  _abi.ptr(self.exp_avg_sq), self.flat_p.numel(), self.lr / bc1, b1, b2, self.eps, 1.0 / bc2 ** 0.5,
+                  _abi.stream_ptr(self.flat_p.device))
+        for m in self._cached:
+            m.invalidate_weight_cache()
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0):

@@ -271,6 +271,14 @@ int spn_debug_tc_aborts(int* out_host);
  * deltas per pipeline phase of the spn_sum_tc_fwd / _bwd_x kernels; copies the 24 counters to out_host (host pointer) and optionally resets. */
 int spn_debug_tc_prof(unsigned long long* out_host, int reset);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Adam update over flat fp32 buffers (one launch for the whole model): torch.optim.Adam semantics without amsgrad /
+ * weight decay, as used by mnist_experiments/mnist_gen_train.py:599, :669, :720.  step_size = lr / (1 - beta1^t), inv_sqrt_bc2 = 1 / sqrt(1 -
+ * beta2^t); all pointers 16-byte aligned.
+ * ------------------------------------------------------------------------------------------------------------- */
+int spn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float step_size, float beta1, float beta2,
+                  float eps, float inv_sqrt_bc2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
