@@ -115,6 +115,26 @@ class ClockSampler:
         self.index, self.rows, self.stop, self.thread = index, [], threading.Event(), None
 
     def _loop(self):
+        # NVML directly (a sample every few ms, so that even a 45 ms timed region gets several); nvidia-smi as fall-back
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            bits = [("hw_slowdown", getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                    ("hw_thermal_slowdown", getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                    ("sw_thermal_slowdown", getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                    ("sw_power_cap", getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4))]
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                mask = int(get_reasons(h))
+                self.rows.append([str(sm), str(mx)] + ["Active" if mask & b else "Not Active" for _, b in bits])
+                self.stop.wait(0.004)
+            return
+        except Exception:
+            pass
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
