@@ -63,6 +63,7 @@ __device__ unsigned long long g_tc2_prof[24];
 enum { OPG_FWD = 0, OPG_DXR = 1, OPG_DXL = 2 };
 
 struct OpgArgs {
+    unsigned int* counter;   // work counter of this launch (dynamic item scheduling), zeroed by the host
     const float* x;        // [d_in][R][B][C]
     const uint8_t* wimg;   // [2][d_out][R][K*C] bf16: image, then pair-transposed image
     const float* lw;       // fp32 weights [1][d_out][K][OC][R] (exact rescue path, FWD)
@@ -271,14 +272,21 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
     uint32_t m_stage = 0, m_tile = 0;                               // the MMA warp's own counters (kept warp-uniform)
     TC2_DECL;
 
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++items_done) {
+    // Items are handed out dynamically (one atomic per item): when another kernel holds some SMs -- NCCL's all-reduce
+    // of the upper layers' gradients overlaps this backward -- the CTAs that start late simply find less work left,
+    // instead of a static 1/gridDim share that would become a second wave.
+    __shared__ int s_next[2];
+    for (;; ++items_done) {
+        if (threadIdx.x == 0) s_next[items_done & 1] = (int)atomicAdd(a.counter, 1u);
+        __syncthreads();  // the previous item is finished by every role (its last epilogue waited for its last MMA)
+        const int item = __shfl_sync(0xffffffffu, s_next[items_done & 1], 0);
+        if (item >= nitems) break;
         const int split = item % a.nsplit;
         const int sr = item / a.nsplit;
         const int r = sr % a.R, s = sr / a.R;
         const int tile_begin = split * tiles_per_split;
         const int tile_end = min(a.ntiles, tile_begin + tiles_per_split);
         const bool has_l = 2 * s < a.d_in, has_r = 2 * s + 1 < a.d_in;
-        __syncthreads();  // the previous item is finished by every role (its last epilogue waited for its last MMA)
         if (__shfl_sync(0xffffffffu, *abort_flag, 0)) break;
         if (warp == 16) {
             // =============================================== MMA issuer ===============================================
@@ -771,6 +779,17 @@ __global__ void __launch_bounds__(256) tc_wimage_t_kernel(const uint4* __restric
     img2[i] = img[sr * per_sr + srce];
 }
 
+// one zeroed work counter per launch, taken round-robin from a small ring (launches in flight never come near 256)
+__device__ unsigned int g_opg_counters[256];
+static unsigned int* opg_next_counter(cudaStream_t st) {
+    static unsigned int* base = nullptr;
+    static unsigned int next = 0;
+    if (!base && cudaGetSymbolAddress((void**)&base, g_opg_counters) != cudaSuccess) return nullptr;
+    unsigned int* c = base + (next++ & 255u);
+    if (cudaMemsetAsync(c, 0, sizeof(unsigned int), st) != cudaSuccess) return nullptr;
+    return c;
+}
+
 template <int C, int MODE>
 static int launch_opg(const OpgArgs& a, cudaStream_t st) {
     constexpr int W_BYTES = C * C * C * 2;
@@ -786,7 +805,10 @@ static int launch_opg(const OpgArgs& a, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int nitems = a.d_out * a.R * a.nsplit;
-    opg_kernel<C, MODE><<<nitems < sms ? nitems : sms, 544, SMEM, st>>>(a);
+    OpgArgs b = a;
+    b.counter = opg_next_counter(st);
+    if (!b.counter) return SPN_ERR_ARG;
+    opg_kernel<C, MODE><<<nitems < sms ? nitems : sms, 544, SMEM, st>>>(b);
     return spn_launch_status();
 }
 

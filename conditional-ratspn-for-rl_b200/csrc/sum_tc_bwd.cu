@@ -20,6 +20,7 @@ __device__ int g_tc_bwd_aborts = 0;
 #endif
 
 struct TcBwdArgs {
+    unsigned int* counter;   // work counter of this launch (dynamic item scheduling), zeroed by the host
     const uint8_t* fhand; // per (s, r, row tile): packed eL, eR ([pair][128 rows] words) + shifts, written by the forward kernel
     const uint8_t* hand;  // per (s, r, row tile): G tile (B-operand layout), written by the dX kernel
     float* dwt;           // [d_out][R][K][OC] linear-domain weight gradient
@@ -120,14 +121,19 @@ __global__ void __launch_bounds__(320, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
     uint32_t n_stage = 0, n_tile = 0, items_done = 0;   // per-role ring positions (persist across items)
     uint32_t m_stage = 0, m_tile = 0;                   // the MMA warp's own counters (kept warp-uniform)
 
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++items_done) {
+    // dynamic item scheduling (see opg_kernel): late CTAs -- SMs held by a concurrent NCCL kernel -- find less work left
+    __shared__ int s_next[2];
+    for (;; ++items_done) {
+        if (threadIdx.x == 0) s_next[items_done & 1] = (int)atomicAdd(a.counter, 1u);
+        __syncthreads();  // the previous item (incl. its epilogue reads of TMEM) is finished by every role
+        const int item = __shfl_sync(0xffffffffu, s_next[items_done & 1], 0);
+        if (item >= nitems) break;
         const int grp = item % ngroups;
         const int sr = item / ngroups;
         const int r = sr % a.R, s = sr / a.R;
         const int chunk_begin = grp * GC;
         const int chunk_end = min(NCHUNK, chunk_begin + GC);
         const int nch = chunk_end - chunk_begin;
-        __syncthreads();  // the previous item (incl. its epilogue reads of TMEM) is finished by every role
         if (__shfl_sync(0xffffffffu, *abort_flag, 0)) break;
         if (warp == 9) {
             // =============================================== MMA issuer ===============================================
@@ -363,6 +369,16 @@ __global__ void __launch_bounds__(256) tc_dw_finish_vec_kernel(const float* __re
 
 extern "C" int spn_sum_tc_supported(int c, int oc, int R);
 
+__device__ unsigned int g_bwd_counters[256];
+static unsigned int* bwd_next_counter(cudaStream_t st) {
+    static unsigned int* base = nullptr;
+    static unsigned int next = 0;
+    if (!base && cudaGetSymbolAddress((void**)&base, g_bwd_counters) != cudaSuccess) return nullptr;
+    unsigned int* c = base + (next++ & 255u);
+    if (cudaMemsetAsync(c, 0, sizeof(unsigned int), st) != cudaSuccess) return nullptr;
+    return c;
+}
+
 template <int C, int OC, int NPAD, int GC>
 static int launch_bwd_w(const TcBwdArgs& a, cudaStream_t st) {
     constexpr int NCHUNK = ((C / 8) * (C / 8) + 1) / 2;
@@ -378,7 +394,10 @@ static int launch_bwd_w(const TcBwdArgs& a, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int nitems = a.d_out * a.R * NGROUPS;
-    sum_tc_bwd_w_kernel<C, OC, NPAD, GC><<<nitems < sms ? nitems : sms, 320, SMEM, st>>>(a, NGROUPS);
+    TcBwdArgs b = a;
+    b.counter = bwd_next_counter(st);
+    if (!b.counter) return SPN_ERR_ARG;
+    sum_tc_bwd_w_kernel<C, OC, NPAD, GC><<<nitems < sms ? nitems : sms, 320, SMEM, st>>>(b, NGROUPS);
     return spn_launch_status();
 }
 
