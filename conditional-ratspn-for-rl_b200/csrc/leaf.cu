@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) leaf_bwd_x_kernel(LeafArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Per-conditional parameters (CSPN: Wsets == w), x without leaf-channel / repetition dims, R % 4 == 0, contiguous
+// Per-conditional parameters (CSPN: Wsets == w), R % 4 == 0, contiguous
 // [.., I, R] outputs: every parameter is read by exactly one row per n-sample, so both directions are HBM streams.  Each
 // thread handles FOUR consecutive repetitions of one (row, scope / feature, channel): 16-byte loads of mu / sigma /
 // permutation / gradient and 16-byte stores, four times the bytes in flight of the scalar kernels above.
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) leaf_ps_fwd_kernel(LeafArgs a) {
         const float mu_v[4] = {m4.x, m4.y, m4.z, m4.w}, sg_v[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float xv = xb[(int64_t)src[q] * a.sx_f];
+            const float xv = xb[(int64_t)src[q] * a.sx_f + (int64_t)i * a.sx_i + (int64_t)(r0 + q) * a.sx_r];
             if (!isnan(xv)) {
                 const float d = xv - mu_v[q];
                 float lp = -(d * d) * (1.f / (2.f * sg_v[q] * sg_v[q])) - (logf(sg_v[q]) + SPN_LOG_SQRT_2PI);
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) leaf_ps_bwd_param_kernel(LeafArgs a) {
         const float* xb = a.x + b * a.sx_b;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float xv = xb[(int64_t)src[q] * a.sx_f];
+            const float xv = xb[(int64_t)src[q] * a.sx_f + (int64_t)i * a.sx_i + (int64_t)(r0 + q) * a.sx_r];
             if (!isnan(xv)) {
                 const float d = xv - mu_v[q];
                 dmu[q] += gv[q] * d * inv_var[q];
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(256) leaf_ps_bwd_param_kernel(LeafArgs a) {
 }
 
 static bool leaf_ps_vec_ok(const LeafArgs& a) {
-    return a.Wsets != 1 && a.Wsets == a.w && a.R % 4 == 0 && a.sx_i == 0 && a.sx_r == 0 && a.so_r == 1 &&
+    return a.Wsets != 1 && a.Wsets == a.w && a.R % 4 == 0 && a.so_r == 1 &&
            a.so_c % 4 == 0 && a.so_d % 4 == 0 && a.so_b % 4 == 0;
 }
 

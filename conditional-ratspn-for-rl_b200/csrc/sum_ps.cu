@@ -24,7 +24,7 @@ struct PsArgs {
     int B, w, d_in, d_out, c, oc, R;
 };
 
-// grid (d_out, B); block = oc * R threads (one per output of the (row, scope) pair)
+// grid (B, d_out); block = oc * R threads (one per output of the (row, scope) pair)
 __global__ void __launch_bounds__(1024) sum_ps_fwd_kernel(PsArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int ocr = a.oc * a.R, c = a.c, ic = c * c;
@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(1024) sum_ps_fwd_kernel(PsArgs a) {
     float* xl = ring + PS_NSTG * rows_per_stage * ocr;                            // [c][R]
     float* xr = xl + c * a.R;                                                     // [c][R]
     uint64_t* full = reinterpret_cast<uint64_t*>(xr + c * a.R);                   // [PS_NSTG]
-    const int s = blockIdx.x;
-    const int64_t b = blockIdx.y;
+    const int s = blockIdx.y;
+    const int64_t b = blockIdx.x;
     const int t = threadIdx.x;
     const int r = t % a.R;
     const float* slab = a.lw + (((int64_t)(b % a.w) * a.d_out + s) * ic) * ocr;
@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(1024) sum_ps_bwd_kernel(PsBwdArgs a) {
     float* dxl = xr + C * R;                                                      // [C][R]
     float* dxr = dxl + C * R;                                                     // [C][R]
     uint64_t* full = reinterpret_cast<uint64_t*>(dxr + C * R);                    // [PSB_NIN]
-    const int s = blockIdx.x;
-    const int64_t b = blockIdx.y;
+    const int s = blockIdx.y;
+    const int64_t b = blockIdx.x;
     const int t = threadIdx.x, lane = t & 31;
     const int r = t % R;
     const int64_t slab_off = ((b * a.d_out + s) * (int64_t)ic) * ocr;
@@ -242,7 +242,7 @@ static int launch_ps_bwd(const PsBwdArgs& a, int B, cudaStream_t st) {
     const int smem = (PSB_NIN + PSB_NOUT) * a.rows_per_stage * ocr * 4 + 4 * C * a.R * 4 + PSB_NIN * 8 + 16;
     cudaError_t e = cudaFuncSetAttribute(sum_ps_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return spn_cuda_status(e);
-    sum_ps_bwd_kernel<C><<<dim3(a.d_out, B), ocr, smem, st>>>(a);
+    sum_ps_bwd_kernel<C><<<dim3(B, a.d_out), ocr, smem, st>>>(a);
     return spn_launch_status();
 }
 
@@ -265,7 +265,7 @@ extern "C" int spn_sum_ps_fwd(const float* x, int64_t sx_b, int64_t sx_d, int d_
     if (!x || !lw || !out || B < 0 || w <= 0 || B % w != 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
     if (!spn_sum_ps_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
     if (B == 0) return SPN_OK;
-    if (B > 65535) return SPN_ERR_UNSUPPORTED;
+    if (d_out > 65535) return SPN_ERR_UNSUPPORTED;
     PsArgs a{};
     a.x = x; a.sx_b = sx_b; a.sx_d = sx_d; a.lw = lw; a.out = out;
     a.B = B; a.w = w; a.d_in = d_in; a.d_out = d_out; a.c = c; a.oc = oc; a.R = R;
@@ -274,7 +274,7 @@ extern "C" int spn_sum_ps_fwd(const float* x, int64_t sx_b, int64_t sx_d, int d_
     const int smem = PS_NSTG * rows * ocr * 4 + 2 * c * R * 4 + PS_NSTG * 8 + 16;
     cudaError_t e = cudaFuncSetAttribute(sum_ps_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return spn_cuda_status(e);
-    sum_ps_fwd_kernel<<<dim3(d_out, B), ocr, smem, (cudaStream_t)stream>>>(a);
+    sum_ps_fwd_kernel<<<dim3(B, d_out), ocr, smem, (cudaStream_t)stream>>>(a);
     return spn_launch_status();
 }
 
@@ -294,7 +294,7 @@ extern "C" int spn_sum_ps_bwd(const float* x, int64_t sx_b, int64_t sx_d, int d_
     if (B != w) return SPN_ERR_UNSUPPORTED;   // one row per weight set (several rows would have to accumulate into dlw)
     if (!spn_sum_ps_bwd_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
     if (B == 0) return SPN_OK;
-    if (B > 65535) return SPN_ERR_UNSUPPORTED;
+    if (d_out > 65535) return SPN_ERR_UNSUPPORTED;
     PsBwdArgs a{};
     a.x = x; a.sx_b = sx_b; a.sx_d = sx_d; a.lw = lw; a.out = out; a.g = g; a.dlw = dlw; a.dx = dx;
     a.sdx_b = sdx_b; a.sdx_d = sdx_d; a.w = w; a.d_in = d_in; a.d_out = d_out; a.oc = oc; a.R = R;

@@ -175,7 +175,7 @@ class SumFn(torch.autograd.Function):
         xprod, sx, d_in, c, sw, ints, so, out_shape = _sum_geometry(x, lw, mode, layout)
         out = torch.empty(out_shape, device=x.device, dtype=torch.float32)
         Wsets, w, B, d_out, ic, oc, R, _ = ints
-        if (mode == "xsum" and layout == "ref" and Wsets == w and w > 1 and B <= 65535 and ic * oc * R * 4 >= 16384
+        if (mode == "xsum" and layout == "ref" and Wsets == w and w > 1 and d_out <= 65535 and ic * oc * R * 4 >= 16384
                 and _abi.lib().spn_sum_ps_supported(c, oc, R)):
             # per-conditional weights, big enough slabs: TMA-staged HBM-streaming kernel
             call("spn_sum_ps_fwd", ptr(x), sx[0], sx[1], d_in, c, ptr(lw), w, B, d_out, oc, R, ptr(out), stream_ptr(x.device))

@@ -98,3 +98,28 @@ def test_per_conditional_leaf_vectorised_kernels_vs_oracle(n, w, F, D, I, R, tan
     for name, a, b in (("dmu", mu_t.grad, mu_o.grad), ("dsigma", sg_t.grad, sg_o.grad)):
         err = (a.cpu().double() - b).abs().max().item()
         assert err <= 2e-5 * b.abs().max().item() + 1e-6, f"{name}: {err} vs scale {b.abs().max().item()}"
+
+
+def test_per_conditional_leaf_with_channel_and_repetition_dims_in_x():
+    """Entropy path (rat_spn.py:654-659): leaf samples x [n, w, F, I, R] scored without permutation, per-conditional
+    parameters, R % 4 == 0 -> vectorised kernels with strided x."""
+    from oracle import spn_oracle as O
+    from ratspn_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    n, w, F, D, I, R = 3, 40, 24, 2, 6, 4
+    arch = O.Arch(F=F, D=D, R=R, S=2, I=I, C=1, tanh_squash=False)
+    x = torch.randn(n, w, F, I, R, generator=g)
+    x[1, 2, 5] = float("nan")
+    mu = torch.randn(w, F, I, R, generator=g)
+    sigma = torch.rand(w, F, I, R, generator=g) * 0.9 + 0.05
+    go = torch.randn(n, w, arch.d0, I, R, generator=g)
+    mu_o, sg_o = mu.double().requires_grad_(True), sigma.double().requires_grad_(True)
+    ref = O.leaf_product(O.leaf_log_prob(x.double(), mu_o, sg_o, arch), arch)
+    (ref * go.double()).sum().backward()
+    mu_t, sg_t = mu.to(DEV).requires_grad_(True), sigma.to(DEV).requires_grad_(True)
+    out = ops.leaf_forward(x.to(DEV), mu_t, sg_t, None, arch.card, False, "ref")
+    (out * go.to(DEV)).sum().backward()
+    assert (out.cpu().double() - ref).abs().max().item() <= 2e-6 * ref.abs().max().item() + 1e-5
+    for name, a, b in (("dmu", mu_t.grad, mu_o.grad), ("dsigma", sg_t.grad, sg_o.grad)):
+        err = (a.cpu().double() - b).abs().max().item()
+        assert err <= 2e-5 * b.abs().max().item() + 1e-6, f"{name}: {err}"
