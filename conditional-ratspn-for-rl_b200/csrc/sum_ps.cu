@@ -115,6 +115,146 @@ __global__ void __launch_bounds__(1024) sum_ps_fwd_kernel(PsArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Forward for MANY rows per weight set (B = n * w with n >> 1: the recursive entropy scores K * n samples per
+// conditional, rat_spn.py:661-676).  One block per (weight set, scope) walks its rows in tiles of PSR_RT: the slab
+// streams through the TMA ring once per row tile (from L2 after the first), is turned into linear weights W = exp(lw)
+// in place, and every thread (one per output (o, r)) keeps PSR_RT accumulators:
+//     out[b,o,r] = mL + mR + log sum_l eL[b,l,r] * ( sum_r' eR[b,r',r] * W[(l,r'),o,r] )
+// i.e. 2 exps per input instead of one exp per (input pair, output); the inner loop is one broadcast LDS + one FFMA.
+constexpr int PSR_RT = 32;
+
+struct PsRowsArgs {
+    const float* x; int64_t sx_b, sx_d;
+    const float* lw; float* out;
+    int B, w, d_in, d_out, oc, R, rows_per_stage;
+};
+
+template <int C>
+__global__ void __launch_bounds__(256) sum_ps_rows_fwd_kernel(PsRowsArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int ocr = a.oc * a.R, R = a.R;
+    constexpr int ic = C * C;
+    const int rps = a.rows_per_stage;  // multiple of C
+    float* ring = reinterpret_cast<float*>(smem);                                  // [PS_NSTG][rps][ocr]
+    float* eL = ring + PS_NSTG * rps * ocr;                                        // [PSR_RT][C][R]
+    float* eR = eL + PSR_RT * C * R;                                               // [PSR_RT][C][R]
+    float* sh = eR + PSR_RT * C * R;                                               // [PSR_RT][R]  mL + mR (or -inf: dead)
+    uint64_t* full = reinterpret_cast<uint64_t*>(sh + PSR_RT * R);                 // [PS_NSTG]
+    const int j = blockIdx.x, s = blockIdx.y;
+    const int t = threadIdx.x, r = t % R;
+    const float* slab = a.lw + (((int64_t)j * a.d_out + s) * ic) * ocr;
+    const int nstage = ic / rps;
+    const int nrows = a.B / a.w;       // rows of this weight set: b = j + k * w
+    const bool has_l = 2 * s < a.d_in, has_r = 2 * s + 1 < a.d_in;
+    if (t == 0) {
+        for (int i = 0; i < PS_NSTG; ++i) mbar_init(full + i, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int k) {  // thread 0 only; k = global stage counter over all row tiles
+        const int ks = k % nstage;
+        const uint32_t bytes = (uint32_t)rps * ocr * 4;
+        uint64_t* bar = full + k % PS_NSTG;
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_g2s(ring + (k % PS_NSTG) * rps * ocr, slab + (int64_t)ks * rps * ocr, bytes, bar);
+    };
+    const int ntile = (nrows + PSR_RT - 1) / PSR_RT;
+    const int total_stages = ntile * nstage;
+    if (t == 0)
+        for (int k = 0; k < min(PS_NSTG, total_stages); ++k) issue(k);
+    int kg = 0;  // global stage counter
+    for (int tile = 0; tile < ntile; ++tile) {
+        const int row0 = tile * PSR_RT;
+        const int nr = min(PSR_RT, nrows - row0);
+        __syncthreads();  // previous tile's eL / eR / sh are no longer read
+        // exp(x - max) of both children for the rows of this tile: thread e handles (row, r) pairs
+        for (int e = t; e < PSR_RT * R; e += blockDim.x) {
+            const int row = e / R, rr = e % R;
+            float ml = -CUDART_INF_F, mr = -CUDART_INF_F;
+            const int64_t b = (int64_t)j + (int64_t)(row0 + min(row, nr - 1)) * a.w;
+            const float* xl = a.x + b * a.sx_b + (int64_t)(2 * s) * a.sx_d + rr;
+            const float* xr = a.x + b * a.sx_b + (int64_t)(2 * s + 1) * a.sx_d + rr;
+            for (int q = 0; q < C; ++q) {
+                if (has_l) ml = fmaxf(ml, xl[q * R]);
+                if (has_r) mr = fmaxf(mr, xr[q * R]);
+            }
+            if (!has_l) ml = 0.f;
+            if (!has_r) mr = 0.f;
+            const bool dead = ml == -CUDART_INF_F || mr == -CUDART_INF_F;
+            for (int q = 0; q < C; ++q) {
+                eL[(row * C + q) * R + rr] = dead ? 0.f : (has_l ? __expf(xl[q * R] - ml) : 1.f);
+                eR[(row * C + q) * R + rr] = dead ? 0.f : (has_r ? __expf(xr[q * R] - mr) : 1.f);
+            }
+            sh[row * R + rr] = dead ? -CUDART_INF_F : ml + mr;
+        }
+        __syncthreads();
+        float acc[PSR_RT];
+#pragma unroll
+        for (int q = 0; q < PSR_RT; ++q) acc[q] = 0.f;
+        int l = 0;
+        for (int ks = 0; ks < nstage; ++ks, ++kg) {
+            while (!mbar_try_wait(full + kg % PS_NSTG, (kg / PS_NSTG) & 1)) {}
+            float* wst = ring + (kg % PS_NSTG) * rps * ocr + t;
+            for (int j0 = 0; j0 < rps; j0 += C, ++l) {
+                float tl[PSR_RT];
+#pragma unroll
+                for (int q = 0; q < PSR_RT; ++q) tl[q] = 0.f;
+#pragma unroll 4
+                for (int rp = 0; rp < C; ++rp) {
+                    const float wv = __expf(wst[(j0 + rp) * ocr]);
+                    const float* er = eR + rp * R + r;
+#pragma unroll
+                    for (int q = 0; q < PSR_RT; ++q) tl[q] = fmaf(er[q * C * R], wv, tl[q]);
+                }
+                const float* el = eL + l * R + r;
+#pragma unroll
+                for (int q = 0; q < PSR_RT; ++q) acc[q] = fmaf(el[q * C * R], tl[q], acc[q]);
+            }
+            __syncthreads();  // everyone is done with this stage: refill it
+            if (t == 0 && kg + PS_NSTG < total_stages) issue(kg + PS_NSTG);
+        }
+#pragma unroll
+        for (int q = 0; q < PSR_RT; ++q) {
+            if (q < nr) {
+                const int64_t b = (int64_t)j + (int64_t)(row0 + q) * a.w;
+                const float shift = sh[q * R + r];
+                float res;
+                if (shift == -CUDART_INF_F) {
+                    res = -CUDART_INF_F;
+                } else if (acc[q] >= 1e-30f) {
+                    res = shift + __logf(acc[q]);
+                } else {
+                    // exact two-pass log-sum-exp (underflow: all mass far below the child maxima)
+                    const float* xl = a.x + b * a.sx_b + (int64_t)(2 * s) * a.sx_d + r;
+                    const float* xr = a.x + b * a.sx_b + (int64_t)(2 * s + 1) * a.sx_d + r;
+                    float m2 = -CUDART_INF_F;
+                    for (int i = 0; i < ic; ++i)
+                        m2 = fmaxf(m2, (has_l ? xl[(i / C) * R] : 0.f) + (has_r ? xr[(i % C) * R] : 0.f) + slab[(int64_t)i * ocr + t]);
+                    res = m2;
+                    if (m2 != -CUDART_INF_F) {
+                        float acc2 = 0.f;
+                        for (int i = 0; i < ic; ++i)
+                            acc2 += expf((has_l ? xl[(i / C) * R] : 0.f) + (has_r ? xr[(i % C) * R] : 0.f) + slab[(int64_t)i * ocr + t] - m2);
+                        res = m2 + logf(acc2);
+                    }
+                }
+                a.out[(b * a.d_out + s) * ocr + t] = res;
+            }
+        }
+    }
+}
+
+template <int C>
+static int launch_ps_rows(const PsRowsArgs& a, cudaStream_t st) {
+    const int ocr = a.oc * a.R;
+    const int smem = PS_NSTG * a.rows_per_stage * ocr * 4 + 2 * PSR_RT * C * a.R * 4 + PSR_RT * a.R * 4 + PS_NSTG * 8 + 16;
+    cudaError_t e = cudaFuncSetAttribute(sum_ps_rows_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return spn_cuda_status(e);
+    sum_ps_rows_fwd_kernel<C><<<dim3(a.w, a.d_out), ocr, smem, st>>>(a);
+    return spn_launch_status();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Fused backward for one row per weight set (B == w: the CSPN log-likelihood training step).  The slab of a
 // (conditional, scope) is read ONCE (TMA ring, as in the forward) and its gradient written ONCE (staged in shared memory,
 // TMA bulk store); the activation gradients of the two children fall out of the same pass:
@@ -255,6 +395,8 @@ static int ps_bwd_rows_per_stage(int c, int ocr) {
 
 }  // namespace
 
+extern "C" int spn_sum_ps_bwd_supported(int c, int oc, int R);
+
 extern "C" int spn_sum_ps_supported(int c, int oc, int R) {
     const int ocr = oc * R;
     return (ocr >= 32 && ocr <= 1024 && ocr % 4 == 0 && PS_STAGE_BYTES / (ocr * 4) >= 1 && c >= 1 && c <= 256) ? 1 : 0;
@@ -266,6 +408,18 @@ extern "C" int spn_sum_ps_fwd(const float* x, int64_t sx_b, int64_t sx_d, int d_
     if (!spn_sum_ps_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
     if (B == 0) return SPN_OK;
     if (d_out > 65535) return SPN_ERR_UNSUPPORTED;
+    // many rows per weight set: block per (weight set, scope), linear-domain accumulation (see sum_ps_rows_fwd_kernel)
+    if (B / w >= 16 && oc * R <= 256 && spn_sum_ps_bwd_supported(c, oc, R) &&
+        (size_t)PS_NSTG * ps_bwd_rows_per_stage(c, oc * R) * oc * R * 4 + 2 * PSR_RT * c * R * 4 <= 200 * 1024) {
+        PsRowsArgs ra{};
+        ra.x = x; ra.sx_b = sx_b; ra.sx_d = sx_d; ra.lw = lw; ra.out = out;
+        ra.B = B; ra.w = w; ra.d_in = d_in; ra.d_out = d_out; ra.oc = oc; ra.R = R;
+        ra.rows_per_stage = ps_bwd_rows_per_stage(c, oc * R);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (c == 8) return launch_ps_rows<8>(ra, st);
+        if (c == 16) return launch_ps_rows<16>(ra, st);
+        return launch_ps_rows<32>(ra, st);
+    }
     PsArgs a{};
     a.x = x; a.sx_b = sx_b; a.sx_d = sx_d; a.lw = lw; a.out = out;
     a.B = B; a.w = w; a.d_in = d_in; a.d_out = d_out; a.c = c; a.oc = oc; a.R = R;

@@ -19,7 +19,8 @@ def _general(x, lw):
     return out
 
 
-@pytest.mark.parametrize("n,w,d_in,c,oc,R", [(1, 48, 4, 16, 16, 8), (3, 20, 3, 8, 16, 4), (1, 7, 2, 16, 8, 8), (2, 5, 8, 12, 64, 16)])
+@pytest.mark.parametrize("n,w,d_in,c,oc,R", [(1, 48, 4, 16, 16, 8), (3, 20, 3, 8, 16, 4), (1, 7, 2, 16, 8, 8), (2, 5, 8, 12, 64, 16),
+                                           (40, 6, 4, 16, 16, 8), (17, 5, 3, 8, 16, 4), (70, 3, 2, 32, 8, 8)])  # >= 16 rows per set: rows kernel
 def test_per_sample_sum_forward_matches_general_kernel(n, w, d_in, c, oc, R):
     from ratspn_b200 import ops
     from ratspn_b200 import _abi
