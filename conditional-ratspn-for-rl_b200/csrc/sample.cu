@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) sample_sum_kernel(SampleSumArgs a) {
 
     float best = -CUDART_INF_F;
     int besti = 0x7fffffff;
-    for (int i = lane; i < a.ic; i += G) {
+    auto logit = [&](int i) -> float {
         int r = rsel, ii = i;
         if (a.root) { r = i / a.ic_top; ii = i - r * a.ic_top; }
         float v = lwp[(int64_t)ii * a.sw_i + (int64_t)r * a.sw_r];
@@ -63,15 +63,36 @@ __global__ void __launch_bounds__(256) sample_sum_kernel(SampleSumArgs a) {
             if (xr) off += xr[(int64_t)rp * a.sxc_c + (int64_t)r * a.sxc_r];
             v += off;
         }
-        if (!a.mpe) {
-            if (a.gumbel) {
-                v += a.gumbel[((q * a.d + s) * (int64_t)a.ic + i) * a.Rs + rs];
-            } else {
-                const uint64_t elem = ((((uint64_t)q + a.q_offset) * a.d + s) * (uint64_t)a.ic + i) * a.Rs + rs;
-                v += spn_gumbel(elem, stream_id, seed_v);
+        return v;
+    };
+    if (!a.mpe && !a.gumbel && a.Rs == 1 && (a.ic & 3) == 0) {
+        // in-kernel noise, one repetition per item: the virtual noise elements of consecutive in-channels are consecutive,
+        // so one Philox block (four words) serves four in-channels -- the same values spn_gumbel() gives one at a time
+        const uint64_t base4 = ((((uint64_t)q + a.q_offset) * a.d + s) * (uint64_t)a.ic) >> 2;
+        for (int i4 = lane; i4 < (a.ic >> 2); i4 += G) {
+            const uint4 rnd = spn_philox4x32(base4 + i4, stream_id, seed_v);
+            const uint32_t bits[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = 4 * i4 + j;
+                const float e = -__logf(spn_u01(bits[j]));
+                const float v = logit(i) - __logf(fmaxf(e, 1e-30f));
+                if (v > best || besti == 0x7fffffff) { best = v; besti = i; }
             }
         }
-        if (v > best || besti == 0x7fffffff) { best = v; besti = i; }
+    } else {
+        for (int i = lane; i < a.ic; i += G) {
+            float v = logit(i);
+            if (!a.mpe) {
+                if (a.gumbel) {
+                    v += a.gumbel[((q * a.d + s) * (int64_t)a.ic + i) * a.Rs + rs];
+                } else {
+                    const uint64_t elem = ((((uint64_t)q + a.q_offset) * a.d + s) * (uint64_t)a.ic + i) * a.Rs + rs;
+                    v += spn_gumbel(elem, stream_id, seed_v);
+                }
+            }
+            if (v > best || besti == 0x7fffffff) { best = v; besti = i; }
+        }
     }
 #pragma unroll
     for (int sh = G / 2; sh > 0; sh >>= 1) {

@@ -321,19 +321,28 @@ def _i32c(t):
     return t.to(torch.int32).contiguous() if t is not None else None
 
 
-def sample_sum(lw, root, Q, d, Rs, pa, pa_strides, unravel, rep, xc, Qe, gumbel, mpe, seed=0, q_offset=0):
-    """One Sum layer of the top-down pass (include/spn_b200.h: spn_sample_sum).  Returns int32 [Q, d, Rs]."""
+def sampling_weights(lw: torch.Tensor) -> torch.Tensor:
+    """Shared log-weights [1, d, ic, oc, R] re-laid out [1, d, R, oc, ic] (in-channel contiguous) for the sampling
+    kernels: every (sample, scope) reads ONE column (its parent's out-channel) over all in-channels, which is a 4-byte
+    gather with stride oc*R in the parameter layout (1600 sectors per column at cfg 2) and one contiguous 6.4 KB segment
+    in this one.  Pass the result to sample_sum(..., transposed=True)."""
+    require_cuda(lw)
+    return _f32c(lw).permute(0, 1, 4, 3, 2).contiguous()
+
+
+def sample_sum(lw, root, Q, d, Rs, pa, pa_strides, unravel, rep, xc, Qe, gumbel, mpe, seed=0, q_offset=0,
+               transposed=False):
+    """One Sum layer of the top-down pass (include/spn_b200.h: spn_sample_sum).  Returns int32 [Q, d, Rs].
+    ``transposed``: ``lw`` comes from sampling_weights() ([W, d, R, oc, ic])."""
     require_cuda(lw, pa, rep, xc, gumbel)
     lw = _f32c(lw)
     Wsets = lw.shape[0]
-    if root:
-        _, _, KR, oc, _ = lw.shape
-        ic = KR
-        sw = (KR * oc, 0, oc, 1, 0)  # the repetition offset is applied through ic_top inside the kernel
+    if transposed:
+        _, dl, Rw, oc, ic = lw.shape
+    elif root:
+        _, _, ic, oc, _ = lw.shape
     else:
-        _, dl, ic, oc, R = lw.shape
-        assert dl == d
-        sw = (dl * ic * oc * R, ic * oc * R, oc * R, R, 1)
+        _, dl, ic, oc, Rw = lw.shape
     w = Wsets if Wsets != 1 else 1
     c, xc_din, sxc, ic_top = 0, 0, (0, 0, 0, 0), 0
     if xc is not None:
@@ -341,11 +350,15 @@ def sample_sum(lw, root, Q, d, Rs, pa, pa_strides, unravel, rep, xc, Qe, gumbel,
         xc_din, c, Rx = xc.shape[-3:]
         sxc = (xc_din * c * Rx, c * Rx, Rx, 1)
     if root:
-        Rr = root  # number of repetitions
-        ic_top = ic // Rr
-        sw = (KR * oc, 0, oc, 1, ic_top * oc)
+        ic_top = ic // root  # root = number of repetitions; in-channel k = r * ic_top + i
+        # (w, d, i, o, r) element strides; the repetition offset is applied through ic_top inside the kernel
+        sw = (ic * oc, 0, 1, ic, ic_top) if transposed else (ic * oc, 0, oc, 1, ic_top * oc)
         if xc is None:
             c = int(round(math.sqrt(ic_top)))
+    else:
+        assert dl == d
+        sw = (dl * Rw * oc * ic, Rw * oc * ic, 1, ic, oc * ic) if transposed else \
+            (dl * ic * oc * Rw, ic * oc * Rw, oc * Rw, Rw, 1)
     out = torch.empty(Q, d, Rs, device=lw.device, dtype=torch.int32)
     hseed, dseed = _seed_args(seed)
     call("spn_sample_sum", ptr(lw), *sw, Wsets, w, Q, d, ic, oc, Rs, ptr(pa), *pa_strides, int(unravel), ptr(rep),

@@ -360,6 +360,12 @@ class RatSpn(nn.Module):
             assert tuple(t.shape) == tuple(shape), f"noise shape {tuple(t.shape)} != {tuple(shape)}"
             return t.to(device=dev, dtype=th.float32).contiguous()
 
+        def column_major(lw):
+            """Shared weights of a wide layer, many samples: in-channel-contiguous copy (ops.sampling_weights)."""
+            if lw.shape[0] == 1 and lw.shape[2] >= 64 and Q >= 64:
+                return ops.sampling_weights(lw), True
+            return lw, False
+
         rep = None
         parent = None          # int32 [Q, d, Rs]: channel chosen at the CrossProduct currently above us
         parent_strides = None
@@ -380,7 +386,8 @@ class RatSpn(nn.Module):
             pa = node.expand(*lead).reshape(Q).contiguous()
             g = take((*lead, 1, K, 1))
             xc = self.root._input_cache_fused if self.root._is_input_cache_enabled else None
-            k0 = ops.sample_sum(lwr, cfg.R, Q, 1, 1, pa, (1, 0, 0), False, None, xc, Qe, g, is_mpe, seed)
+            lwt, tr = column_major(lwr)
+            k0 = ops.sample_sum(lwt, cfg.R, Q, 1, 1, pa, (1, 0, 0), False, None, xc, Qe, g, is_mpe, seed, transposed=tr)
             k0 = k0.view(Q)
             rep = th.div(k0, ic_top, rounding_mode='floor').to(th.int32)
             parent = (k0 - rep * ic_top).to(th.int32).view(Q, 1, 1)
@@ -407,7 +414,9 @@ class RatSpn(nn.Module):
                 d = layer.in_features
                 g = take((*lead, d, layer.in_channels, cfg.R))
                 xc = layer._input_cache_fused if layer._is_input_cache_enabled else None
-                parent = ops.sample_sum(layer.weights, 0, Q, d, Rs, pa, (1, 0, 0), False, None, xc, Qe, g, is_mpe, seed)
+                lwt, tr = column_major(layer.weights)
+                parent = ops.sample_sum(lwt, 0, Q, d, Rs, pa, (1, 0, 0), False, None, xc, Qe, g, is_mpe, seed,
+                                        transposed=tr)
                 parent_strides = (d * Rs, Rs, 1)
                 start = layer_index - 1
 
@@ -419,8 +428,9 @@ class RatSpn(nn.Module):
             d = layer.in_features
             g = take((*lead, d, layer.in_channels, Rs))
             xc = layer._input_cache_fused if layer._is_input_cache_enabled else None
-            parent = ops.sample_sum(layer.weights, 0, Q, d, Rs, parent, parent_strides, True, rep, xc, Qe, g, is_mpe,
-                                    seed)
+            lwt, tr = column_major(layer.weights)
+            parent = ops.sample_sum(lwt, 0, Q, d, Rs, parent, parent_strides, True, rep, xc, Qe, g, is_mpe,
+                                    seed, transposed=tr)
             parent_strides = (d * Rs, Rs, 1)
 
         base = self._leaf.base_leaf
