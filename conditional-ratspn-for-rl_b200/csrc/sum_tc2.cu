@@ -75,6 +75,7 @@ struct OpgArgs {
                            //   FWD: packed eL, eR ([pair][128 rows] words) + row shifts mL, mR  -> read by the dX / dW kernels
                            //   DXR: G tile in the dW kernel's B-operand layout                    -> read by the dW kernel
     const uint8_t* fhand;  // DX, optional: the forward's hand-off (then no x rows are loaded and nothing is exponentiated)
+    const uint8_t* ghand;  // DXL, optional: the G tiles the DXR launch of the same call handed off (then out / g are not read)
     int B, d_in, d_out, R;
     int ntiles, nsplit, debug, dbg_n;
 };
@@ -466,6 +467,7 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
                     float* my_m = Ms + vb * 2 * 128 + row;
                     constexpr int FH_BYTES = 2 * NPAIR * 512 + 1024;   // forward hand-off per tile: eL, eR, shifts
                     const bool from_fwd = MODE != OPG_FWD && a.fhand != nullptr;
+                    const bool g_ready = MODE == OPG_DXL && from_fwd && a.ghand != nullptr;   // G arrives by TMA as well
                     if (from_fwd) {
                     } else if (STAGED) {
                         mbar_wait_sticky(x_full, n_tile & 1, abort_flag);
@@ -503,7 +505,10 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
                         // DXR: U = eL, scale = eR.  DXL: U = eR, scale = eL.  Straight from the forward's hand-off by TMA.
                         if (warp == 8) {
                             const uint8_t* src = a.fhand + ((size_t)sr * a.ntiles + tile) * FH_BYTES;
-                            mbar_arrive_expect_tx_elect(h_full + vb, FH_BYTES);
+                            mbar_arrive_expect_tx_elect(h_full + vb, FH_BYTES + (g_ready ? NPAIR * 512 : 0));
+                            if (g_ready)
+                                bulk_g2s_elect(Vs + vb * NPAIR * 128, a.ghand + ((size_t)sr * a.ntiles + tile) * (NPAIR * 512), NPAIR * 512,
+                                               h_full + vb);
                             bulk_g2s_elect(MODE == OPG_DXR ? Us + vb * NPAIR * 128 : Es + vb * NPAIR * 128, src, NPAIR * 512, h_full + vb);
                             bulk_g2s_elect(MODE == OPG_DXR ? Es + vb * NPAIR * 128 : Us + vb * NPAIR * 128, src + NPAIR * 512, NPAIR * 512, h_full + vb);
                             bulk_g2s_elect(Ms + vb * 2 * 128, src + 2 * NPAIR * 512, 1024, h_full + vb);
@@ -515,7 +520,9 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
 #pragma unroll
                         for (int j = 0; j < NPAIR; ++j) dst[j * 128] = e[j];
                     }
-                    if (MODE != OPG_FWD) {
+                    if (g_ready) {
+                        mbar_wait_sticky(h_full + vb, (n_tile >> 1) & 1, abort_flag);  // eL, eR, shifts and G have landed
+                    } else if (MODE != OPG_FWD) {
                         // G = g * exp(shift - out) = g / (linear-domain sum); out = -inf (impossible row): no gradient.  The
                         // exponent is capped so that rows whose sum underflowed in the forward (rescue path) stay finite.
                         // Half 0 produces the o-groups [0, GH0), half 1 [GH0, NVG) (whole 16-byte chunks of 8 outputs), written
@@ -900,9 +907,12 @@ extern "C" int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g
     a.fhand = (const uint8_t*)fhand;
     a.B = B; a.d_in = d_in; a.d_out = d_out; a.R = R;
     opg_split(a, B, d_out, R);
-    int rc = dispatch_opg<OPG_DXL>(c, a, (cudaStream_t)stream);
+    // right child first: it also hands the G tiles over (to the dW kernel, and to the left-child launch below, which then
+    // neither reads out / g nor recomputes G)
+    int rc = dispatch_opg<OPG_DXR>(c, a, (cudaStream_t)stream);
     if (rc != SPN_OK) return rc;
-    return dispatch_opg<OPG_DXR>(c, a, (cudaStream_t)stream);
+    if (a.hand && a.fhand) a.ghand = a.hand;
+    return dispatch_opg<OPG_DXL>(c, a, (cudaStream_t)stream);
 }
 
 extern "C" int spn_debug_tc_prof(unsigned long long* out_host, int reset) {
