@@ -113,29 +113,39 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.stop, self.thread = index, [], threading.Event(), None
-
-    def _loop(self):
-        # NVML directly (a sample every few ms, so that even a 45 ms timed region gets several); nvidia-smi as fall-back
-        try:
+        self.nvml = None
+        try:  # NVML directly: a sample every few ms, so that even a 45 ms timed region gets several
             import pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            bits = [("hw_slowdown", getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8)),
-                    ("hw_thermal_slowdown", getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
-                    ("sw_thermal_slowdown", getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
-                    ("sw_power_cap", getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4))]
-            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
                 getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            bits = [getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                    getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                    getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4)]
             mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            reasons(h)
+            self.nvml = (pynvml, h, reasons, bits, mx)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        pynvml, h, reasons, bits, mx = self.nvml
+        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        mask = int(reasons(h))
+        self.rows.append([str(sm), str(mx)] + ["Active" if mask & b else "Not Active" for b in bits])
+
+    def _loop(self):
+        if self.nvml is not None:
             while not self.stop.is_set():
-                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
-                mask = int(get_reasons(h))
-                self.rows.append([str(sm), str(mx)] + ["Active" if mask & b else "Not Active" for _, b in bits])
+                try:
+                    self._sample_nvml()
+                except Exception:
+                    pass
                 self.stop.wait(0.004)
             return
-        except Exception:
-            pass
-        while not self.stop.is_set():
+        while not self.stop.is_set():  # fall-back: nvidia-smi (slow: ~100 ms per sample)
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
                                       str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
@@ -153,6 +163,17 @@ class ClockSampler:
     def __exit__(self, *a):
         self.stop.set()
         self.thread.join(timeout=6)
+        if not self.rows:  # the region was shorter than one sampling period: sample right at its end
+            try:
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
