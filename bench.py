@@ -239,7 +239,7 @@ def main():
     sum_layers = [m for m in model.modules() if hasattr(m, "invalidate_weight_cache")]
 
     # Adam as in mnist_gen_train.py:599, as one launch over flat buffers (spn_adam_step); SPN_TORCH_ADAM=1 -> torch's fused Adam
-    if os.environ.get("SPN_TORCH_ADAM"):
+    if os.environ.get("SPN_TORCH_ADAM") or (args.graph and world == 1):  # FlatAdam keeps its step count on the host: not capturable
         opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
     else:
         opt = FlatAdam(reducer, lr=1e-3, module=model)

@@ -97,7 +97,8 @@ class FlatAdam:
     gradient buffer, so the update of the whole model is a single 28-byte-per-parameter HBM stream.
 
     ``module``: the model whose tensor-core operand-image caches must be invalidated after every step (the kernel
-    writes the parameters behind autograd's version counters)."""
+    writes the parameters behind autograd's version counters).  The step count (bias correction) lives on the host, so a
+    step must not be captured into a CUDA graph; use ``torch.optim.Adam(capturable=True)`` there."""
 
     def __init__(self, reducer: FlatGradAllReducer, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  module: torch.nn.Module = None):
