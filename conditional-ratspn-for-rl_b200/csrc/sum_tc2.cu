@@ -23,6 +23,7 @@
 // Outputs whose linear-domain sum underflows are recomputed exactly in fp32, so results keep th.logsumexp semantics.
 #include <stdlib.h>
 
+#include <atomic>
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -789,10 +790,14 @@ __global__ void __launch_bounds__(256) tc_wimage_t_kernel(const uint4* __restric
 // one zeroed work counter per launch, taken round-robin from a small ring (launches in flight never come near 256)
 __device__ unsigned int g_opg_counters[256];
 static unsigned int* opg_next_counter(cudaStream_t st) {
-    static unsigned int* base = nullptr;
-    static unsigned int next = 0;
-    if (!base && cudaGetSymbolAddress((void**)&base, g_opg_counters) != cudaSuccess) return nullptr;
-    unsigned int* c = base + (next++ & 255u);
+    static std::atomic<unsigned int*> base{nullptr};   // forward and backward launch from different host threads
+    static std::atomic<unsigned int> next{0};
+    unsigned int* b = base.load();
+    if (!b) {
+        if (cudaGetSymbolAddress((void**)&b, g_opg_counters) != cudaSuccess) return nullptr;
+        base.store(b);
+    }
+    unsigned int* c = b + (next.fetch_add(1) & 255u);
     if (cudaMemsetAsync(c, 0, sizeof(unsigned int), st) != cudaSuccess) return nullptr;
     return c;
 }

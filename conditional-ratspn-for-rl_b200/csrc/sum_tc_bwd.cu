@@ -7,6 +7,7 @@
 //                                             softmax backward of the weight normalisation)
 #include <stdlib.h>
 
+#include <atomic>
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -371,10 +372,14 @@ extern "C" int spn_sum_tc_supported(int c, int oc, int R);
 
 __device__ unsigned int g_bwd_counters[256];
 static unsigned int* bwd_next_counter(cudaStream_t st) {
-    static unsigned int* base = nullptr;
-    static unsigned int next = 0;
-    if (!base && cudaGetSymbolAddress((void**)&base, g_bwd_counters) != cudaSuccess) return nullptr;
-    unsigned int* c = base + (next++ & 255u);
+    static std::atomic<unsigned int*> base{nullptr};   // forward and backward launch from different host threads
+    static std::atomic<unsigned int> next{0};
+    unsigned int* b = base.load();
+    if (!b) {
+        if (cudaGetSymbolAddress((void**)&b, g_bwd_counters) != cudaSuccess) return nullptr;
+        base.store(b);
+    }
+    unsigned int* c = b + (next.fetch_add(1) & 255u);
     if (cudaMemsetAsync(c, 0, sizeof(unsigned int), st) != cudaSuccess) return nullptr;
     return c;
 }
