@@ -455,6 +455,43 @@ def new_seed(device, mpe: bool = False):
     return int(torch.randint(0, 2 ** 62, (1,)).item())
 
 
+class EntropyCombineFn(torch.autograd.Function):
+    """H = sum_k exp(lw) * (-lw + ce + lwd + own - ll) over the in-channels (and the repetitions when ``reduce_r``);
+    see include/spn_b200.h: spn_entropy_combine_fwd.  ``lwd_has_grad``: the responsibility's log-weight term is not
+    detached (aux_with_grad), so it cancels the weight-entropy term in the gradient as well as in the value."""
+
+    @staticmethod
+    def forward(ctx, lw, ce, own, ll, reduce_r, lwd_has_grad):
+        require_cuda(lw, ce, own, ll)
+        lw, ce, own, ll = _f32c(lw), _f32c(ce), _f32c(own), _f32c(ll)
+        w, d, ic, oc, R = lw.shape
+        assert ce.shape == (w, d, ic, R) and own.shape == (w, d, ic, R) and ll.shape == lw.shape
+        H = torch.empty((w, d, oc) if reduce_r else (w, d, oc, R), device=lw.device, dtype=torch.float32)
+        call("spn_entropy_combine_fwd", ptr(lw), ptr(ce), ptr(own), ptr(ll), w * d, ic, oc, R, int(reduce_r), ptr(H),
+             stream_ptr(lw.device))
+        ctx.save_for_backward(lw, ce, own, ll)
+        ctx.flags = (bool(reduce_r), bool(lwd_has_grad))
+        return H
+
+    @staticmethod
+    def backward(ctx, gH):
+        lw, ce, own, ll = ctx.saved_tensors
+        reduce_r, lwd_has_grad = ctx.flags
+        w, d, ic, oc, R = lw.shape
+        need = ctx.needs_input_grad
+        dlw = torch.empty_like(lw) if need[0] else None
+        dce = torch.empty_like(ce) if need[1] else None
+        down = torch.empty_like(own) if need[2] else None
+        dll = torch.empty_like(ll) if need[3] else None
+        call("spn_entropy_combine_bwd", ptr(lw), ptr(ce), ptr(own), ptr(ll), ptr(_f32c(gH)), w * d, ic, oc, R,
+             int(reduce_r), int(lwd_has_grad), ptr(dlw), ptr(dce), ptr(down), ptr(dll), stream_ptr(lw.device))
+        return dlw, dce, down, dll, None, None
+
+
+def entropy_combine(lw, ce, own, ll, reduce_r=False, lwd_has_grad=False):
+    return EntropyCombineFn.apply(lw, ce, own, ll, reduce_r, lwd_has_grad)
+
+
 def launches() -> int:
     return _abi.LAUNCHES
 

@@ -603,13 +603,21 @@ class RatSpn(nn.Module):
                     ll = layer.forward(child_ll, detach_params=not aux_with_grad)
                     log_weights = layer.weights if aux_with_grad else layer.weights.detach()
                 ll = ll.permute(1, 2, 0, 3, 4)  # [w, d, K, oc, R]
-                own_ll = th.diagonal(child_ll, dim1=0, dim2=3).permute(0, 1, 3, 2).unsqueeze(-2)  # [w, d, K, 1, R]
-                responsibility = log_weights + own_ll - ll
-                [weighted_ch_ents, weighted_aux_resp], weight_entropy = self.weigh_tensors(
-                    layer_index=layer_index, tensors=[child_entropies.unsqueeze(3), responsibility],
-                    return_weight_ent=True)
-                node_entropies = weight_entropy + weighted_ch_ents + weighted_aux_resp
-                if verbose:
+                own_ll = th.diagonal(child_ll, dim1=0, dim2=3).permute(0, 1, 3, 2)  # [w, d, K, R]
+                if not verbose:
+                    # one fused kernel per direction (spn_entropy_combine_*): weight entropy + weighted child entropies +
+                    # weighted log-responsibilities; `weights_g` carries the gradient of the mixture weights, the
+                    # responsibility's own log-weight term only does so with aux_with_grad (it is detached otherwise)
+                    is_root = layer_index == self.max_layer_index
+                    weights_g = self.root_weights_split_by_rep if is_root else layer.weights
+                    node_entropies = ops.entropy_combine(weights_g, child_entropies, own_ll, ll, reduce_r=is_root,
+                                                         lwd_has_grad=aux_with_grad)
+                else:
+                    responsibility = log_weights + own_ll.unsqueeze(-2) - ll
+                    [weighted_ch_ents, weighted_aux_resp], weight_entropy = self.weigh_tensors(
+                        layer_index=layer_index, tensors=[child_entropies.unsqueeze(3), responsibility],
+                        return_weight_ent=True)
+                    node_entropies = weight_entropy + weighted_ch_ents + weighted_aux_resp
                     metrics.update({'weight_entropy': weight_entropy.detach(),
                                     'responsibility': responsibility.detach()})
         logging_dict = {}

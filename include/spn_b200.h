@@ -272,6 +272,20 @@ int spn_debug_tc_aborts(int* out_host);
 int spn_debug_tc_prof(unsigned long long* out_host, int reset);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Sum-level combination of the recursive entropy approximation (rat_spn.py:661-746 with weigh_tensors :591-623):
+ *   H[n, o, r] = sum_k exp(lw[k,o,r]) * (-lw[k,o,r] + ce[k,r] + lwd[k,o,r] + own[k,r] - ll[k,o,r])
+ * (weight entropy + weighted child entropies + weighted log-responsibilities; lwd = lw in value, the responsibility's
+ * `log_weights` term that the reference detaches unless aux_with_grad).  lw, ll [n, ic, oc, R]; ce, own [n, ic, R];
+ * H [n, oc, R], or [n, oc] with reduce_r = 1 (root: also summed over the repetitions).  All contiguous fp32.
+ * Backward: gH like H -> dlw, dll like lw; dce, down like ce (any output pointer may be NULL).
+ * ------------------------------------------------------------------------------------------------------------- */
+int spn_entropy_combine_fwd(const float* lw, const float* ce, const float* own, const float* ll, int64_t n, int ic, int oc,
+                            int R, int reduce_r, float* H, void* stream);
+int spn_entropy_combine_bwd(const float* lw, const float* ce, const float* own, const float* ll, const float* gH, int64_t n,
+                            int ic, int oc, int R, int reduce_r, int lwd_has_grad, float* dlw, float* dce, float* down,
+                            float* dll, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Adam update over flat fp32 buffers (one launch for the whole model): torch.optim.Adam semantics without amsgrad /
  * weight decay, as used by mnist_experiments/mnist_gen_train.py:599, :669, :720.  step_size = lr / (1 - beta1^t), inv_sqrt_bc2 = 1 / sqrt(1 -
  * beta2^t); all pointers 16-byte aligned.

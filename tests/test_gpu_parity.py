@@ -209,15 +209,16 @@ def test_recursive_entropy_no_grad_vs_golden(tag, mask):
     assert_close(H, c.t(f"{tag}__H"), 1e-4, 1e-4, tag)
 
 
+@pytest.mark.parametrize("verbose", [True, False])  # False: fused spn_entropy_combine kernels; True: logged composite
 @pytest.mark.parametrize("tag,aux", [("entgrad", False), ("entgradaux", True)])
-def test_recursive_entropy_gradients_vs_golden(tag, aux):
+def test_recursive_entropy_gradients_vs_golden(tag, aux, verbose):
     c = Case("ratspn_pad_tanh")
     m = build_ratspn(c, DEV)
     m._test_noise = c.noise(tag)
     H, log = m.recursive_entropy_approx(sample_size=4, aux_with_grad=aux, marginal_mask=c.t("marginal_mask").to(DEV),
-                                        verbose=True)
+                                        verbose=verbose)
     assert_close(H, c.t(f"{tag}__H"), 1e-4, 1e-4, tag)
-    assert any(k.startswith("lay8/rep0/node_entropy") for k in log)
+    assert any(k.startswith("lay8/rep0/node_entropy") for k in log) == verbose
     (-H.sum()).backward()
     ref = c.grads(f"{tag}__grad__")
     got = model_grads(m)
