@@ -6,6 +6,7 @@ north star); everything downstream of ``set_params`` -- log-likelihood, sampling
 weight kernels of libspn_b200.so, where every weight is read exactly once (HBM-streaming).
 """
 import logging
+from contextlib import contextmanager
 from dataclasses import dataclass
 from typing import Optional, Tuple, Type
 
@@ -170,10 +171,32 @@ class CSPN(RatSpn):
         base.mean_param = th.zeros(0, base.in_features, self.config.I, self.config.R, device=dev)
         base.std_param = th.zeros(0, base.in_features, self.config.I, self.config.R, device=dev)
 
+    _pinned_condition = None
+
+    @contextmanager
+    def conditioned(self, condition: th.Tensor):
+        """Evaluate the gating network ONCE for several calls on the same conditionals (the SAC actor update
+        calls ``sample`` and ``recursive_entropy_approx`` on the same observations, sb3.py:132-137 and :158-162):
+
+            with cspn.conditioned(obs):
+                ctx = cspn.sample(mode='onehot', condition=obs)
+                ent, _ = cspn.recursive_entropy_approx(condition=obs)
+            (loss built from both).backward()       # ONE backward: the calls share the gating network's graph
+
+        Inside the block, calls that pass this very tensor as ``condition`` re-use the installed parameters; any other
+        ``condition`` is evaluated as usual.  Opt-in because sharing the autograd graph between separate ``backward()``
+        calls would need ``retain_graph``."""
+        self.set_params(condition)
+        self._pinned_condition = condition
+        try:
+            yield self
+        finally:
+            self._pinned_condition = None
+
     # ---------------------------------------------------------------------------------- condition= wrappers
     def forward(self, x: th.Tensor, condition: th.Tensor = None, **kwargs) -> th.Tensor:
         """Conditional log-likelihood log p(x | condition); x [batch, conditionals, F, 1, 1] (cspn.py:72-100)."""
-        if condition is not None:
+        if condition is not None and condition is not self._pinned_condition:
             self.set_params(condition)
         weight_sets = self._leaf.base_leaf.mean_param.shape[0]
         if x.dim() == 3:
@@ -186,25 +209,25 @@ class CSPN(RatSpn):
         return super().forward(x, **kwargs)
 
     def recursive_entropy_approx(self, condition: th.Tensor = None, **kwargs) -> Tuple[th.Tensor, Optional[dict]]:
-        if condition is not None:
+        if condition is not None and condition is not self._pinned_condition:
             self.set_params(condition)
         return super().recursive_entropy_approx(**kwargs)
 
     def naive_entropy_approx(self, condition: th.Tensor = None, **kwargs) -> th.Tensor:
-        if condition is not None:
+        if condition is not None and condition is not self._pinned_condition:
             self.set_params(condition)
         return super().naive_entropy_approx(**kwargs)
 
     def huber_entropy_lb(self, condition: th.Tensor = None, **kwargs):
         """Huber et al. entropy lower bound of p(. | condition)   (cspn.py:112-115)."""
-        if condition is not None:
+        if condition is not None and condition is not self._pinned_condition:
             self.set_params(condition)
         return super().huber_entropy_lb(**kwargs)
 
     def sample(self, mode: str = None, condition: th.Tensor = None, class_index=None, evidence: th.Tensor = None,
                **kwargs):
         """Sample x ~ p(. | condition)   (cspn.py:125-145)."""
-        if condition is not None:
+        if condition is not None and condition is not self._pinned_condition:
             self.set_params(condition)
         assert class_index is None or condition.shape[0] == len(class_index), \
             "The batch size of the condition must equal the length of the class index list if they are provided!"

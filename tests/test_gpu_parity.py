@@ -340,3 +340,30 @@ def test_baseline_config2_width_properties_and_oracle_slice():
     with torch.no_grad():
         ref = O.forward(P, arch, x[:3], microbatch=1)
     assert_close(full[:3], ref, LL_RT, LL_AT, "config-2 width, 3 rows vs oracle")
+
+
+def test_cspn_conditioned_block_shares_one_gating_pass_vs_golden():
+    """``with cspn.conditioned(obs)``: sample + entropy on one evaluation of the gating network; same values and
+    gradients as the reference's policy-update pattern (which evaluates it twice)."""
+    c = Case("cspn_small")
+    m = build_cspn(c, DEV)
+    cond = c.t("cond").to(DEV)
+    ev = c.t("evidence").to(DEV)
+    m._test_noise = c.noise("sac")
+    calls = []
+    orig = m.set_params
+    m.set_params = lambda x: (calls.append(1), orig(x))[1]
+    with m.conditioned(cond):
+        ctx = m.sample(mode="onehot", condition=cond, evidence=ev)
+        H, _ = m.recursive_entropy_approx(condition=cond, sample_size=3, marginal_mask=c.t("failed").to(DEV))
+    assert len(calls) == 1 and len(m._test_noise) == 0
+    assert_close(ctx.sample, c.t("sac__sample"), 1e-5, 1e-5, "SAC sample")
+    assert_close(H, c.t("sac__H"), 1e-4, 1e-4, "SAC entropy")
+    (-(0.1 * H + ctx.sample.squeeze(0).squeeze(0).squeeze(-1).sum(-1)).mean()).backward()
+    ref = c.grads("sac__grad__")
+    got = model_grads(m)
+    for k in ref:
+        grad_close(got[k], ref[k], f"sac grad {k}")
+    m._test_noise = None
+    m.sample(mode="index", condition=cond)   # outside the block the gating network runs again
+    assert len(calls) == 2

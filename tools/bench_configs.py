@@ -76,8 +76,9 @@ def cfg3():
 
     def update():
         m.zero_grad(set_to_none=True)
-        ctx = m.sample(mode="onehot", condition=obs, evidence=ev)
-        H, _ = m.recursive_entropy_approx(condition=obs, sample_size=5, marginal_mask=failed)
+        with m.conditioned(obs):  # one gating-network pass for sample + entropy (one backward)
+            ctx = m.sample(mode="onehot", condition=obs, evidence=ev)
+            H, _ = m.recursive_entropy_approx(condition=obs, sample_size=5, marginal_mask=failed)
         act = ctx.sample.reshape(B, 17)
         (-(0.1 * H + act.sum(-1)).mean()).backward()
         m.zero_grad(set_to_none=True)
@@ -97,8 +98,9 @@ def cfg3():
     def update_static():
         for p in params:
             p.grad.zero_()
-        ctx = m.sample(mode="onehot", condition=obs, evidence=ev)
-        H, _ = m.recursive_entropy_approx(condition=obs, sample_size=5, marginal_mask=failed)
+        with m.conditioned(obs):  # one gating-network pass for sample + entropy (one backward)
+            ctx = m.sample(mode="onehot", condition=obs, evidence=ev)
+            H, _ = m.recursive_entropy_approx(condition=obs, sample_size=5, marginal_mask=failed)
         act = ctx.sample.reshape(B, 17)
         (-(0.1 * H + act.sum(-1)).mean()).backward()
         (-m(xs, condition=obs).mean()).backward()
