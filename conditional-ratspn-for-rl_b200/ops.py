@@ -4,6 +4,7 @@ Each ``torch.autograd.Function`` here is a forward/backward kernel pair; PyTorch
 current stream and the autograd tape.  All tensors must live on a CUDA device -- there is no other backend.
 """
 import math
+import os
 
 import torch
 
@@ -176,6 +177,7 @@ class SumFn(torch.autograd.Function):
         out = torch.empty(out_shape, device=x.device, dtype=torch.float32)
         Wsets, w, B, d_out, ic, oc, R, _ = ints
         if (mode == "xsum" and layout == "ref" and Wsets == w and w > 1 and d_out <= 65535 and ic * oc * R * 4 >= 16384
+                and not os.environ.get("SPN_NO_PS")  # A/B switch for tests: force the general kernels
                 and _abi.lib().spn_sum_ps_supported(c, oc, R)):
             # per-conditional weights, big enough slabs: TMA-staged HBM-streaming kernel
             call("spn_sum_ps_fwd", ptr(x), sx[0], sx[1], d_in, c, ptr(lw), w, B, d_out, oc, R, ptr(out), stream_ptr(x.device))

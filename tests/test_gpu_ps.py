@@ -87,3 +87,47 @@ def test_fused_per_sample_backward_matches_general_kernels(w, d_in, c, oc, R):
         scale = float(ref.abs().max())
         assert float((got - ref).abs().max()) <= 2e-5 * scale + 1e-7, f"{what}: {float((got - ref).abs().max()):.3e} vs scale {scale:.3e}"
     assert float(x.grad[0, 0, 0, :, 0].abs().max()) == 0.0 or torch.isfinite(x.grad[0, 0, 0, :, 0]).all()
+
+
+@pytest.mark.parametrize("n", [1, 20])
+def test_cspn_model_streaming_paths_match_general_kernels(n, monkeypatch):
+    """Whole CSPN (gating net -> per-conditional weights) through the streaming kernels (n = 1: fused backward; n = 20:
+    many-rows forward + general backward) against the same model forced onto the general exact kernels."""
+    import numpy as np
+    import ratspn_b200 as rb
+    torch.manual_seed(3)
+    np.random.seed(3)
+    cfg = rb.CspnConfig()
+    cfg.F_cond = (6,)
+    cfg.F, cfg.R, cfg.D, cfg.I, cfg.S, cfg.C = 32, 4, 3, 8, 16, 1
+    cfg.dropout = 0.0
+    cfg.leaf_base_class = rb.RatNormal
+    cfg.leaf_base_kwargs = {"min_sigma": 0.05, "max_sigma": 1.0}
+    cfg.tanh_squash = False
+    cfg.feat_layers, cfg.sum_param_layers, cfg.dist_param_layers = [8], [8], [8]
+    cfg.cond_layers_inner_act = torch.nn.LeakyReLU
+    m = rb.CSPN(cfg).to(DEV)
+    w = 12
+    cond = torch.randn(w, 6, device=DEV)
+    x = torch.randn(n, w, 32, 1, 1, device=DEV)
+    x[0, 1, ::5] = float("nan")
+    res = []
+    for general in (False, True):
+        if general:
+            monkeypatch.setenv("SPN_NO_PS", "1")
+        else:
+            monkeypatch.delenv("SPN_NO_PS", raising=False)
+        m.zero_grad(set_to_none=True)
+        ll = m(x, condition=cond)
+        (-ll.mean()).backward()
+        with torch.no_grad():
+            torch.manual_seed(11)
+            H, _ = m.recursive_entropy_approx(condition=cond, sample_size=20)
+        res.append((ll.detach().clone(), H.clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+    (ll_a, H_a, g_a), (ll_b, H_b, g_b) = res
+    torch.testing.assert_close(ll_a, ll_b, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(H_a, H_b, rtol=1e-4, atol=1e-3)
+    assert set(g_a) == set(g_b)
+    for k in g_b:
+        scale = float(g_b[k].abs().max()) + 1e-12
+        assert float((g_a[k] - g_b[k]).abs().max()) <= 2e-4 * scale + 1e-7, k
