@@ -43,6 +43,8 @@ SIGNATURES = {
     "spn_entropy_combine_fwd": [_P, _P, _P, _P, _L, _I, _I, _I, _I, _P, _P],
     "spn_entropy_combine_bwd": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "spn_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _P],
+    "spn_sum_ps_fwd_raw": [_P, _L, _L, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "spn_sum_ps_bwd_raw": [_P, _L, _L, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _P],
     "spn_sum_ps_bwd_supported": [_I, _I, _I],
     "spn_sum_ps_bwd": [_P, _L, _L, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _L, _L, _P],
     "spn_xprod_fwd": [_P, _I, _I, _I, _I, _P, _P],

@@ -44,6 +44,9 @@ class CspnConfig(RatSpnConfig):
     sum_param_layers: list = None
     dist_param_layers: list = None
     cond_layers_inner_act: Type[nn.Module] = nn.LeakyReLU
+    # extension: keep the inner Sum layers' head outputs UNNORMALISED and fold F.log_softmax into the
+    # streaming kernels; `layer.weight_param` is then raw (as for a RatSpn), `layer.weights` normalises on read
+    fuse_weight_norm: bool = False
 
     def __setattr__(self, key, value):
         if hasattr(self, key):
@@ -134,7 +137,9 @@ class CSPN(RatSpn):
         for layer in self._inner_layers:
             if isinstance(layer, Sum):
                 shape = (B, layer.in_features, layer.in_channels, layer.out_channels, layer.num_repetitions)
-                layer.weight_param = F.log_softmax(next(head)(hidden).view(shape), dim=2)
+                raw = next(head)(hidden).view(shape)
+                layer._raw_weights = bool(self.config.fuse_weight_norm)
+                layer.weight_param = raw if layer._raw_weights else F.log_softmax(raw, dim=2)
             else:
                 layer.num_conditionals = B
         root = self.root

@@ -21,10 +21,15 @@ struct PsArgs {
     const float* x; int64_t sx_b, sx_d;   // x [B][d_in][c][R] (c, R contiguous)
     const float* lw;                      // [w][d_out][ic][oc][R] contiguous
     float* out;                           // [B][d_out][oc][R] contiguous
+    float* logz;                          // RAW: log-normaliser of the unnormalised weights, [B][d_out][oc][R] (output)
     int B, w, d_in, d_out, c, oc, R;
 };
 
-// grid (B, d_out); block = oc * R threads (one per output of the (row, scope) pair)
+// grid (B, d_out); block = oc * R threads (one per output of the (row, scope) pair).
+// RAW: `lw` holds the UNNORMALISED head outputs of the gating network; the log_softmax over the in-channels
+// (cspn.py:274, :282) is fused: out = lse_i(x_i + raw_i) - lse_i(raw_i), both sums relative to one running maximum of the
+// raw weights, and the normaliser is written out for the backward kernel.
+template <bool RAW>
 __global__ void __launch_bounds__(1024) sum_ps_fwd_kernel(PsArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int ocr = a.oc * a.R, c = a.c, ic = c * c;
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(1024) sum_ps_fwd_kernel(PsArgs a) {
     const float ms = dead ? 0.f : mx * L2E;
     // the right-child terms of this repetition, pre-scaled for ex2: thread-private column of a [c][blockDim] array is not
     // needed -- xr is re-used in place (all threads of a repetition read the same value: broadcast)
-    float acc = 0.f;
+    float acc = 0.f, accz = 0.f, M = -CUDART_INF_F;   // RAW: accz = sum exp2(v - M), acc = sum exp2(v - M + child terms)
     int l = 0, rp = 0;
     float lvs = fmaf(xl[r], L2E, -ms);
     for (int k = 0; k < nstage; ++k) {
@@ -84,8 +89,21 @@ __global__ void __launch_bounds__(1024) sum_ps_fwd_kernel(PsArgs a) {
         const float* wst = ring + (k % PS_NSTG) * rows_per_stage * ocr + t;
 #pragma unroll 4
         for (int j = 0; j < nrow; ++j) {
-            const float arg = fmaf(wst[j * ocr] + xr[rp * a.R + r], L2E, lvs);
-            acc += ex2_approx(arg);
+            if (RAW) {
+                const float v = wst[j * ocr] * L2E;
+                if (v > M) {
+                    const float sc = ex2_approx(M - v);   // exp2(-inf) = 0 on the first element
+                    acc *= sc;
+                    accz *= sc;
+                    M = v;
+                }
+                const float e = ex2_approx(v - M);
+                accz += e;
+                acc += e * ex2_approx(fmaf(xr[rp * a.R + r], L2E, lvs));
+            } else {
+                const float arg = fmaf(wst[j * ocr] + xr[rp * a.R + r], L2E, lvs);
+                acc += ex2_approx(arg);
+            }
             if (++rp == c) {
                 rp = 0;
                 ++l;
@@ -95,19 +113,21 @@ __global__ void __launch_bounds__(1024) sum_ps_fwd_kernel(PsArgs a) {
         __syncthreads();  // everyone is done with this stage: refill it
         if (t == 0 && k + PS_NSTG < nstage) issue(k + PS_NSTG);
     }
+    const float lz = RAW ? (M + __log2f(accz)) * 0.6931471805599453f : 0.f;   // lse_i(raw_i)
+    if (RAW) a.logz[(b * a.d_out + s) * ocr + t] = lz;
     float res;
     if (dead) {
         res = -CUDART_INF_F;
     } else if (acc >= 1e-30f) {
-        res = mx + __logf(acc);
+        res = mx + __logf(acc) - (RAW ? __logf(accz) : 0.f);
     } else {
         // exact two-pass log-sum-exp over t_i = x_i + lw_i (underflow: all mass far below the child maxima)
         float m2 = -CUDART_INF_F;
-        for (int i = 0; i < ic; ++i) m2 = fmaxf(m2, xl[(i / c) * a.R + r] + xr[(i % c) * a.R + r] + slab[(int64_t)i * ocr + t]);
+        for (int i = 0; i < ic; ++i) m2 = fmaxf(m2, xl[(i / c) * a.R + r] + xr[(i % c) * a.R + r] + slab[(int64_t)i * ocr + t] - lz);
         res = m2;
         if (m2 != -CUDART_INF_F) {
             float acc2 = 0.f;
-            for (int i = 0; i < ic; ++i) acc2 += expf(xl[(i / c) * a.R + r] + xr[(i % c) * a.R + r] + slab[(int64_t)i * ocr + t] - m2);
+            for (int i = 0; i < ic; ++i) acc2 += expf(xl[(i / c) * a.R + r] + xr[(i % c) * a.R + r] + slab[(int64_t)i * ocr + t] - lz - m2);
             res = m2 + logf(acc2);
         }
     }
@@ -265,6 +285,7 @@ static int launch_ps_rows(const PsRowsArgs& a, cudaStream_t st) {
 // per-sample weights.
 struct PsBwdArgs {
     const float* x; int64_t sx_b, sx_d;
+    const float* logz;   // RAW: lse_i(raw_i) from the forward, [B][d_out][oc][R]
     const float* lw; const float* out; const float* g;
     float* dlw; float* dx; int64_t sdx_b, sdx_d;
     int w, d_in, d_out, oc, R, rows_per_stage;
@@ -273,7 +294,9 @@ struct PsBwdArgs {
 constexpr int PSB_NIN = 3;   // slab stages in flight (loads)
 constexpr int PSB_NOUT = 2;  // gradient stages (stores)
 
-template <int C>
+// RAW: `lw` holds unnormalised weights; d raw[i] = g * (p_i - w_i) with p_i = exp(x_i + raw_i - logz - out) (responsibility)
+// and w_i = exp(raw_i - logz) (the softmax backward folded in: sum_i dlw_i = g).
+template <int C, bool RAW>
 __global__ void __launch_bounds__(1024) sum_ps_bwd_kernel(PsBwdArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int ocr = a.oc * a.R, R = a.R;
@@ -321,7 +344,8 @@ __global__ void __launch_bounds__(1024) sum_ps_bwd_kernel(PsBwdArgs a) {
     float gv = a.g[(b * a.d_out + s) * ocr + t];
     const bool dead = ov == -CUDART_INF_F;   // impossible output: no gradient (th.logsumexp backward gives 0 * nan -> we give 0)
     if (dead) gv = 0.f;
-    const float os = dead ? 0.f : ov * L2E;
+    const float zs = RAW ? a.logz[(b * a.d_out + s) * ocr + t] * L2E : 0.f;
+    const float os = (dead ? 0.f : ov * L2E) + zs;
     float xrs[C];                            // right-child terms of this repetition, pre-scaled
 #pragma unroll
     for (int q = 0; q < C; ++q) xrs[q] = xr[q * R + r] * L2E;
@@ -350,9 +374,9 @@ __global__ void __launch_bounds__(1024) sum_ps_bwd_kernel(PsBwdArgs a) {
             float acc_l = 0.f;
 #pragma unroll
             for (int q = 0; q < C; ++q) {
-                const float arg = fmaf(wst[(j0 + q) * ocr], L2E, lvs + xrs[q]);
-                const float val = gv * ex2_approx(arg);
-                ost[(j0 + q) * ocr] = val;
+                const float wv = wst[(j0 + q) * ocr];
+                const float val = gv * ex2_approx(fmaf(wv, L2E, lvs + xrs[q]));
+                ost[(j0 + q) * ocr] = RAW ? val - gv * ex2_approx(fmaf(wv, L2E, -zs)) : val;
                 acc_l += val;
                 acc_r[q] += val;
             }
@@ -376,14 +400,18 @@ __global__ void __launch_bounds__(1024) sum_ps_bwd_kernel(PsBwdArgs a) {
     }
 }
 
-template <int C>
-static int launch_ps_bwd(const PsBwdArgs& a, int B, cudaStream_t st) {
+template <int C, bool RAW>
+static int launch_ps_bwd2(const PsBwdArgs& a, int B, cudaStream_t st) {
     const int ocr = a.oc * a.R;
     const int smem = (PSB_NIN + PSB_NOUT) * a.rows_per_stage * ocr * 4 + 4 * C * a.R * 4 + PSB_NIN * 8 + 16;
-    cudaError_t e = cudaFuncSetAttribute(sum_ps_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(sum_ps_bwd_kernel<C, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return spn_cuda_status(e);
-    sum_ps_bwd_kernel<C><<<dim3(B, a.d_out), ocr, smem, st>>>(a);
+    sum_ps_bwd_kernel<C, RAW><<<dim3(B, a.d_out), ocr, smem, st>>>(a);
     return spn_launch_status();
+}
+template <int C>
+static int launch_ps_bwd(const PsBwdArgs& a, int B, cudaStream_t st) {
+    return a.logz ? launch_ps_bwd2<C, true>(a, B, st) : launch_ps_bwd2<C, false>(a, B, st);
 }
 
 static int ps_bwd_rows_per_stage(int c, int ocr) {
@@ -400,6 +428,26 @@ extern "C" int spn_sum_ps_bwd_supported(int c, int oc, int R);
 extern "C" int spn_sum_ps_supported(int c, int oc, int R) {
     const int ocr = oc * R;
     return (ocr >= 32 && ocr <= 1024 && ocr % 4 == 0 && PS_STAGE_BYTES / (ocr * 4) >= 1 && c >= 1 && c <= 256) ? 1 : 0;
+}
+
+static int ps_fwd_rowwise(const float* x, int64_t sx_b, int64_t sx_d, int d_in, int c, const float* lw, int w, int B,
+                          int d_out, int oc, int R, float* out, float* logz, cudaStream_t st) {
+    PsArgs a{};
+    a.x = x; a.sx_b = sx_b; a.sx_d = sx_d; a.lw = lw; a.out = out; a.logz = logz;
+    a.B = B; a.w = w; a.d_in = d_in; a.d_out = d_out; a.c = c; a.oc = oc; a.R = R;
+    const int ocr = oc * R;
+    const int rows = PS_STAGE_BYTES / (ocr * 4);
+    const int smem = PS_NSTG * rows * ocr * 4 + 2 * c * R * 4 + PS_NSTG * 8 + 16;
+    if (logz) {
+        cudaError_t e = cudaFuncSetAttribute(sum_ps_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return spn_cuda_status(e);
+        sum_ps_fwd_kernel<true><<<dim3(B, d_out), ocr, smem, st>>>(a);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(sum_ps_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return spn_cuda_status(e);
+        sum_ps_fwd_kernel<false><<<dim3(B, d_out), ocr, smem, st>>>(a);
+    }
+    return spn_launch_status();
 }
 
 extern "C" int spn_sum_ps_fwd(const float* x, int64_t sx_b, int64_t sx_d, int d_in, int c, const float* lw, int w, int B,
@@ -420,16 +468,18 @@ extern "C" int spn_sum_ps_fwd(const float* x, int64_t sx_b, int64_t sx_d, int d_
         if (c == 16) return launch_ps_rows<16>(ra, st);
         return launch_ps_rows<32>(ra, st);
     }
-    PsArgs a{};
-    a.x = x; a.sx_b = sx_b; a.sx_d = sx_d; a.lw = lw; a.out = out;
-    a.B = B; a.w = w; a.d_in = d_in; a.d_out = d_out; a.c = c; a.oc = oc; a.R = R;
-    const int ocr = oc * R;
-    const int rows = PS_STAGE_BYTES / (ocr * 4);
-    const int smem = PS_NSTG * rows * ocr * 4 + 2 * c * R * 4 + PS_NSTG * 8 + 16;
-    cudaError_t e = cudaFuncSetAttribute(sum_ps_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return spn_cuda_status(e);
-    sum_ps_fwd_kernel<<<dim3(B, d_out), ocr, smem, (cudaStream_t)stream>>>(a);
-    return spn_launch_status();
+    return ps_fwd_rowwise(x, sx_b, sx_d, d_in, c, lw, w, B, d_out, oc, R, out, nullptr, (cudaStream_t)stream);
+}
+
+// Same with UNNORMALISED weights (the gating network's raw head outputs): F.log_softmax over the in-channels
+// (cspn.py:274, :282) fused; logz [B, d_out, oc, R] receives lse_i(raw_i) for spn_sum_ps_bwd_raw.  One row per weight set.
+extern "C" int spn_sum_ps_fwd_raw(const float* x, int64_t sx_b, int64_t sx_d, int d_in, int c, const float* raw, int w, int B,
+                                  int d_out, int oc, int R, float* out, float* logz, void* stream) {
+    if (!x || !raw || !out || !logz || B < 0 || w <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
+    if (B != w) return SPN_ERR_UNSUPPORTED;
+    if (!spn_sum_ps_supported(c, oc, R) || d_out > 65535) return SPN_ERR_UNSUPPORTED;
+    if (B == 0) return SPN_OK;
+    return ps_fwd_rowwise(x, sx_b, sx_d, d_in, c, raw, w, B, d_out, oc, R, out, logz, (cudaStream_t)stream);
 }
 
 extern "C" int spn_sum_ps_bwd_supported(int c, int oc, int R) {
@@ -451,6 +501,25 @@ extern "C" int spn_sum_ps_bwd(const float* x, int64_t sx_b, int64_t sx_d, int d_
     if (d_out > 65535) return SPN_ERR_UNSUPPORTED;
     PsBwdArgs a{};
     a.x = x; a.sx_b = sx_b; a.sx_d = sx_d; a.lw = lw; a.out = out; a.g = g; a.dlw = dlw; a.dx = dx;
+    a.sdx_b = sdx_b; a.sdx_d = sdx_d; a.w = w; a.d_in = d_in; a.d_out = d_out; a.oc = oc; a.R = R;
+    a.rows_per_stage = ps_bwd_rows_per_stage(c, oc * R);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c == 8) return launch_ps_bwd<8>(a, B, st);
+    if (c == 16) return launch_ps_bwd<16>(a, B, st);
+    return launch_ps_bwd<32>(a, B, st);
+}
+
+// Backward of spn_sum_ps_fwd_raw: draw [w, d_out, c*c, oc, R] is the gradient w.r.t. the UNNORMALISED weights (softmax
+// backward fused), dx as in spn_sum_ps_bwd.
+extern "C" int spn_sum_ps_bwd_raw(const float* x, int64_t sx_b, int64_t sx_d, int d_in, int c, const float* raw, int w, int B,
+                                  int d_out, int oc, int R, const float* logz, const float* out, const float* g, float* draw,
+                                  float* dx, int64_t sdx_b, int64_t sdx_d, void* stream) {
+    if (!x || !raw || !logz || !out || !g || !draw || !dx || B < 0 || w <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
+    if (B != w) return SPN_ERR_UNSUPPORTED;
+    if (!spn_sum_ps_bwd_supported(c, oc, R) || d_out > 65535) return SPN_ERR_UNSUPPORTED;
+    if (B == 0) return SPN_OK;
+    PsBwdArgs a{};
+    a.x = x; a.sx_b = sx_b; a.sx_d = sx_d; a.lw = raw; a.logz = logz; a.out = out; a.g = g; a.dlw = draw; a.dx = dx;
     a.sdx_b = sdx_b; a.sdx_d = sdx_d; a.w = w; a.d_in = d_in; a.d_out = d_out; a.oc = oc; a.R = R;
     a.rows_per_stage = ps_bwd_rows_per_stage(c, oc * R);
     cudaStream_t st = (cudaStream_t)stream;

@@ -56,13 +56,17 @@ class DiffSampleFn(th.autograd.Function):
         y, ch = ops.sample_leaf(mu, sigma, Q, plan.card, Rs, parent, pstr, rep, plan.eps, plan.mpe, plan.inv32, plan.ev,
                                 plan.ev_strides, Qe, plan.squash, True, plan.seed)
         plan.ch, plan.rep = ch, rep
-        ctx.plan, ctx.rec, ctx.lws, ctx.xcs, ctx.leaf = plan, rec, lws, xcs, (mu, sigma, y)
+        ctx.plan, ctx.rec, ctx.lws, ctx.xcs, ctx.leaf = plan, rec, lws, xcs, (mu, sigma)
+        # the output must go through save_for_backward: a plain attribute would close a reference cycle (node -> y -> node)
+        # that keeps the whole autograd graph (and its AccumulateGrad nodes) alive until the cyclic GC runs
+        ctx.save_for_backward(y)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         plan, rec, lws, xcs = ctx.plan, ctx.rec, ctx.lws, ctx.xcs
-        mu, sigma, y = ctx.leaf
+        mu, sigma = ctx.leaf
+        (y,) = ctx.saved_tensors
         k = len(plan.steps)
         Q, Qe, Rs = plan.Q, plan.Qe, plan.Rs
         through_sums = k > 0 and not plan.mpe

@@ -4,6 +4,7 @@ bound by launch overhead, not by the device).  Everything on the hot path is cap
 synchronises, kernels take the caller's stream, and the in-kernel noise of the sampling kernels is keyed by a device
 word refreshed inside the graph (ops.new_seed), so every replay draws fresh samples.
 """
+import gc
 from typing import Callable
 
 import torch
@@ -22,6 +23,7 @@ class GraphedCall:
     """
 
     def __init__(self, fn: Callable, warmup: int = 3):
+        gc.collect()  # autograd graphs kept alive only by reference cycles would pin default-stream AccumulateGrad nodes
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)

@@ -48,6 +48,7 @@ class Sum(AbstractLayer):
         self._input_cache = None        # stand-alone forward: the layer input itself (layers.py:102-103)
         self._input_cache_fused = None  # fused forward: the *CrossProduct input* this layer's input derives from
         self.consolidated_weights = None
+        self._raw_weights = False       # CSPN with fused weight normalisation: weight_param holds the raw head outputs
         self._tc_cache = {}             # bf16 operand image + log-normaliser of weight_param (tensor-core path)
 
     def __getstate__(self):
@@ -71,7 +72,7 @@ class Sum(AbstractLayer):
     @property
     def weights(self) -> th.Tensor:
         """Log-weights [w, d, ic, oc, r]; normalised over ic on every read for a RatSpn (layers.py:81-88)."""
-        if self.ratspn:
+        if self.ratspn or self._raw_weights:
             return F.log_softmax(self.weight_param, dim=2)
         return self.weight_param
 

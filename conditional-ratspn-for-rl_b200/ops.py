@@ -205,6 +205,54 @@ class SumFn(torch.autograd.Function):
         return dx, dlw, None, None
 
 
+def sum_raw_supported(x: torch.Tensor, raw: torch.Tensor) -> bool:
+    """Can SumRawFn take this (activations [*, w, d_in, c, R], unnormalised per-conditional weights [w, d, c*c, oc, R])?
+    One row per weight set, slabs of at least 16 KB, channel counts of the streaming kernels."""
+    if x.dim() < 4 or raw.dim() != 5 or not x.is_cuda:
+        return False
+    w, d_out, ic, oc, R = raw.shape
+    c = x.shape[-2]
+    B = x.numel() // (x.shape[-3] * c * R) if x.shape[-1] == R else -1
+    return (w > 1 and B == w and c * c == ic and d_out <= 65535 and ic * oc * R * 4 >= 16384
+            and x.dtype == torch.float32 and raw.dtype == torch.float32
+            and bool(_abi.lib().spn_sum_ps_supported(c, oc, R)) and bool(_abi.lib().spn_sum_ps_bwd_supported(c, oc, R)))
+
+
+class SumRawFn(torch.autograd.Function):
+    """Fused CrossProduct + Sum for per-conditional UNNORMALISED weights (CSPN gating-net head outputs): the
+    F.log_softmax(dim=2) of cspn.py:274, :282 is folded into the streaming kernels (spn_sum_ps_fwd_raw / _bwd_raw), which
+    saves two full passes over the weights in the forward and three in the backward."""
+
+    @staticmethod
+    def forward(ctx, x, raw):
+        require_cuda(x, raw)
+        x, raw = _f32c(x), _f32c(raw)
+        w, d_out, ic, oc, R = raw.shape
+        d_in, c = x.shape[-3], x.shape[-2]
+        out = torch.empty(*x.shape[:-3], d_out, oc, R, device=x.device, dtype=torch.float32)
+        logz = torch.empty(w, d_out, oc, R, device=x.device, dtype=torch.float32)
+        sxb, sxd = d_in * c * R, c * R
+        call("spn_sum_ps_fwd_raw", ptr(x), sxb, sxd, d_in, c, ptr(raw), w, w, d_out, oc, R, ptr(out), ptr(logz),
+             stream_ptr(x.device))
+        ctx.save_for_backward(x, raw, out, logz)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, raw, out, logz = ctx.saved_tensors
+        w, d_out, ic, oc, R = raw.shape
+        d_in, c = x.shape[-3], x.shape[-2]
+        sxb, sxd = d_in * c * R, c * R
+        dx, draw = torch.empty_like(x), torch.empty_like(raw)
+        call("spn_sum_ps_bwd_raw", ptr(x), sxb, sxd, d_in, c, ptr(raw), w, w, d_out, oc, R, ptr(logz), ptr(out),
+             ptr(_f32c(g)), ptr(draw), ptr(dx), sxb, sxd, stream_ptr(x.device))
+        return (dx if ctx.needs_input_grad[0] else None), (draw if ctx.needs_input_grad[1] else None)
+
+
+def sum_forward_raw(x, raw):
+    return SumRawFn.apply(x, raw)
+
+
 class SumTcFn(torch.autograd.Function):
     """Shared-weight fused CrossProduct + Sum on the tensor cores; activations in the internal [d, R, B, c] layout.
 

@@ -235,7 +235,11 @@ class RatSpn(nn.Module):
                 continue
             if caching:
                 layer._input_cache_fused = h.detach()
-            h = ops.sum_forward(h, layer._weights_for(detach_params), "xsum")
+            if layer._raw_weights and ops.sum_raw_supported(h, layer.weight_param):
+                # CSPN with fused weight normalisation: the raw head outputs go straight into the streaming kernels
+                h = ops.sum_forward_raw(h, layer.weight_param.detach() if detach_params else layer.weight_param)
+            else:
+                h = ops.sum_forward(h, layer._weights_for(detach_params), "xsum")
         if layer_index == self.max_layer_index:
             if caching:
                 self.root._input_cache_fused = h.detach()

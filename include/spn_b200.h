@@ -138,6 +138,17 @@ int spn_sum_ps_bwd(const float* x, int64_t sx_b, int64_t sx_d, int d_in, int c, 
                    int oc, int R, const float* out, const float* g, float* dlw, float* dx, int64_t sdx_b,
                    int64_t sdx_d, void* stream);
 
+/* The same pair for UNNORMALISED per-conditional weights (the raw head outputs of the gating network): the
+ * F.log_softmax over the in-channels of cspn.py:274, :282 is fused into both directions.
+ *   forward : out = lse_i(x_i + raw_i) - lse_i(raw_i); logz [B, d_out, oc, R] receives lse_i(raw_i)
+ *   backward: draw[i] = g * (exp(x_i + raw_i - logz - out) - exp(raw_i - logz)); dx as above
+ * One row per weight set (B == w). */
+int spn_sum_ps_fwd_raw(const float* x, int64_t sx_b, int64_t sx_d, int d_in, int c, const float* raw, int w, int B,
+                       int d_out, int oc, int R, float* out, float* logz, void* stream);
+int spn_sum_ps_bwd_raw(const float* x, int64_t sx_b, int64_t sx_d, int d_in, int c, const float* raw, int w, int B,
+                       int d_out, int oc, int R, const float* logz, const float* out, const float* g, float* draw,
+                       float* dx, int64_t sdx_b, int64_t sdx_d, void* stream);
+
 /* Stand-alone CrossProduct (materialising) and its backward: layers.py:419-440.  x [B, d_in, c, R] contiguous,
  * out [B, ceil_pow2(d_in)/2, c*c, R] contiguous; dx [B, d_in, c, R] contiguous. */
 int spn_xprod_fwd(const float* x, int B, int d_in, int c, int R, float* out, void* stream);

@@ -131,3 +131,54 @@ def test_cspn_model_streaming_paths_match_general_kernels(n, monkeypatch):
     for k in g_b:
         scale = float(g_b[k].abs().max()) + 1e-12
         assert float((g_a[k] - g_b[k]).abs().max()) <= 2e-4 * scale + 1e-7, k
+
+
+@pytest.mark.parametrize("n", [1, 3])
+def test_cspn_fused_weight_normalisation_matches_reference_semantics(n):
+    """CspnConfig.fuse_weight_norm: the raw head outputs go into spn_sum_ps_fwd_raw / _bwd_raw (log_softmax fused).
+    Same LL, same gradients w.r.t. the gating network, same MPE sample and entropy as the unfused model."""
+    import numpy as np
+    import ratspn_b200 as rb
+
+    def build(fused):
+        torch.manual_seed(5)
+        np.random.seed(5)
+        cfg = rb.CspnConfig()
+        cfg.F_cond = (6,)
+        cfg.F, cfg.R, cfg.D, cfg.I, cfg.S, cfg.C = 32, 4, 3, 8, 16, 1
+        cfg.dropout = 0.0
+        cfg.leaf_base_class = rb.RatNormal
+        cfg.leaf_base_kwargs = {"min_sigma": 0.05, "max_sigma": 1.0}
+        cfg.tanh_squash = False
+        cfg.feat_layers, cfg.sum_param_layers, cfg.dist_param_layers = [8], [8], [8]
+        cfg.cond_layers_inner_act = torch.nn.LeakyReLU
+        cfg.fuse_weight_norm = fused
+        return rb.CSPN(cfg).to(DEV)
+
+    ref, fus = build(False), build(True)
+    fus.load_state_dict(ref.state_dict())
+    w = 10
+    cond = torch.randn(w, 6, device=DEV) * 3.0   # large head outputs: the running-maximum rescaling is exercised
+    x = torch.randn(n, w, 32, 1, 1, device=DEV)
+    out = []
+    for m in (ref, fus):
+        m.zero_grad(set_to_none=True)
+        ll = m(x, condition=cond)
+        (-ll.mean()).backward()
+        with torch.no_grad():
+            mpe = m.sample(mode="index", condition=cond, is_mpe=True).sample
+            torch.manual_seed(9)
+            H, _ = m.recursive_entropy_approx(condition=cond, sample_size=4)
+        out.append((ll.detach(), mpe, H, {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+    if n == 1:
+        assert fus._inner_layers[1]._raw_weights and not ref._inner_layers[1]._raw_weights
+        # weight_param holds the raw head outputs, .weights normalises on read
+        assert float(fus._inner_layers[1].weights.exp().sum(2).sub(1).abs().max()) < 1e-4
+    (ll_a, mpe_a, H_a, g_a), (ll_b, mpe_b, H_b, g_b) = out
+    torch.testing.assert_close(ll_b, ll_a, rtol=1e-5, atol=2e-4)
+    torch.testing.assert_close(mpe_b, mpe_a)
+    torch.testing.assert_close(H_b, H_a, rtol=1e-4, atol=1e-3)
+    assert set(g_a) == set(g_b)
+    for k in g_a:
+        scale = float(g_a[k].abs().max()) + 1e-12
+        assert float((g_a[k] - g_b[k]).abs().max()) <= 3e-4 * scale + 1e-7, k

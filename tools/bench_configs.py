@@ -218,11 +218,61 @@ def cfg5_narrow_train(w=512):
             "abi_calls": launches}
 
 
+def cfg5_narrow_train_raw(w=512):
+    """As cfg5_narrow_train, but the trainable tensors are the UNNORMALISED weights (what a gating network emits):
+    (a) reference semantics, F.log_softmax by ATen + normalised-weight kernels; (b) CspnConfig.fuse_weight_norm semantics,
+    raw weights straight into spn_sum_ps_fwd_raw / _bwd_raw."""
+    res = {}
+    for fused in (False, True):
+        torch.manual_seed(0); np.random.seed(0)
+        cfg = rb.CspnConfig()
+        cfg.F_cond = (4,)
+        cfg.F, cfg.R, cfg.D, cfg.I, cfg.S, cfg.C = 1024, 8, 6, 16, 16, 1
+        cfg.dropout = 0.0
+        cfg.leaf_base_class = rb.RatNormal
+        cfg.leaf_base_kwargs = {"min_sigma": 0.001, "max_sigma": 1.0}
+        cfg.tanh_squash = False
+        cfg.feat_layers, cfg.sum_param_layers, cfg.dist_param_layers = [4], [4], [4]
+        m = rb.RatSpn.__new__(rb.CSPN)
+        rb.RatSpn.__init__(m, cfg)
+        m.replace_layer_params()
+        m = m.to(DEV)
+        raws, inner = [], []
+        for layer in list(m._inner_layers) + [m.root]:
+            if isinstance(layer, rb.Sum):
+                shape = (w, layer.in_features, layer.in_channels, layer.out_channels, layer.num_repetitions)
+                raws.append(torch.randn(shape, device=DEV).requires_grad_(True))
+                inner.append(layer)
+            else:
+                layer.num_conditionals = w
+        base = m._leaf.base_leaf
+        base.mean_param = torch.randn(w, 1024, 16, 8, device=DEV).requires_grad_(True)
+        base.std_param = (torch.rand(w, 1024, 16, 8, device=DEV) * 0.9 + 0.05).requires_grad_(True)
+        params = raws + [base.mean_param, base.std_param]
+        x = torch.randn(1, w, 1024, 1, 1, device=DEV)
+
+        def step():
+            for p in params:
+                p.grad = None
+            for layer, raw in zip(inner, raws):
+                is_root = layer is m.root
+                layer._raw_weights = fused and not is_root
+                layer.weight_param = raw if layer._raw_weights else torch.log_softmax(raw, dim=2)
+            (-rb.RatSpn.forward(m, x).mean()).backward()
+        ms, launches = timed(step, reps=5)
+        res["fused" if fused else "log_softmax_by_aten"] = {"ms": ms, "abi_calls": launches}
+        del m, raws, params
+        torch.cuda.empty_cache()
+    res["config"] = f"cfg5-narrow training step on UNNORMALISED per-conditional weights (w={w}): F.log_softmax + kernels vs fused"
+    return res
+
+
 def main():
     out_path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "configs.json")
     res = {"device": torch.cuda.get_device_name(0), "lib": _abi.version()}
     for name, fn in (("cfg1", cfg1), ("cfg3", cfg3), ("cfg4", cfg4), ("cfg5_narrow", cfg5_narrow),
-                     ("cfg5_narrow_train", cfg5_narrow_train)):
+                     ("cfg5_narrow_train", cfg5_narrow_train),
+                     ("cfg5_narrow_train_raw", cfg5_narrow_train_raw)):
         t0 = time.time()
         try:
             res[name] = fn()
