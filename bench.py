@@ -101,7 +101,7 @@ def run_reference_arm(args):
             "config": {"workload": workload_name(), "note": "CPU host cores; each step = one 8-row micro-batch"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -198,6 +198,9 @@ def build_model(device):
     return rb.RatSpn(cfg).to(device)
 
 
+_RESULT_OUT = sys.stdout
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -209,6 +212,12 @@ def main():
     ap.add_argument("--graph", action="store_true",
                     help="replay the step from a CUDA graph (1 GPU only; the step is device-bound, gain about 2 %%)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON record): everything else written to fd 1 by libraries (the NCCL version
+    # banner, warnings) is sent to stderr
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -413,7 +422,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * CFG["F"] * 4,
                         "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "abi_calls_per_step": abi_calls_per_step, "roofline": roof, "tc_kernels": kernels, "cpu_baseline": cb, "loss": loss_host}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
