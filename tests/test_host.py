@@ -128,3 +128,41 @@ def test_forward_argument_checks_happen_before_any_kernel():
         m(torch.randn(2, 1, 17, 1, 1).double())  # dtype
     with pytest.raises(AssertionError):
         m.sample(mode=None)
+
+
+def test_cspn_conditioned_block_evaluates_the_gating_network_once():
+    """CSPN.conditioned(): calls that pass the pinned tensor re-use the installed parameters; host-only check through
+    huber_entropy_lb (parameters -> tensor ops, no kernels)."""
+    import ratspn_b200 as rb
+    torch.manual_seed(0)
+    cfg = rb.CspnConfig()
+    cfg.F_cond = (5,)
+    cfg.F, cfg.R, cfg.D, cfg.I, cfg.S, cfg.C = 8, 2, 2, 3, 3, 1
+    cfg.dropout, cfg.leaf_base_class, cfg.tanh_squash = 0.0, rb.RatNormal, True
+    cfg.leaf_base_kwargs = {"min_sigma": 0.001, "max_sigma": 1.0}
+    cfg.feat_layers, cfg.sum_param_layers, cfg.dist_param_layers = [8], [8], [8]
+    m = rb.CSPN(cfg)
+    cond, other = torch.randn(4, 5), torch.randn(4, 5)
+    calls = []
+    orig = m.set_params
+    m.set_params = lambda x: (calls.append(x), orig(x))[1]
+    with m.conditioned(cond):
+        a, _ = m.huber_entropy_lb(condition=cond, verbose=False)
+        b, _ = m.huber_entropy_lb(condition=cond, verbose=False)
+        assert len(calls) == 1 and torch.equal(a, b)
+        c, _ = m.huber_entropy_lb(condition=other, verbose=False)   # a different tensor is evaluated as usual
+        assert len(calls) == 2 and not torch.equal(a, c)
+    assert m._pinned_condition is None
+    m.huber_entropy_lb(condition=cond, verbose=False)
+    assert len(calls) == 3
+    # fused weight normalisation: weight_param holds the raw head outputs, .weights normalises on read
+    cfg.fuse_weight_norm = True
+    f = rb.CSPN(cfg)
+    f.load_state_dict(m.state_dict())
+    f.set_params(cond)
+    lay = f._inner_layers[1]
+    assert lay._raw_weights and not f.root._raw_weights
+    assert float(lay.weight_param.exp().sum(2).sub(1).abs().max()) > 1e-3
+    assert float(lay.weights.exp().sum(2).sub(1).abs().max()) < 1e-5
+    m.set_params(cond)
+    assert torch.allclose(lay.weights, m._inner_layers[1].weights, atol=1e-6)
