@@ -210,7 +210,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true",
-                    help="replay the step from a CUDA graph (1 GPU only; the step is device-bound, gain about 2 %%)")
+                    help="replay the step from a CUDA graph (1 GPU only; uses torch's capturable Adam: 8.83 ms vs 8.65 ms for the "
+                         "default eager launches with the flat Adam -- the step is device-bound)")
     args = ap.parse_args()
     # stdout carries exactly ONE line (the JSON record): everything else written to fd 1 by libraries (the NCCL version
     # banner, warnings) is sent to stderr
@@ -275,7 +276,7 @@ def main():
     sync_all()
 
     # Optionally the whole step is captured once into a CUDA graph and replayed.  Off by default: the step is
-    # device-bound (9.9 vs 10.1 ms), and the asynchronous per-parameter all-reduce hooks are not captured at N > 1.
+    # device-bound, and the asynchronous per-parameter all-reduce hooks are not captured at N > 1.
     use_graph = args.graph and world == 1
     xin = resident[0].clone()
     l0 = _abi.LAUNCHES
