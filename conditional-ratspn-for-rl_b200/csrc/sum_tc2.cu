@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
                         for (int j = 0; j < NPAIR; ++j) e[j] = __float_as_uint(v[j]);
                     }
                     {
-                        if (!STAGED && i + 2 < nt && b + 256 < a.B && has_mine) {
+                        if (!STAGED && !from_fwd && i + 2 < nt && b + 256 < a.B && has_mine) {  // x rows are only read without the forward's hand-off
                             const char* nx = reinterpret_cast<const char*>(xbase + (b + 256) * C);
                             prefetch_l2(nx);
                             prefetch_l2(nx + C * 4 - 4);
