@@ -668,3 +668,80 @@ def cspn_params(sd: Dict[str, torch.Tensor], arch: Arch, condition: torch.Tensor
     P["sigma"] = bound_stds(torch.nn.functional.linear(hd, sd["dist_std_head.weight"], sd["dist_std_head.bias"]).view(shp),
                             min_sigma, max_sigma)
     return P
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Entropy lower bound of Huber et al. 2008 (rat_spn.py:825-951), restated per repetition pair
+# ----------------------------------------------------------------------------------------------------------------
+def huber_entropy_lb(P: Dict, arch: Arch, layer_index: Optional[int] = None, detach_weights: bool = False,
+                     add_sub_weight_ent: bool = False, marginal_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """H(sum_k w_k p_k) >= -sum_k w_k log sum_j w_j z_kj with z_kj = int p_k p_j dx.
+
+    The reference carries log z for every pair of nodes and every pair of repetitions.  Leaves (rat_spn.py:849-861):
+    int N(x; m1, v1) N(x; m2, v2) dx = N(m1; m2, v1 + v2), evaluated between slot f of repetition d and the slot of
+    repetition c that holds the same original feature (the reference inverts the permutation per repetition and
+    re-applies the one of the second repetition index); masked original features contribute log z = 0.
+    Product / CrossProduct add the logs of the joined scopes (:864-887), a Sum mixes linearly (:888-921):
+        M[a, o, c, d]   = log sum_b w[b, o, d] z[a, b, c, d]
+        bound[o, c]     = -sum_a w[a, o, c] M[a, o, c, c]                 (root: M also summed over d, bound over c)
+        z'[o1, o2, c, d] = sum_a w[a, o2, c] exp(M[a, o1, c, d])
+    Returns the bound of the nodes of ``layer_index`` ([W, d, oc, R]; root [W, 1, C])."""
+    if layer_index is None:
+        layer_index = arch.max_layer_index
+    assert 1 <= layer_index <= arch.max_layer_index
+    mu, var, perm = P["mu"], P["sigma"] ** 2, P["perm"]
+    inv = invert_permutation(perm)
+    W, F, I, R = mu.shape
+    assert F % arch.card == 0, "the reference reshapes [F] -> [F / card, card] without padding (rat_spn.py:866-868)"
+    per_pair = []
+    for c in range(R):
+        row = []
+        for d in range(R):
+            slot_c = inv[perm[:, d], c]                                    # slot of repetition c with the same feature
+            m1, v1 = mu[:, slot_c, :, c], var[:, slot_c, :, c]             # [W, F, I]  (index a)
+            m2, v2 = mu[:, :, :, d], var[:, :, :, d]                       # [W, F, I]  (index b)
+            v = v1.unsqueeze(3) + v2.unsqueeze(2)
+            lz = -0.5 * (m1.unsqueeze(3) - m2.unsqueeze(2)) ** 2 / v - 0.5 * torch.log(2.0 * math.pi * v)
+            if marginal_mask is not None:
+                masked = marginal_mask.bool()[:, perm[:, d]]               # [W, F]: mask of the original feature
+                lz = torch.where(masked.view(*masked.shape, 1, 1), torch.zeros_like(lz), lz)
+            row.append(lz)
+        per_pair.append(torch.stack(row, dim=-1))                           # [W, F, a, b, d]
+    L = torch.stack(per_pair, dim=-2)                                       # [W, F, a, b, c, d]
+    L = L.reshape(W, F // arch.card, arch.card, I, I, R, R).sum(2)
+
+    bound = None
+    for li in range(1, layer_index + 1):
+        if li % 2 == 1:  # CrossProduct: pad the scopes to an even count with log z = 0, pair (2j, 2j + 1)
+            if L.shape[1] % 2 == 1:
+                L = torch.cat((L, torch.zeros_like(L[:, :1])), dim=1)
+            left, right = L[:, 0::2], L[:, 1::2]
+            o = left.shape[2]
+            # new node (a', a): right child a', left child a  (index order of rat_spn.py:872-887)
+            L = (right[:, :, :, None, :, None] + left[:, :, None, :, None, :]).reshape(W, left.shape[1], o * o, o * o, R, R)
+            continue
+        is_root = li == arch.max_layer_index
+        if is_root:
+            lw_full = P["lw_root"]                                           # [W, 1, R * ic, C, 1], k = r * ic + i
+            ic = lw_full.shape[2] // R
+            lw = lw_full.view(lw_full.shape[0], 1, R, ic, -1).permute(0, 1, 3, 4, 2)   # [W, 1, ic, C, R]
+            w_ent = -(lw_full * lw_full.exp()).sum(2)                       # [W, 1, C, 1]
+        else:
+            lw = P["lw"][li // 2 - 1]                                        # [W, d, ic, oc, R]
+            w_ent = -(lw * lw.exp()).sum(2)                                  # [W, d, oc, R]
+        wgt = lw.detach() if detach_weights else lw
+        # M[w, s, a, o, c, d] = logsumexp_b (L[w, s, a, b, c, d] + wgt[w, s, b, o, d])
+        M = torch.logsumexp(L.unsqueeze(4) + wgt[:, :, None, :, :, None, :], dim=3)
+        if add_sub_weight_ent:
+            t = w_ent.unsqueeze(2).unsqueeze(-1)                             # broadcast as rat_spn.py:903-905
+            M = M - t + t.detach()
+        if is_root:
+            M = torch.logsumexp(M, dim=-1)                                   # [W, 1, a, C, c]
+            bound = -(wgt.exp() * M).sum(dim=2).sum(-1)                      # [W, 1, C]
+        else:
+            own = torch.diagonal(M, dim1=-2, dim2=-1)                        # [W, d, a, o, c]
+            bound = -(wgt.exp() * own).sum(dim=2)                            # [W, d, o, R]
+        if li < layer_index:
+            # z'[w, s, o1, o2, c, d] = sum_a w[a, o2, c] exp(M[a, o1, c, d])
+            L = torch.logsumexp(M.unsqueeze(4) + wgt[:, :, :, None, :, :, None], dim=2)
+    return bound

@@ -103,3 +103,49 @@ def test_index_helpers_round_trip():
         assert idx == list(np.unravel_index(flat, shape))
         assert utils.tensor_index_to_flat_index(idx, shape) == flat
     assert utils.flat_index_to_tensor_index(torch.tensor(33), shape) == [1, 2, 3]
+
+
+def test_oracle_huber_bound_is_pinned_to_the_reference_and_checks_the_product_on_random_models():
+    """oracle/spn_oracle.huber_entropy_lb (per-repetition-pair restatement) against the golden vectors of the
+    unmodified reference, then product vs oracle on seeded random architectures (host tensors, fp32 vs fp64)."""
+    from oracle import spn_oracle as O
+    import ratspn_b200 as rb
+    arch = O.Arch(F=16, D=3, R=3, S=3, I=4, C=2)
+    sd = {k[len("rat__sd__"):]: _t(k) for k in GOLD.files if k.startswith("rat__sd__")}
+    raw = {}
+    for k in list(sd):
+        if k.split(".")[-1] in ("weight_param", "mean_param", "std_param") and not k.startswith("_sampling_root"):
+            sd[k] = sd[k].double().requires_grad_(True)
+            raw[k] = sd[k]
+    P = O.params_from_ratspn_state(sd, arch, min_sigma=0.05, max_sigma=1.5, dtype=torch.float64)
+    for li in (2, 4, 6):
+        got = O.huber_entropy_lb(P, arch, layer_index=li)
+        torch.testing.assert_close(got.float(), _t(f"rat__lb_layer{li}"), rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(O.huber_entropy_lb(P, arch, marginal_mask=_t("rat__mask")).float(), _t("rat__lb_mask"),
+                               rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(O.huber_entropy_lb(P, arch, detach_weights=True, add_sub_weight_ent=True).float(),
+                               _t("rat__lb_flags"), rtol=2e-5, atol=2e-5)
+    lb = O.huber_entropy_lb(P, arch, add_sub_weight_ent=True)
+    (lb * torch.tensor([1.0, -0.5], dtype=torch.float64)).sum().backward()
+    for k, p in raw.items():
+        key = "rat__grad__" + k
+        if key in GOLD.files:
+            ref = _t(key).double()
+            assert float((p.grad - ref).abs().max()) <= 2e-4 * float(ref.abs().max()) + 1e-8, k
+    # product vs oracle on random models
+    for seed, (F, D, R, S, I, C) in enumerate([(12, 2, 2, 3, 2, 1), (8, 3, 3, 2, 3, 2), (20, 2, 2, 4, 3, 3)]):
+        torch.manual_seed(40 + seed)
+        np.random.seed(40 + seed)
+        cfg = rb.RatSpnConfig()
+        cfg.F, cfg.D, cfg.R, cfg.S, cfg.I, cfg.C = F, D, R, S, I, C
+        cfg.dropout, cfg.leaf_base_class, cfg.leaf_base_kwargs, cfg.tanh_squash = 0.0, rb.RatNormal, {}, False
+        m = rb.RatSpn(cfg)
+        a = O.Arch(F=F, D=D, R=R, S=S, I=I, C=C)
+        Pm = O.params_from_ratspn_state({k: v.detach().double() for k, v in m.state_dict().items()}, a,
+                                        dtype=torch.float64)
+        mask = torch.zeros(1, F, dtype=torch.bool)
+        mask[0, 1::4] = True
+        for li in range(2, a.max_layer_index + 1, 2):
+            got, _ = m.huber_entropy_lb(layer_index=li, verbose=False, marginal_mask=mask)
+            ref = O.huber_entropy_lb(Pm, a, layer_index=li, marginal_mask=mask)
+            torch.testing.assert_close(got.double(), ref, rtol=1e-4, atol=1e-4)
