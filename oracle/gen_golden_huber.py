@@ -75,6 +75,26 @@ def main():
     for k, p in cm.named_parameters():
         if p.grad is not None:
             out["cspn__grad__" + k] = p.grad.numpy().copy()
+    # oracle vs reference on the stored quantities (appended to PIN_REPORT.txt)
+    from oracle import spn_oracle as O
+    arch = O.Arch(F=16, D=3, R=3, S=3, I=4, C=2)
+    sd = {k[len("rat__sd__"):]: torch.from_numpy(v) for k, v in out.items() if k.startswith("rat__sd__")}
+    P = O.params_from_ratspn_state(sd, arch, min_sigma=0.05, max_sigma=1.5, dtype=torch.float64)
+    lines = []
+    checks = [(f"huber lb layer {li}", O.huber_entropy_lb(P, arch, layer_index=li), out[f"rat__lb_layer{li}"]) for li in (2, 4, 6)]
+    checks.append(("huber lb marginal_mask", O.huber_entropy_lb(P, arch, marginal_mask=mask), out["rat__lb_mask"]))
+    checks.append(("huber lb detach + add_sub", O.huber_entropy_lb(P, arch, detach_weights=True, add_sub_weight_ent=True),
+                   out["rat__lb_flags"]))
+    for what, got, ref in checks:
+        ref = torch.from_numpy(np.asarray(ref)).double()
+        d = float((got - ref).abs().max())
+        lines.append(f"{'ratspn_huber':18s} {what:34s} max|d|={d:.3e} rel={d / float(ref.abs().max()):.3e} shape={tuple(ref.shape)}")
+    for ln in lines:
+        print(ln)
+    report = os.path.join(ROOT, "tests", "golden", "PIN_REPORT.txt")
+    old = [l for l in open(report).read().splitlines() if not l.startswith("ratspn_huber")] if os.path.exists(report) else []
+    with open(report, "w") as f:
+        f.write("\n".join(old + lines) + "\n")
     path = os.path.join(ROOT, "tests", "golden", "huber.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in out.items() if "lb" in k})
