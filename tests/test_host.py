@@ -166,3 +166,23 @@ def test_cspn_conditioned_block_evaluates_the_gating_network_once():
     assert float(lay.weights.exp().sum(2).sub(1).abs().max()) < 1e-5
     m.set_params(cond)
     assert torch.allclose(lay.weights, m._inner_layers[1].weights, atol=1e-6)
+
+
+def test_flat_grad_buffer_slices_are_256_byte_aligned_views():
+    """Every parameter's .grad is a view into the flat buffer starting on a 64-element (256-byte) boundary (the kernels
+    use 16-byte vector / TMA accesses on whole tensors); rebind() restores the views after set_to_none."""
+    from ratspn_b200.parallel import FlatGradAllReducer
+    ps = [torch.nn.Parameter(torch.randn(s)) for s in [(3, 5), (7,), (64,), (2, 2, 2)]]
+    red = FlatGradAllReducer(ps)
+    assert red.offsets == [0, 64, 128, 192] and red.numel == 256
+    base = red.flat.data_ptr()
+    for p, off in zip(ps, red.offsets):
+        assert p.grad.data_ptr() == base + 4 * off and p.grad.shape == p.shape
+    (ps[0].sum() * 2 + ps[3].sum()).backward()
+    assert float(red.flat[:15].sum()) == 30.0 and float(red.flat[192:200].sum()) == 8.0 and float(red.flat[15:192].abs().sum()) == 0.0
+    for p in ps:
+        p.grad = None
+    red.rebind()
+    assert all(p.grad.data_ptr() == base + 4 * off for p, off in zip(ps, red.offsets))
+    red.zero_()
+    assert float(red.flat.abs().sum()) == 0.0
