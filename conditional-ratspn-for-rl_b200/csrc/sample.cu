@@ -3,6 +3,7 @@
 // Reference semantics: layers.py:130-237, :442-511, distributions.py:248-302, :384-393, rat_spn.py:538-580
 // (SURVEY A.2).  Categorical draws are argmax(logits + Gumbel) with first-index tie break; the noise is either
 // supplied (bit-exact parity tests) or generated in-kernel with Philox keyed by the global element index.
+#include <stdlib.h>
 #include "common.cuh"
 
 struct SampleSumArgs {
@@ -103,6 +104,81 @@ __global__ void __launch_bounds__(256) sample_sum_kernel(SampleSumArgs a) {
     if (lane == 0 && live) a.out[item] = besti;
 }
 
+// Variant for layers sampled in every repetition (rep == null, Rs % 4 == 0, in-kernel noise, no MPE): one group of G lanes
+// serves FOUR repetitions of a (sample, scope) -- the noise elements (q, s, i, rs .. rs + 3) are consecutive, so one Philox
+// block yields all four (the same values spn_gumbel() gives one at a time), and the Philox rounds, which dominate the
+// instruction count of the scalar kernel, are paid once per four draws.
+template <int G>
+__global__ void __launch_bounds__(256) sample_sum_r4_kernel(SampleSumArgs a) {
+    const int lane = threadIdx.x & (G - 1);
+    const uint64_t seed_v = a.seed_dev ? *a.seed_dev : a.seed;
+    const int R4 = a.Rs >> 2;
+    const int64_t items = (int64_t)a.Q * a.d * R4;
+    int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool live = item < items;
+    if (!live) item = items - 1;
+    const int r0 = (int)(item % R4) * 4;
+    const int s = (int)((item / R4) % a.d);
+    const int64_t q = item / ((int64_t)R4 * a.d);
+    const int ws = a.Wsets == 1 ? 0 : (int)(q % a.w);
+    const float* lwp[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int o;
+        if (a.unravel) {
+            const int p = a.pa[q * a.sp_q + (int64_t)(s >> 1) * a.sp_s + (int64_t)(r0 + j) * a.sp_r];
+            o = (s & 1) ? p % a.oc : p / a.oc;
+        } else {
+            o = a.pa[q * a.sp_q + (int64_t)s * a.sp_s + (int64_t)(r0 + j) * a.sp_r];
+        }
+        lwp[j] = a.lw + (int64_t)ws * a.sw_w + (int64_t)s * a.sw_d + (int64_t)o * a.sw_o + (int64_t)(r0 + j) * a.sw_r;
+    }
+    const int64_t qe = a.xc ? q % a.Qe : 0;
+    const float* xl = nullptr;
+    const float* xr = nullptr;
+    if (a.xc) {
+        if (2 * s < a.xc_din) xl = a.xc + qe * a.sxc_b + (int64_t)(2 * s) * a.sxc_d;
+        if (2 * s + 1 < a.xc_din) xr = a.xc + qe * a.sxc_b + (int64_t)(2 * s + 1) * a.sxc_d;
+    }
+    const uint64_t stream_id = ((uint64_t)a.d << 40) ^ ((uint64_t)a.ic << 8) ^ (uint64_t)a.Rs;
+    const uint64_t base = ((((uint64_t)q + a.q_offset) * a.d + s) * (uint64_t)a.ic) * a.Rs + r0;   // multiple of 4
+    float best[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    int besti[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    for (int i = lane; i < a.ic; i += G) {
+        const uint4 rnd = spn_philox4x32((base + (uint64_t)i * a.Rs) >> 2, stream_id, seed_v);
+        const uint32_t bits[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+        int l = 0, rp = 0;
+        if (a.xc) { l = i / a.c; rp = i - l * a.c; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v = lwp[j][(int64_t)i * a.sw_i];
+            if (a.xc) {
+                if (xl) v += xl[(int64_t)l * a.sxc_c + (int64_t)(r0 + j) * a.sxc_r];
+                if (xr) v += xr[(int64_t)rp * a.sxc_c + (int64_t)(r0 + j) * a.sxc_r];
+            }
+            const float e = -__logf(spn_u01(bits[j]));
+            v -= __logf(fmaxf(e, 1e-30f));
+            if (v > best[j] || besti[j] == 0x7fffffff) { best[j] = v; besti[j] = i; }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int sh = G / 2; sh > 0; sh >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best[j], sh);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti[j], sh);
+            if (oi != 0x7fffffff && (besti[j] == 0x7fffffff || ov > best[j] || (ov == best[j] && oi < besti[j]))) {
+                best[j] = ov;
+                besti[j] = oi;
+            }
+        }
+    }
+    if (lane == 0 && live) {
+        int32_t* dst = a.out + (q * a.d + s) * (int64_t)a.Rs + r0;
+        dst[0] = besti[0]; dst[1] = besti[1]; dst[2] = besti[2]; dst[3] = besti[3];
+    }
+}
+
 struct SampleLeafArgs {
     const float* mu; const float* sigma;
     int Wsets, w, Q, F, I, R, card, Rs;
@@ -167,8 +243,19 @@ extern "C" int spn_sample_sum(const float* lw, int64_t sw_w, int64_t sw_d, int64
     a.root = root; a.ic_top = ic_top; a.gumbel = gumbel; a.mpe = mpe; a.seed = seed; a.q_offset = q_offset; a.seed_dev = seed_dev; a.out = out;
     int G = 4;
     while (G < 32 && G < ic) G <<= 1;
-    const unsigned blocks = spn_blocks((int64_t)Q * d * Rs * G, 256);
     cudaStream_t st = (cudaStream_t)stream;
+    if (!root && !rep && !mpe && !gumbel && Rs % 4 == 0 && !getenv("SPN_NO_R4")) {  // every repetition sampled, in-kernel noise:
+        // 4 repetitions per group (SPN_NO_R4: A/B switch of tests/test_gpu_sampling.py)
+        const unsigned blocks4 = spn_blocks((int64_t)Q * d * (Rs / 4) * G, 256);
+        switch (G) {
+            case 4: sample_sum_r4_kernel<4><<<blocks4, 256, 0, st>>>(a); break;
+            case 8: sample_sum_r4_kernel<8><<<blocks4, 256, 0, st>>>(a); break;
+            case 16: sample_sum_r4_kernel<16><<<blocks4, 256, 0, st>>>(a); break;
+            default: sample_sum_r4_kernel<32><<<blocks4, 256, 0, st>>>(a); break;
+        }
+        return spn_launch_status();
+    }
+    const unsigned blocks = spn_blocks((int64_t)Q * d * Rs * G, 256);
     switch (G) {
         case 4: sample_sum_kernel<4><<<blocks, 256, 0, st>>>(a); break;
         case 8: sample_sum_kernel<8><<<blocks, 256, 0, st>>>(a); break;
