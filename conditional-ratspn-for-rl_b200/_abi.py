@@ -120,7 +120,11 @@ def ptr(t):
 
 
 def stream_ptr(device=None):
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    p = _StreamPtr(torch.cuda.current_stream(device).cuda_stream)
+    if device is not None:
+        device = torch.device(device)
+        p.device_index = device.index if device.index is not None else torch.cuda.current_device()
+    return p
 
 
 def require_cuda(*tensors):
@@ -131,7 +135,21 @@ def require_cuda(*tensors):
                 f"{t.device}. Move the model and its inputs to a B200 ('cuda'); there is no CPU path.")
 
 
+class _StreamPtr(ctypes.c_void_p):
+    """cudaStream_t handle that remembers which device it belongs to (see ``call``)."""
+    device_index = None
+
+
 def call(name, *args):
+    """Invoke a kernel-launching entry point.  The ABI launches on the CURRENT device, so when the stream argument (last
+    argument of every launching entry point, built by ``stream_ptr(tensor.device)``) belongs to another device --
+    single-process multi-GPU use -- that device is made current around the call."""
     global LAUNCHES
     LAUNCHES += 1
+    st = args[-1] if args else None
+    idx = getattr(st, "device_index", None)
+    if idx is not None and idx != torch.cuda.current_device():
+        with torch.cuda.device(idx):
+            check(getattr(lib(), name)(*args), name)
+        return
     check(getattr(lib(), name)(*args), name)

@@ -240,12 +240,14 @@ extern "C" int spn_sample_sum(const float* lw, int64_t sw_w, int64_t sw_d, int64
     a.Wsets = Wsets; a.w = w; a.Q = Q; a.d = d; a.ic = ic; a.oc = oc; a.Rs = Rs;
     a.pa = pa; a.sp_q = sp_q; a.sp_s = sp_s; a.sp_r = sp_r; a.unravel = unravel; a.rep = rep;
     a.xc = xc; a.sxc_b = sxc_b; a.sxc_d = sxc_d; a.sxc_c = sxc_c; a.sxc_r = sxc_r; a.xc_din = xc_din; a.c = c; a.Qe = Qe;
+    const bool one_rep_per_group = (mpe & 2) != 0;   // bit 1 of `mpe`: A/B selector of the kernel variant (same indices)
+    mpe &= 1;
     a.root = root; a.ic_top = ic_top; a.gumbel = gumbel; a.mpe = mpe; a.seed = seed; a.q_offset = q_offset; a.seed_dev = seed_dev; a.out = out;
     int G = 4;
     while (G < 32 && G < ic) G <<= 1;
     cudaStream_t st = (cudaStream_t)stream;
-    if (!root && !rep && !mpe && !gumbel && Rs % 4 == 0 && !getenv("SPN_NO_R4")) {  // every repetition sampled, in-kernel noise:
-        // 4 repetitions per group (SPN_NO_R4: A/B switch of tests/test_gpu_sampling.py)
+    if (!root && !rep && !mpe && !gumbel && Rs % 4 == 0 && !one_rep_per_group) {  // every repetition sampled, in-kernel noise:
+        // 4 repetitions per group
         const unsigned blocks4 = spn_blocks((int64_t)Q * d * (Rs / 4) * G, 256);
         switch (G) {
             case 4: sample_sum_r4_kernel<4><<<blocks4, 256, 0, st>>>(a); break;

@@ -656,8 +656,8 @@ __global__ void __launch_bounds__(544, 1) opg_kernel(OpgArgs a) {
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (threadIdx.x == 0 && *abort_flag) atomicAdd(&g_tc2_aborts, 1);
     if (warp == 16) tmem_dealloc(tmem_base, 512);
+    if (threadIdx.x == 0) tc_abort_trap(abort_flag, &g_tc2_aborts);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -787,19 +787,42 @@ __global__ void __launch_bounds__(256) tc_wimage_t_kernel(const uint4* __restric
     img2[i] = img[sr * per_sr + srce];
 }
 
-// one zeroed work counter per launch, taken round-robin from a small ring (launches in flight never come near 256)
-__device__ unsigned int g_opg_counters[256];
-static unsigned int* opg_next_counter(cudaStream_t st) {
-    static std::atomic<unsigned int*> base{nullptr};   // forward and backward launch from different host threads
-    static std::atomic<unsigned int> next{0};
-    unsigned int* b = base.load();
+// One zeroed work counter per launch.  Eager launches take slots round-robin from a ring (launches in flight never come
+// near its size).  Launches recorded into a CUDA graph keep their slot for the life of the graph (the memset node re-zeroes
+// it on every replay), so they draw from a separate region that the eager ring never wraps onto; one ring per device.
+constexpr unsigned int TC_EAGER_SLOTS = 1024, TC_GRAPH_SLOTS = 3072;
+__device__ unsigned int g_tc_counters[TC_EAGER_SLOTS + TC_GRAPH_SLOTS];
+unsigned int* tc_next_counter(cudaStream_t st) {
+    constexpr int MAXDEV = 64;
+    static std::atomic<unsigned int*> base[MAXDEV];     // forward and backward launch from different host threads
+    static std::atomic<unsigned int> next_eager[MAXDEV], next_graph[MAXDEV];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return nullptr;
+    unsigned int* b = base[dev].load();
     if (!b) {
-        if (cudaGetSymbolAddress((void**)&b, g_opg_counters) != cudaSuccess) return nullptr;
-        base.store(b);
+        if (cudaGetSymbolAddress((void**)&b, g_tc_counters) != cudaSuccess) return nullptr;
+        base[dev].store(b);
     }
-    unsigned int* c = b + (next.fetch_add(1) & 255u);
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) return nullptr;
+    unsigned int* c;
+    if (cs == cudaStreamCaptureStatusActive) {
+        const unsigned int i = next_graph[dev].fetch_add(1);
+        if (i >= TC_GRAPH_SLOTS) return nullptr;          // > 3072 tensor-core launches captured in this process
+        c = b + TC_EAGER_SLOTS + i;
+    } else {
+        c = b + (next_eager[dev].fetch_add(1) % TC_EAGER_SLOTS);
+    }
     if (cudaMemsetAsync(c, 0, sizeof(unsigned int), st) != cudaSuccess) return nullptr;
     return c;
+}
+
+// cudaFuncSetAttribute is per device: remember which devices a kernel has been configured on
+bool tc_configured_on_device(std::atomic<unsigned long long>& mask, int* dev_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *dev_out = dev;
+    return dev < 64 && ((mask.load() >> dev) & 1ull);
 }
 
 template <int C, int MODE>
@@ -807,18 +830,17 @@ static int launch_opg(const OpgArgs& a, cudaStream_t st) {
     constexpr int W_BYTES = C * C * C * 2;
     constexpr int SMEM = W_BYTES + 1024 + 2 * 2 * (C / 2) * 128 * 4 + (MODE == OPG_FWD ? 2 * 128 * C * 4 : 2 * (C / 2) * 128 * 4) +
                          2 * 2 * 128 * 4 + (2 * 4 + 12) * 8 + 16;
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0, sms = 148;
+    if (!tc_configured_on_device(configured, &dev)) {
         cudaError_t e = cudaFuncSetAttribute(opg_kernel<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return spn_cuda_status(e);
-        configured = true;
+        if (dev < 64) configured.fetch_or(1ull << dev);
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int nitems = a.d_out * a.R * a.nsplit;
     OpgArgs b = a;
-    b.counter = opg_next_counter(st);
+    b.counter = tc_next_counter(st);
     if (!b.counter) return SPN_ERR_ARG;
     opg_kernel<C, MODE><<<nitems < sms ? nitems : sms, 544, SMEM, st>>>(b);
     return spn_launch_status();
@@ -839,13 +861,15 @@ static void opg_split(OpgArgs& a, int B, int d_out, int R) {
     int nsplit = (8 * 148 + d_out * R - 1) / (d_out * R);
     if (nsplit > a.ntiles / 4) nsplit = a.ntiles / 4;
     if (nsplit < 1) nsplit = 1;
-    const char* ns = getenv("SPN_TC_NSPLIT");  // tuning experiments
+#ifdef SPN_TC_DEBUGSW   // tuning experiments: only in builds with the experiment switches
+    const char* ns = getenv("SPN_TC_NSPLIT");
     if (ns && atoi(ns) > 0 && atoi(ns) <= a.ntiles) nsplit = atoi(ns);
-    a.nsplit = nsplit;
     const char* dbg = getenv("SPN_TC_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;
     const char* dn = getenv("SPN_TC_N");
     a.dbg_n = dn ? atoi(dn) : 0;
+#endif
+    a.nsplit = nsplit;
 }
 
 extern "C" int spn_sum_tc_supported(int c, int oc, int R) {

@@ -248,8 +248,8 @@ __global__ void __launch_bounds__(320, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (threadIdx.x == 0 && *abort_flag) atomicAdd(&g_tc_bwd_aborts, 1);
     if (warp == 9) tmem_dealloc(tmem_base, 512);
+    if (threadIdx.x == 0) tc_abort_trap(abort_flag, &g_tc_bwd_aborts);
 }
 
 // csum[s][o][r] = sum over rows b with out > -inf of g[s][r][b][o].  For normalised weights lw = param - logz the
@@ -370,37 +370,25 @@ __global__ void __launch_bounds__(256) tc_dw_finish_vec_kernel(const float* __re
 
 extern "C" int spn_sum_tc_supported(int c, int oc, int R);
 
-__device__ unsigned int g_bwd_counters[256];
-static unsigned int* bwd_next_counter(cudaStream_t st) {
-    static std::atomic<unsigned int*> base{nullptr};   // forward and backward launch from different host threads
-    static std::atomic<unsigned int> next{0};
-    unsigned int* b = base.load();
-    if (!b) {
-        if (cudaGetSymbolAddress((void**)&b, g_bwd_counters) != cudaSuccess) return nullptr;
-        base.store(b);
-    }
-    unsigned int* c = b + (next.fetch_add(1) & 255u);
-    if (cudaMemsetAsync(c, 0, sizeof(unsigned int), st) != cudaSuccess) return nullptr;
-    return c;
-}
+unsigned int* tc_next_counter(cudaStream_t st);                                             // sum_tc2.cu
+bool tc_configured_on_device(std::atomic<unsigned long long>& mask, int* dev_out);          // sum_tc2.cu
 
 template <int C, int OC, int NPAD, int GC>
 static int launch_bwd_w(const TcBwdArgs& a, cudaStream_t st) {
     constexpr int NCHUNK = ((C / 8) * (C / 8) + 1) / 2;
     constexpr int NGROUPS = (NCHUNK + GC - 1) / GC;
     constexpr int SMEM = 4 * 128 * 128 * 2 + 2 * ((C / 2) * 512 + 1024) + 2 * 2 * (C / 2) * 512 + (2 * 4 + 7) * 8 + 16;
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0, sms = 148;
+    if (!tc_configured_on_device(configured, &dev)) {
         cudaError_t e = cudaFuncSetAttribute(sum_tc_bwd_w_kernel<C, OC, NPAD, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return spn_cuda_status(e);
-        configured = true;
+        if (dev < 64) configured.fetch_or(1ull << dev);
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int nitems = a.d_out * a.R * NGROUPS;
     TcBwdArgs b = a;
-    b.counter = bwd_next_counter(st);
+    b.counter = tc_next_counter(st);
     if (!b.counter) return SPN_ERR_ARG;
     sum_tc_bwd_w_kernel<C, OC, NPAD, GC><<<nitems < sms ? nitems : sms, 320, SMEM, st>>>(b, NGROUPS);
     return spn_launch_status();
@@ -415,10 +403,12 @@ extern "C" int spn_sum_tc_bwd_w(const void* fhand, const void* hand, const float
     a.fhand = (const uint8_t*)fhand; a.hand = (const uint8_t*)hand; a.dwt = dwt_workspace;
     a.B = B; a.d_in = d_in; a.d_out = d_out; a.R = R;
     a.ntiles = (B + 127) / 128;
+#ifdef SPN_TC_DEBUGSW
     {
         const char* dbg = getenv("SPN_TC_DEBUG");
         a.debug = dbg ? atoi(dbg) : 0;
     }
+#endif
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (c == 40) rc = launch_bwd_w<40, 40, 48, 7>(a, st);

@@ -75,6 +75,17 @@ __device__ __forceinline__ void mbar_wait_sticky(uint64_t* bar, uint32_t parity,
         : "memory");
 }
 
+// Teardown check of the tensor-core kernels: a CTA whose abort flag is up (timed-out wait, or a TMEM allocation that did
+// not start at column 0) kills the launch.  __trap() makes the error sticky for the context, so training cannot go on
+// with wrong log-likelihoods or gradients.
+__device__ __forceinline__ void tc_abort_trap(volatile int* abort_flag, int* counter) {
+    if (*abort_flag) {
+        atomicAdd(counter, 1);
+        __threadfence_system();
+        __trap();
+    }
+}
+
 // Non-blocking probe of an mbarrier phase, returned as a warp-uniform value (lane 0's result, broadcast by a shuffle so
 // that the compiler knows a branch on it is not divergent).  Used to learn EARLY -- before a long blocking instruction
 // sequence -- that the next hand-off has already happened, so that its ~90-clk try_wait latency is not paid in series.

@@ -4,12 +4,24 @@ Each ``torch.autograd.Function`` here is a forward/backward kernel pair; PyTorch
 current stream and the autograd tape.  All tensors must live on a CUDA device -- there is no other backend.
 """
 import math
-import os
 
 import torch
 
 from . import _abi
 from ._abi import call, ptr, require_cuda, stream_ptr
+
+
+# Test hook (tests/test_gpu_ps.py): route per-conditional Sum layers through the general kernels instead of the streaming ones.
+FORCE_GENERAL_SUM = False
+
+# Bumped by everything that writes parameters behind autograd's version counters (parallel.FlatAdam.step,
+# parallel.broadcast_parameters): part of the key of every derived-buffer cache (bf16 operand images, int32 permutations).
+PARAM_EPOCH = 0
+
+
+def bump_param_epoch():
+    global PARAM_EPOCH
+    PARAM_EPOCH += 1
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -177,7 +189,7 @@ class SumFn(torch.autograd.Function):
         out = torch.empty(out_shape, device=x.device, dtype=torch.float32)
         Wsets, w, B, d_out, ic, oc, R, _ = ints
         if (mode == "xsum" and layout == "ref" and Wsets == w and w > 1 and d_out <= 65535 and ic * oc * R * 4 >= 16384
-                and not os.environ.get("SPN_NO_PS")  # A/B switch for tests: force the general kernels
+                and not FORCE_GENERAL_SUM  # A/B switch of the tests: force the general kernels
                 and _abi.lib().spn_sum_ps_supported(c, oc, R)):
             # per-conditional weights, big enough slabs: TMA-staged HBM-streaming kernel
             call("spn_sum_ps_fwd", ptr(x), sx[0], sx[1], d_in, c, ptr(lw), w, B, d_out, oc, R, ptr(out), stream_ptr(x.device))
@@ -381,9 +393,10 @@ def sampling_weights(lw: torch.Tensor) -> torch.Tensor:
 
 
 def sample_sum(lw, root, Q, d, Rs, pa, pa_strides, unravel, rep, xc, Qe, gumbel, mpe, seed=0, q_offset=0,
-               transposed=False):
+               transposed=False, one_rep_per_group=False):
     """One Sum layer of the top-down pass (include/spn_b200.h: spn_sample_sum).  Returns int32 [Q, d, Rs].
-    ``transposed``: ``lw`` comes from sampling_weights() ([W, d, R, oc, ic])."""
+    ``transposed``: ``lw`` comes from sampling_weights() ([W, d, R, oc, ic]).  ``one_rep_per_group``: kernel-variant
+    selector (bit 1 of the ABI's ``mpe`` flags): same indices, one repetition per lane group instead of four."""
     require_cuda(lw, pa, rep, xc, gumbel)
     lw = _f32c(lw)
     Wsets = lw.shape[0]
@@ -572,7 +585,7 @@ def tc_prepare_cached(w: torch.Tensor, raw: bool, cache):
     """(wimg, logz) for ``w``; re-used from ``cache`` while the tensor (storage, version) is unchanged."""
     if torch.cuda.is_current_stream_capturing():
         cache = None  # a captured graph must rebuild the image on every replay (the weights change between replays)
-    key = (w.data_ptr(), w._version, tuple(w.shape), bool(raw))
+    key = (w.data_ptr(), w._version, tuple(w.shape), bool(raw), PARAM_EPOCH)
     if cache is not None and cache.get("key") == key:
         return cache["wimg"], cache["logz"]
     res = tc_prepare(w, raw)

@@ -50,7 +50,8 @@ class FlatGradAllReducer:
         self._handles = []
         for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-        if overlap and self._distributed():
+        if overlap:
+            # registered unconditionally: the process group may be initialised after this object is built
             for p in self.params:
                 p.register_post_accumulate_grad_hook(self._hook)
 
@@ -59,7 +60,7 @@ class FlatGradAllReducer:
         return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
     def _hook(self, p: torch.nn.Parameter):
-        if p.grad is None:
+        if p.grad is None or not self._distributed():
             return
         if self.average:
             p.grad.mul_(1.0 / dist.get_world_size())
@@ -81,11 +82,12 @@ class FlatGradAllReducer:
     def all_reduce(self, async_op: bool = False):
         if not self._distributed():
             return None
-        if self.overlap:
+        if self.overlap and self._handles:
             for h in self._handles:
                 h.wait()
             self._handles.clear()
             return None
+        # no per-parameter collectives were queued (overlap off, or the hooks did not fire): one flat all-reduce
         if self.average:
             self.flat.mul_(1.0 / dist.get_world_size())
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
@@ -96,9 +98,11 @@ class FlatAdam:
     (``spn_adam_step``): the parameters are re-homed as views into one flat fp32 buffer next to the reducer's flat
     gradient buffer, so the update of the whole model is a single 28-byte-per-parameter HBM stream.
 
-    ``module``: the model whose tensor-core operand-image caches must be invalidated after every step (the kernel
-    writes the parameters behind autograd's version counters).  The step count (bias correction) lives on the host, so a
-    step must not be captured into a CUDA graph; use ``torch.optim.Adam(capturable=True)`` there."""
+    The kernel writes the parameters behind autograd's version counters, so every step bumps ``ops.PARAM_EPOCH``, which
+    is part of the key of all derived-buffer caches (bf16 operand images of the tensor-core path, int32 permutations):
+    the next forward rebuilds them.  ``module`` is accepted for backward compatibility and additionally frees the stale
+    images eagerly.  The step count (bias correction) lives on the host, so a step must not be captured into a CUDA
+    graph; use ``torch.optim.Adam(capturable=True)`` there."""
 
     def __init__(self, reducer: FlatGradAllReducer, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  module: torch.nn.Module = None):
@@ -122,6 +126,8 @@ class FlatAdam:
         _abi.call("spn_adam_step", _abi.ptr(self.flat_p), _abi.ptr(self.reducer.flat), _abi.ptr(self.exp_avg),
                   _abi.ptr(self.exp_avg_sq), self.flat_p.numel(), self.lr / bc1, b1, b2, self.eps, 1.0 / bc2 ** 0.5,
                   _abi.stream_ptr(self.flat_p.device))
+        from . import ops
+        ops.bump_param_epoch()
         for m in self._cached:
             m.invalidate_weight_cache()
 
@@ -132,6 +138,10 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0):
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src)
-    for m in module.modules():  # .data writes bypass the version counter the operand-image cache is keyed on
+    from . import ops
+    ops.bump_param_epoch()  # .data writes bypass the version counters the derived-buffer caches are keyed on
+    for m in module.modules():
         if hasattr(m, "invalidate_weight_cache"):
             m.invalidate_weight_cache()
+        if hasattr(m, "_perm_cache"):
+            m._perm_cache = None

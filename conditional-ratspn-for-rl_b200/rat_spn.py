@@ -142,7 +142,7 @@ class RatSpn(nn.Module):
     def _perm32(self) -> Tuple[th.Tensor, th.Tensor]:
         """int32 device copies of (permutation, inv_permutation) for the kernels, refreshed when the buffers change."""
         key = (self.permutation.data_ptr(), self.permutation._version, self.inv_permutation.data_ptr(),
-               self.inv_permutation._version)
+               self.inv_permutation._version, ops.PARAM_EPOCH)
         if self._perm_cache is None or self._perm_cache[0] != key:
             self._perm_cache = (key, self.permutation.data.to(th.int32).contiguous(),
                                 self.inv_permutation.data.to(th.int32).contiguous())
@@ -285,13 +285,23 @@ class RatSpn(nn.Module):
         return h
 
     def _forward_layerwise(self, x, layer_index, x_needs_permutation, detach_params):
-        """Unfused evaluation (one module after the other); only used when dropout is active in training mode."""
+        """Unfused evaluation (one module after the other); only used when dropout is active in training mode.  With the
+        evidence cache enabled the Sum layers also receive the CrossProduct *input* their own input derives from
+        (``_input_cache_fused``), which is what the sampling kernels reweight with -- like the reference
+        (layers.py:102-103, :189-203) this is the activation before dropout is applied."""
         if x_needs_permutation:
             x = self.apply_permutation(x)
         h = self._leaf(x, detach_params=detach_params)
+        below_product = h
         for layer in self._inner_layers[:layer_index]:
+            if isinstance(layer, CrossProduct):
+                below_product = h
+            elif layer._is_input_cache_enabled:
+                layer._input_cache_fused = below_product.detach()
             h = layer(h, detach_params=detach_params)
         if layer_index == self.max_layer_index:
+            if self.root._is_input_cache_enabled:
+                self.root._input_cache_fused = below_product.detach()
             h = h.transpose(-1, -2).flatten(-2, -1).unsqueeze(-1)
             h = self.root(h, detach_params=detach_params)
         return h

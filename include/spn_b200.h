@@ -165,6 +165,8 @@ int spn_xprod_bwd(const float* g, int B, int d_in, int c, int R, float* dx, void
  *   xc      NULL, or activations of the layer below from a forward pass on the evidence [Qe, xc_din, c, R] via
  *           strides; the posterior logit offset is xc[qe, 2s, l, r] + xc[qe, 2s+1, r', r], qe = q % Qe
  *   root    1: this is the root Sum over R*ic_top channels (d = 1, Rs = 1); the repetition is i / ic_top
+ *   mpe     flags: bit 0 = MPE (argmax, no noise); bit 1 = kernel-variant selector (one repetition per lane group
+ *           instead of four when every repetition is sampled with in-kernel noise; same indices, used for A/B tests)
  *   gumbel  [Q, d, ic, Rs] contiguous noise, or NULL with mpe = 1 (argmax) or mpe = 0 (in-kernel Philox, keyed by
  *           seed and the global element index q_offset-shifted so results do not depend on the GPU count);
  *           seed_dev != NULL: the seed is read from device memory instead (one uint64), so that a captured CUDA

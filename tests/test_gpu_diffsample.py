@@ -72,9 +72,10 @@ def _grads(m, extra=()):
 
 def _run(m, composite, monkeypatch, cw_seed=0, **kw):
     from ratspn_b200 import diffsample
+    from tests.composite_onehot import sample_onehot_composite
     if composite:
         def wrapped(spn, ctx, class_index, evidence, layer_index, noise, fuse_post=False):
-            return diffsample.sample_onehot_composite(spn, ctx, class_index, evidence, layer_index, noise), False
+            return sample_onehot_composite(spn, ctx, class_index, evidence, layer_index, noise), False
         monkeypatch.setattr(diffsample, "sample_onehot", wrapped)
     else:
         monkeypatch.undo()

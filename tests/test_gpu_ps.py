@@ -113,10 +113,8 @@ def test_cspn_model_streaming_paths_match_general_kernels(n, monkeypatch):
     x[0, 1, ::5] = float("nan")
     res = []
     for general in (False, True):
-        if general:
-            monkeypatch.setenv("SPN_NO_PS", "1")
-        else:
-            monkeypatch.delenv("SPN_NO_PS", raising=False)
+        from ratspn_b200 import ops
+        monkeypatch.setattr(ops, "FORCE_GENERAL_SUM", general)
         m.zero_grad(set_to_none=True)
         ll = m(x, condition=cond)
         (-ll.mean()).backward()

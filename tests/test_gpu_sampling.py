@@ -72,7 +72,7 @@ def test_in_kernel_noise_four_per_philox_block_is_unbiased_and_deterministic():
 @pytest.mark.parametrize("Rs,ic,with_xc", [(4, 16, False), (8, 64, True), (4, 9, True)])
 def test_four_repetitions_per_group_variant_draws_the_same_indices(Rs, ic, with_xc, monkeypatch):
     """Layers sampled in every repetition with in-kernel noise (entropy path, R % 4 == 0) use one Philox block for four
-    repetitions; indices must equal those of the one-repetition-per-group kernel (SPN_NO_R4=1) for the same seed."""
+    repetitions; indices must equal those of the one-repetition-per-group kernel (``one_rep_per_group=True``) for the same seed."""
     from ratspn_b200 import ops
     g = torch.Generator().manual_seed(Rs * 100 + ic)
     c = int(round(ic ** 0.5))
@@ -81,9 +81,7 @@ def test_four_repetitions_per_group_variant_draws_the_same_indices(Rs, ic, with_
     pa = torch.randint(0, oc * oc, (Q, d // 2, Rs), generator=g).to(torch.int32).to(DEV)
     xc = torch.randn(Q, 2 * d, c, Rs, generator=g).to(DEV) if with_xc else None
     args = (lw, 0, Q, d, Rs, pa, (d // 2 * Rs, Rs, 1), True, None, xc, Q, None, False)
-    monkeypatch.delenv("SPN_NO_R4", raising=False)
     a = ops.sample_sum(*args, seed=4242, q_offset=17)
-    monkeypatch.setenv("SPN_NO_R4", "1")
-    b = ops.sample_sum(*args, seed=4242, q_offset=17)
+    b = ops.sample_sum(*args, seed=4242, q_offset=17, one_rep_per_group=True)
     assert a.shape == (Q, d, Rs) and torch.equal(a, b)
     assert int(a.min()) >= 0 and int(a.max()) < ic and a.float().std() > 0
