@@ -17,6 +17,7 @@ class Case:
         self.F, self.D, self.R, self.S, self.I, self.C, tanh = m[:7]
         self.tanh = bool(tanh)
         self.F_cond = m[7] if len(m) > 7 else None
+        self.hidden = m[8] if len(m) > 8 else 8   # width of the CSPN's feat / sum / dist hidden layers
         self.arch = O.Arch(F=self.F, D=self.D, R=self.R, S=self.S, I=self.I, C=self.C, tanh_squash=self.tanh)
 
     def t(self, key):
@@ -37,7 +38,7 @@ class Case:
 
 
 LEAF_KWARGS = {"ratspn_small": {}, "ratspn_cfg1": {}, "ratspn_pad_tanh": {"min_sigma": 0.001, "max_sigma": 1.0},
-               "cspn_small": {"min_sigma": 0.001, "max_sigma": 1.0}}
+               "cspn_small": {"min_sigma": 0.001, "max_sigma": 1.0}, "cspn_cfg3": {"min_sigma": 0.001, "max_sigma": 1.0}}
 
 
 def oracle_params(case: Case, requires_grad=False, dtype=torch.float32):
@@ -72,9 +73,9 @@ def build_cspn(case: Case, device):
     cfg = rb.CspnConfig()
     cfg.F_cond = (case.F_cond,)
     cfg.C = case.C
-    cfg.feat_layers = [8]
-    cfg.sum_param_layers = [8]
-    cfg.dist_param_layers = [8]
+    cfg.feat_layers = [case.hidden]
+    cfg.sum_param_layers = [case.hidden]
+    cfg.dist_param_layers = [case.hidden]
     cfg.F, cfg.R, cfg.D, cfg.I, cfg.S = case.F, case.R, case.D, case.I, case.S
     cfg.dropout = 0.0
     cfg.leaf_base_class = rb.RatNormal

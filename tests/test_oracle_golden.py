@@ -150,6 +150,35 @@ def test_cspn_sac_update_pattern():
         assert_close(t.grad, g[k], 1e-3, 1e-6, f"sac grad {k}")
 
 
+def test_cspn_at_baseline_config3_shape():
+    """BASELINE config 3 at its real shape (obs 376 / 17 actions, R = I = S = 3, D = 4, [64] hidden; fixture recorded
+    from the unmodified reference by oracle/gen_golden_cfg3.py): LL + gradients, rollout sampling with evidence (incl.
+    MPE), and the policy-update pattern (onehot sample + recursive entropy with the failed-joint mask, one backward)."""
+    c = Case("cspn_cfg3")
+    P, raw = _cspn_params(c, True)
+    out = O.forward(P, c.arch, c.t("x"))
+    assert_close(out, c.t("ll"), RT, AT)
+    (-out.mean()).backward()
+    g = c.grads("ll__grad__")
+    for k, t in raw.items():
+        assert_close(t.grad, g[k], 1e-4, 1e-7, f"ll grad {k}")
+    P0, _ = _cspn_params(c, False)
+    for tag, mpe in (("ixev", False), ("ixevmpe", True)):
+        o = O.sample_index(P0, c.arch, O.NoiseSource(replay=c.noise(tag)), n=1, evidence=c.t("evidence"), is_mpe=mpe)
+        assert_close(o.sample, c.t(f"{tag}__sample"), 1e-6, 1e-6, tag)
+    P, raw = _cspn_params(c, True)
+    ns = O.NoiseSource(replay=c.noise("sac"))
+    s = O.sample_onehot(P, c.arch, ns, n=1, evidence=c.t("evidence"))
+    H = O.recursive_entropy(P, c.arch, ns, sample_size=5, marginal_mask=c.t("failed"), differentiable=True)
+    assert_close(s.sample, c.t("sac__sample"), 1e-6, 1e-6)
+    assert_close(H, c.t("sac__H"), 1e-5, 1e-5)
+    (-(0.1 * H + s.sample.squeeze(0).squeeze(0).squeeze(-1).sum(-1)).mean()).backward()
+    g = c.grads("sac__grad__")
+    for k, t in raw.items():
+        scale = float(g[k].abs().max())
+        assert_close(t.grad, g[k], 0.0, 1e-4 * scale + 1e-9, f"sac grad {k}")
+
+
 def test_structural_invariants():
     c = Case("ratspn_small")
     P, _ = oracle_params(c)

@@ -1,7 +1,7 @@
 """Secondary measurements for the BASELINE.json configs other than the headline one (cfg 1, 3, 4, 5).
 
-Not the driver's bench (that is bench.py, cfg 2): this script records absolute numbers for the other call patterns of the
-hot path on one B200 and writes them as JSON (default: gpurun_out/configs.json).  CUDA-event timing, 3 warm-ups.
+bench.py runs ``CONFIGS`` at N = 1 and reports them under ``extra`` next to the CPU oracle port timed in the same run;
+run stand-alone, this script writes the GPU numbers as JSON (default: gpurun_out/configs.json).  CUDA-event timing, 3 warm-ups.
 """
 import json
 import os
@@ -51,7 +51,7 @@ def cfg1():
         (-m(x).mean()).backward()
     ms, launches = timed(step, reps=20)
     return {"config": "cfg1 RatSpn F=784 D=3 R=5 S=I=10 B=256 fwd+bwd", "ms": ms, "samples_per_s": 256 / ms * 1e3,
-            "abi_calls_per_step": launches, "reference_cpu_ms (SURVEY 6, 8 cores)": 320.0}
+            "abi_calls_per_step": launches}
 
 
 def cfg3():
@@ -118,7 +118,6 @@ def cfg3():
                       "entropy (n=5, mask) fwd+bwd, LL fwd+bwd", "us_per_update": ms * 1e3, "us_per_update_cuda_graph": ms_g * 1e3,
             "rollout_index_sample_with_evidence_B1_us_cuda_graph": ms_gr * 1e3, "abi_calls_per_update": launches,
             "rollout_index_sample_with_evidence_B1_us": ms_r * 1e3, "abi_calls_per_rollout": launches_r,
-            "reference_cpu_ms (SURVEY 6, 8 cores)": 2700.0,
             "note": "latency bound: 1467 circuit parameters per conditional; roofline fractions are meaningless here"}
 
 
@@ -133,7 +132,6 @@ def cfg4():
             out[tag] = {"ms": ms, "samples_per_s": n / ms * 1e3, "output_GB_per_s": n * 784 * 4 / ms / 1e6,
                         "abi_calls": launches}
     out["config"] = "cfg4 RatSpn F=784 D=5 R=40 S=I=40 ancestral sampling, 65536 samples"
-    out["reference_cpu_samples_per_s (SURVEY 6, n=64)"] = 90.0
     return out
 
 
@@ -267,12 +265,14 @@ def cfg5_narrow_train_raw(w=512):
     return res
 
 
+CONFIGS = (("cfg1", cfg1), ("cfg3", cfg3), ("cfg4", cfg4), ("cfg5_narrow", cfg5_narrow),
+           ("cfg5_narrow_train", cfg5_narrow_train), ("cfg5_narrow_train_raw", cfg5_narrow_train_raw))
+
+
 def main():
     out_path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "configs.json")
     res = {"device": torch.cuda.get_device_name(0), "lib": _abi.version()}
-    for name, fn in (("cfg1", cfg1), ("cfg3", cfg3), ("cfg4", cfg4), ("cfg5_narrow", cfg5_narrow),
-                     ("cfg5_narrow_train", cfg5_narrow_train),
-                     ("cfg5_narrow_train_raw", cfg5_narrow_train_raw)):
+    for name, fn in CONFIGS:
         t0 = time.time()
         try:
             res[name] = fn()
