@@ -579,7 +579,7 @@ def main():
             out1 = ops.tc_sum_forward(h0, wimg, w1, logz, fhand)
             g1 = torch.randn_like(out1) / B
             t_fwd = time_alone(lambda: ops.tc_sum_forward(h0, wimg, w1, logz, fhand))
-            hand = ops.tc_hand_buffer(h0, out1)
+            hand = ops.tc_hand_buffer(h0, w1)
             t_bx = time_alone(lambda: ops.tc_sum_backward_x(h0, out1, g1, wimg, w1, fhand, hand))
             t_bw = time_alone(lambda: ops.tc_sum_backward_w(fhand, hand, h0, out1, g1, w1, logz))
             t_prep = time_alone(lambda: ops.tc_prepare(w1, True))

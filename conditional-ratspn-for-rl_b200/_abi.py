@@ -52,13 +52,15 @@ SIGNATURES = {
     "spn_sample_sum": [_P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _I, _P, _P, _L, _L, _L, _L,
                        _I, _I, _I, _I, _I, _P, _I, _U, _U, _P, _P, _P],
     "spn_sum_tc_supported": [_I, _I, _I],
+    "spn_sum_tc_padded_channels": [_I, _I],
     "spn_sum_tc_image_bytes": [_I, _I, _I, _I],
     "spn_sum_tc_prepare": [_P, _I, _I, _I, _I, _P, _P, _P],
-    "spn_sum_tc_fhand_bytes": [_I, _I, _I, _I],
-    "spn_sum_tc_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
-    "spn_sum_tc_hand_bytes": [_I, _I, _I, _I],
-    "spn_sum_tc_bwd_x": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
-    "spn_sum_tc_bwd_w": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "spn_sum_tc_fhand_bytes": [_I, _I, _I, _I, _I],
+    "spn_sum_tc_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "spn_sum_tc_hand_bytes": [_I, _I, _I, _I, _I],
+    "spn_sum_tc_dw_workspace_floats": [_I, _I, _I, _I],
+    "spn_sum_tc_bwd_x": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "spn_sum_tc_bwd_w": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     "spn_debug_tc_aborts": [_P],
     "spn_debug_tc_prof": [_P, _I],
     "spn_root_shared_supported": [_I, _I, _I],
@@ -72,7 +74,8 @@ SIGNATURES = {
                             _I, _P, _I, _P, _P, _P, _P, _P],
 }
 
-_RETURNS_INT64 = {"spn_leaf_workspace_floats", "spn_sum_tc_image_bytes", "spn_sum_tc_hand_bytes", "spn_sum_tc_fhand_bytes"}
+_RETURNS_INT64 = {"spn_leaf_workspace_floats", "spn_sum_tc_image_bytes", "spn_sum_tc_hand_bytes", "spn_sum_tc_fhand_bytes",
+                  "spn_sum_tc_dw_workspace_floats"}
 
 _lib = None
 LAUNCHES = 0  # number of kernel-launching ABI calls made by this process (bench.py reports it)

@@ -31,6 +31,8 @@ def build(force=False, verbose=False):
     extra = ["-DSPN_TC_PROFILE"] if os.environ.get("SPN_TC_PROFILE") else []  # per-phase clock64 hooks (perturbs timing)
     if os.environ.get("SPN_TC_DEBUGSW"):
         extra.append("-DSPN_TC_DEBUGSW")  # SPN_TC_DEBUG / SPN_TC_N experiment switches inside the tensor-core kernels
+    if os.environ.get("SPN_MBAR_HINT_NS"):
+        extra.append("-DSPN_MBAR_HINT_NS=" + os.environ["SPN_MBAR_HINT_NS"])  # experiment: suspend hint of the mbarrier waits
     cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:

@@ -1,5 +1,5 @@
-// dW of the shared-weight CrossProduct+Sum layer on the tensor cores (tcgen05 + TMEM); see sum_tc2.cu for the forward
-// and dX formulation.  With E[b,k] = eL[b,l] eR[b,r'] (k = l*c + r'), W = exp(log-weights) and
+// dW of the CrossProduct+Sum layer with weights shared by many rows, on the tensor cores (tcgen05 + TMEM); see sum_tc3.cu
+// for the forward and dX formulation.  With E[b,k] = eL[b,l] eR[b,r'] (k = l*c + r'), W = exp(log-weights) and
 // G[b,o] = g[b,o] * exp(mL + mR - out[b,o])  (= g / linear-domain sum), SURVEY A.5 gives
 //
 //   dWlin[k,o] = sum_b E[b,k] G[b,o]         (M = k-chunk of 128, N = o, K = rows)   -> spn_sum_tc_bwd_w
@@ -22,10 +22,10 @@ __device__ int g_tc_bwd_aborts = 0;
 
 struct TcBwdArgs {
     unsigned int* counter;   // work counter of this launch (dynamic item scheduling), zeroed by the host
-    const uint8_t* fhand; // per (s, r, row tile): packed eL, eR ([pair][128 rows] words) + shifts, written by the forward kernel
-    const uint8_t* hand;  // per (s, r, row tile): G tile (B-operand layout), written by the dX kernel
-    float* dwt;           // [d_out][R][K][OC] linear-domain weight gradient
-    int B, d_in, d_out, R;
+    const uint8_t* fhand; // per (set, s, r, row tile): packed eL, eR ([pair][128 rows] words) + shifts, written by the forward kernel
+    const uint8_t* hand;  // per (set, s, r, row tile): G tile (B-operand layout), written by the dX kernel
+    float* dwt;           // [nsd][R][P*P][P] linear-domain weight gradient (padded channel counts)
+    int B, d_in, d_out, R;   // B = rows per weight set, d_out = weight sets x scopes (the hand-off index does not separate them)
     int ntiles, debug;    // debug (SPN_TC_DEBUG, timing experiments only): 1 no MMA issue, 3 generators idle
 };
 
@@ -67,7 +67,7 @@ __device__ __forceinline__ void dw_issue_chunk(uint32_t dcol, uint64_t adesc, ui
 //               item they run the epilogue (TMEM -> linear-domain weight gradient).
 //   warp 8      TMA: streams the hand-off tiles (double buffered).
 //   warp 9      MMA issuer.
-template <int C, int OC, int NPAD, int GC>
+template <int C, int OC, int NPAD, int GC, int NSTA>
 __global__ void __launch_bounds__(320, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int ngroups) {
     constexpr int K = C * C;
     constexpr int CB = C / 8;                  // 8-channel blocks per child = o-groups of the G tile
@@ -77,8 +77,7 @@ __global__ void __launch_bounds__(320, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
     constexpr int A_BYTES = 128 * 128 * 2;     // [16 row-groups][16 m-groups][8][8] bf16
     constexpr int V_BYTES = NPAIR * 512;       // one hand-off tile: eL / eR as [pair][128 rows] words, G as [16][CB][8][8] bf16
     constexpr int G_BYTES = V_BYTES + 1024;    // + aliased N-group overrun (N = NPAD > OC reads one block past the tile)
-    constexpr int NSTA = 4;                    // A ring depth
-    static_assert(GC * NPAD <= 512 && OC == C, "unsupported shape");
+    static_assert(GC * NPAD <= 512 && OC == C && NSTA >= 2 && NSTA <= 4, "unsupported shape");   // NSTA: A ring depth
     constexpr uint32_t IDESC = instr_desc_bf16(128, NPAD, 1, 1);
 
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -252,22 +251,27 @@ __global__ void __launch_bounds__(320, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
     if (threadIdx.x == 0) tc_abort_trap(abort_flag, &g_tc_bwd_aborts);
 }
 
-// csum[s][o][r] = sum over rows b with out > -inf of g[s][r][b][o].  For normalised weights lw = param - logz the
-// softmax backward needs sum_k d(lw)[k,o] = sum_b g[b,o] * sum_k pi[b,k,o] = sum_b g[b,o]  (pi sums to one over k), so this
-// column sum of the upstream gradient replaces a second pass over the weight gradient.
+// csum[sg][o][r] = sum over the rows b of weight set `set` with out > -inf of g[s][r][b][o]  (sg = set * d_out + s).  For
+// normalised weights lw = param - logz the softmax backward needs sum_k d(lw)[k,o] = sum_b g[b,o] * sum_k pi[b,k,o] =
+// sum_b g[b,o]  (pi sums to one over k), so this column sum of the upstream gradient replaces a second pass over the weight
+// gradient.  Activations: [d_out][R][Btot = nsets * Bs][OC], rows of one set contiguous.
 __global__ void __launch_bounds__(256) tc_gsum_kernel(const float* __restrict__ out, const float* __restrict__ g,
-                                                     float* __restrict__ csum, int B, int OC, int R, int rows_per_block) {
+                                                     float* __restrict__ csum, int Bs, int Btot, int d_out, int OC, int R,
+                                                     int rows_per_block) {
     __shared__ float4 part[256];
-    const int sr = blockIdx.x;  // s * R + r
+    const int sgr = blockIdx.x;  // (set * d_out + s) * R + r
+    const int r = sgr % R, sg = sgr / R;
+    const int set = sg / d_out, s = sg % d_out;
     const int quads = OC / 4;                   // float4 per row (OC % 4 == 0 on the tensor-core path)
     const int rpi = 256 / quads;                // rows per iteration
     const int q = threadIdx.x % quads, slot = threadIdx.x / quads;
     const int64_t b0 = (int64_t)blockIdx.y * rows_per_block;
-    const int64_t b1 = min((int64_t)B, b0 + rows_per_block);
+    const int64_t b1 = min((int64_t)Bs, b0 + rows_per_block);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (slot < rpi) {
-        const float4* op = reinterpret_cast<const float4*>(out + (int64_t)sr * B * OC) + q;
-        const float4* gp = reinterpret_cast<const float4*>(g + (int64_t)sr * B * OC) + q;
+        const int64_t base = (((int64_t)s * R + r) * Btot + (int64_t)set * Bs) * OC;
+        const float4* op = reinterpret_cast<const float4*>(out + base) + q;
+        const float4* gp = reinterpret_cast<const float4*>(g + base) + q;
 #pragma unroll 4
         for (int64_t b = b0 + slot; b < b1; b += rpi) {
             const float4 ov = __ldg(op + b * quads), gv = __ldg(gp + b * quads);
@@ -285,8 +289,7 @@ __global__ void __launch_bounds__(256) tc_gsum_kernel(const float* __restrict__ 
             const float4 u = part[j * quads + threadIdx.x];
             t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
         }
-        const int s = sr / R, r = sr % R;
-        float* dst = csum + ((int64_t)s * OC + 4 * threadIdx.x) * R + r;
+        float* dst = csum + ((int64_t)sg * OC + 4 * threadIdx.x) * R + r;
         atomicAdd(dst, t.x);
         atomicAdd(dst + R, t.y);
         atomicAdd(dst + 2 * R, t.z);
@@ -294,25 +297,29 @@ __global__ void __launch_bounds__(256) tc_gsum_kernel(const float* __restrict__ 
     }
 }
 
-// Layout-restoring epilogue of dW: dwt[s][r][k][o] (linear-domain gradient) -> gradient w.r.t. the stored tensor, in the
-// parameter layout [1][s][k][o][r]:
+// Layout-restoring epilogue of dW: dwt[sg][r][k' = l*P + r'][P] (linear-domain gradient, padded channel counts) -> gradient
+// w.r.t. the stored tensor, in the parameter layout [sg][k = l*c + r'][o][r]:
 //   logz == NULL: lw holds log-weights;           dlw[k,o]    = exp(lw) * dwt
 //   logz != NULL: lw holds unnormalised params p; dparam[k,o] = softmax(p)[k,o] * (dwt[k,o] - csum[o])   (layers.py:85)
-// One block per (s, tile of KT k); tiles go through shared memory so both sides stay coalesced.
+// One block per (sg, tile of KT = 4 consecutive k, which share their left channel since c % 4 == 0); tiles go through shared
+// memory so both sides stay coalesced.
 __global__ void __launch_bounds__(256) tc_dw_finish_kernel(const float* __restrict__ lw, const float* __restrict__ logz,
                                                           const float* __restrict__ csum, const float* __restrict__ dwt,
-                                                          float* __restrict__ dlw, int d, int K, int OC, int R) {
+                                                          float* __restrict__ dlw, int c, int OC, int R, int P) {
     extern __shared__ float tile[];  // [R][KT*OC + 1]
     constexpr int KT = 4;
+    const int K = c * c;
     const int kt = blockIdx.x % (K / KT);
     const int s = blockIdx.x / (K / KT);
+    const int k0 = kt * KT;
+    const int64_t kp0 = (int64_t)(k0 / c) * P + k0 % c;   // padded index of the tile's first k
     const int n = KT * OC;
     for (int i = threadIdx.x; i < R * n; i += blockDim.x) {
         const int r = i / n, e = i % n;
-        tile[r * (n + 1) + e] = dwt[(((int64_t)s * R + r) * K + (int64_t)kt * KT) * OC + e];
+        tile[r * (n + 1) + e] = dwt[(((int64_t)s * R + r) * P * P + kp0 + e / OC) * P + e % OC];
     }
     __syncthreads();
-    const int64_t base = ((int64_t)s * K + (int64_t)kt * KT) * OC * R;
+    const int64_t base = ((int64_t)s * K + k0) * OC * R;
     const int ocr = OC * R;
     for (int i = threadIdx.x; i < n * R; i += blockDim.x) {
         const int e = i / R, r = i % R;
@@ -326,29 +333,33 @@ __global__ void __launch_bounds__(256) tc_dw_finish_kernel(const float* __restri
     }
 }
 
-// Same, vectorised for R % 4 == 0 and OC % 4 == 0: float4 on both sides (dwt rows of KT*OC floats; parameter rows with r
-// innermost), index arithmetic once per four values.
+// Same, vectorised for R % 4 == 0 (OC % 4 == 0 always holds here): float4 on both sides (dwt rows of OC floats; parameter
+// rows with r innermost), index arithmetic once per four values.
 __global__ void __launch_bounds__(256) tc_dw_finish_vec_kernel(const float* __restrict__ lw, const float* __restrict__ logz,
                                                               const float* __restrict__ csum, const float* __restrict__ dwt,
-                                                              float* __restrict__ dlw, int d, int K, int OC, int R) {
+                                                              float* __restrict__ dlw, int c, int OC, int R, int P) {
     extern __shared__ float tile[];  // [R][KT*OC + 1]
     constexpr int KT = 4;
+    const int K = c * c;
     const int kt = blockIdx.x % (K / KT);
     const int s = blockIdx.x / (K / KT);
-    const int n = KT * OC, n4 = n / 4;
+    const int k0 = kt * KT;
+    const int64_t kp0 = (int64_t)(k0 / c) * P + k0 % c;
+    const int n = KT * OC, n4 = n / 4, oc4 = OC / 4;
     {
         const int rows_per_pass = blockDim.x / n4;
         const int rr = threadIdx.x / n4, e4 = threadIdx.x - rr * n4;
         if (rr < rows_per_pass) {
+            const int kk = e4 / oc4, o4 = e4 - kk * oc4;
             for (int r = rr; r < R; r += rows_per_pass) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(dwt + (((int64_t)s * R + r) * K + (int64_t)kt * KT) * OC) + e4);
+                const float4 v = __ldg(reinterpret_cast<const float4*>(dwt + (((int64_t)s * R + r) * P * P + kp0 + kk) * P) + o4);
                 float* t = tile + r * (n + 1) + 4 * e4;
                 t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
             }
         }
     }
     __syncthreads();
-    const int64_t base = ((int64_t)s * K + (int64_t)kt * KT) * OC * R;
+    const int64_t base = ((int64_t)s * K + k0) * OC * R;
     const int ocr = OC * R, R4 = R / 4;
     const float4* lw4 = reinterpret_cast<const float4*>(lw + base);
     float4* out4 = reinterpret_cast<float4*>(dlw + base);
@@ -360,28 +371,29 @@ __global__ void __launch_bounds__(256) tc_dw_finish_vec_kernel(const float* __re
         if (logz) {
             const int zc = s * ocr + (e % OC) * R + r;
             const float4 z = __ldg(reinterpret_cast<const float4*>(logz + zc));
-            const float4 c = __ldg(reinterpret_cast<const float4*>(csum + zc));
+            const float4 cs = __ldg(reinterpret_cast<const float4*>(csum + zc));
             w.x -= z.x; w.y -= z.y; w.z -= z.z; w.w -= z.w;
-            dv.x -= c.x; dv.y -= c.y; dv.z -= c.z; dv.w -= c.w;
+            dv.x -= cs.x; dv.y -= cs.y; dv.z -= cs.z; dv.w -= cs.w;
         }
         out4[i4] = make_float4(__expf(w.x) * dv.x, __expf(w.y) * dv.y, __expf(w.z) * dv.z, __expf(w.w) * dv.w);
     }
 }
 
 extern "C" int spn_sum_tc_supported(int c, int oc, int R);
+extern "C" int spn_sum_tc_padded_channels(int c, int oc);
+unsigned int* tc_next_counter(cudaStream_t st);                                             // sum_tc3.cu
+bool tc_configured_on_device(std::atomic<unsigned long long>& mask, int* dev_out);          // sum_tc3.cu
 
-unsigned int* tc_next_counter(cudaStream_t st);                                             // sum_tc2.cu
-bool tc_configured_on_device(std::atomic<unsigned long long>& mask, int* dev_out);          // sum_tc2.cu
-
-template <int C, int OC, int NPAD, int GC>
+template <int C, int OC, int NPAD, int GC, int NSTA>
 static int launch_bwd_w(const TcBwdArgs& a, cudaStream_t st) {
     constexpr int NCHUNK = ((C / 8) * (C / 8) + 1) / 2;
     constexpr int NGROUPS = (NCHUNK + GC - 1) / GC;
-    constexpr int SMEM = 4 * 128 * 128 * 2 + 2 * ((C / 2) * 512 + 1024) + 2 * 2 * (C / 2) * 512 + (2 * 4 + 7) * 8 + 16;
+    constexpr int SMEM = NSTA * 128 * 128 * 2 + 2 * ((C / 2) * 512 + 1024) + 2 * 2 * (C / 2) * 512 + (2 * 4 + 7) * 8 + 16;
+    static_assert(SMEM <= 232448, "shared memory budget");
     static std::atomic<unsigned long long> configured{0};
     int dev = 0, sms = 148;
     if (!tc_configured_on_device(configured, &dev)) {
-        cudaError_t e = cudaFuncSetAttribute(sum_tc_bwd_w_kernel<C, OC, NPAD, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaError_t e = cudaFuncSetAttribute(sum_tc_bwd_w_kernel<C, OC, NPAD, GC, NSTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return spn_cuda_status(e);
         if (dev < 64) configured.fetch_or(1ull << dev);
     }
@@ -390,19 +402,28 @@ static int launch_bwd_w(const TcBwdArgs& a, cudaStream_t st) {
     TcBwdArgs b = a;
     b.counter = tc_next_counter(st);
     if (!b.counter) return SPN_ERR_ARG;
-    sum_tc_bwd_w_kernel<C, OC, NPAD, GC><<<nitems < sms ? nitems : sms, 320, SMEM, st>>>(b, NGROUPS);
+    sum_tc_bwd_w_kernel<C, OC, NPAD, GC, NSTA><<<nitems < sms ? nitems : sms, 320, SMEM, st>>>(b, NGROUPS);
     return spn_launch_status();
 }
 
+// dwt workspace (floats): padded linear-domain gradient + the column sums of the fused softmax backward
+extern "C" int64_t spn_sum_tc_dw_workspace_floats(int nsd, int c, int oc, int R) {
+    const int64_t P = spn_sum_tc_padded_channels(c, oc);
+    return (int64_t)nsd * R * P * P * P + (int64_t)nsd * oc * R;
+}
+
 extern "C" int spn_sum_tc_bwd_w(const void* fhand, const void* hand, const float* out, const float* g, const float* lw, const float* logz,
-                                int B, int d_in, int d_out, int c, int oc, int R, float* dwt_workspace, float* dlw,
-                                void* stream) {
-    if (!fhand || !hand || !out || !g || !lw || !dwt_workspace || !dlw || B <= 0 || d_in <= 0 || d_in > 2 * d_out) return SPN_ERR_ARG;
+                                int Bs, int nsets, int d_in, int d_out, int c, int oc, int R, float* dwt_workspace, int csum_ready,
+                                float* dlw, void* stream) {
+    if (!fhand || !hand || !out || !g || !lw || !dwt_workspace || !dlw || Bs <= 0 || nsets <= 0 || d_in <= 0 || d_in > 2 * d_out)
+        return SPN_ERR_ARG;
     if (!spn_sum_tc_supported(c, oc, R)) return SPN_ERR_UNSUPPORTED;
+    const int P = spn_sum_tc_padded_channels(c, oc);
+    const int nsd = nsets * d_out;
     TcBwdArgs a{};
     a.fhand = (const uint8_t*)fhand; a.hand = (const uint8_t*)hand; a.dwt = dwt_workspace;
-    a.B = B; a.d_in = d_in; a.d_out = d_out; a.R = R;
-    a.ntiles = (B + 127) / 128;
+    a.B = Bs; a.d_in = d_in; a.d_out = nsd; a.R = R;
+    a.ntiles = (Bs + 127) / 128;
 #ifdef SPN_TC_DEBUGSW
     {
         const char* dbg = getenv("SPN_TC_DEBUG");
@@ -411,29 +432,44 @@ extern "C" int spn_sum_tc_bwd_w(const void* fhand, const void* hand, const float
 #endif
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if (c == 40) rc = launch_bwd_w<40, 40, 48, 7>(a, st);
-    else if (c == 32) rc = launch_bwd_w<32, 32, 32, 8>(a, st);
-    else if (c == 16) rc = launch_bwd_w<16, 16, 16, 2>(a, st);
-    else return SPN_ERR_UNSUPPORTED;
+    switch (P) {   // <P, P, N = P padded to 16, chunks per item (GC * N <= 512 TMEM columns), A ring depth>
+        case 8: rc = launch_bwd_w<8, 8, 16, 1, 4>(a, st); break;
+        case 16: rc = launch_bwd_w<16, 16, 16, 2, 4>(a, st); break;
+        case 24: rc = launch_bwd_w<24, 24, 32, 5, 4>(a, st); break;
+        case 32: rc = launch_bwd_w<32, 32, 32, 8, 4>(a, st); break;
+        case 40: rc = launch_bwd_w<40, 40, 48, 7, 4>(a, st); break;
+        case 48: rc = launch_bwd_w<48, 48, 48, 9, 4>(a, st); break;
+        case 56: rc = launch_bwd_w<56, 56, 64, 7, 3>(a, st); break;
+        case 64: rc = launch_bwd_w<64, 64, 64, 8, 3>(a, st); break;
+        default: return SPN_ERR_UNSUPPORTED;
+    }
     if (rc != SPN_OK) return rc;
     const int K = c * c;
     float* csum = nullptr;
     if (logz) {
         // the column sums live behind the linear-domain gradient in the caller's workspace
-        csum = dwt_workspace + (size_t)d_out * R * K * oc;
-        cudaError_t e = cudaMemsetAsync(csum, 0, (size_t)d_out * oc * R * sizeof(float), st);
-        if (e != cudaSuccess) return spn_cuda_status(e);
-        const int rows_per_block = 512;
-        dim3 grid(d_out * R, (B + rows_per_block - 1) / rows_per_block);
-        tc_gsum_kernel<<<grid, 256, 0, st>>>(out, g, csum, B, oc, R, rows_per_block);
-        rc = spn_launch_status();
-        if (rc != SPN_OK) return rc;
+        csum = dwt_workspace + (size_t)nsd * R * P * P * P;
+        if (!csum_ready) {   // not already produced by the G pre-pass of spn_sum_tc_bwd_x
+            cudaError_t e = cudaMemsetAsync(csum, 0, (size_t)nsd * oc * R * sizeof(float), st);
+            if (e != cudaSuccess) return spn_cuda_status(e);
+            const int rows_per_block = 512;
+            dim3 grid(nsd * R, (Bs + rows_per_block - 1) / rows_per_block);
+            tc_gsum_kernel<<<grid, 256, 0, st>>>(out, g, csum, Bs, Bs * nsets, d_out, oc, R, rows_per_block);
+            rc = spn_launch_status();
+            if (rc != SPN_OK) return rc;
+        }
     }
     const size_t smem = (size_t)R * (4 * oc + 1) * sizeof(float);
-    if (R % 4 == 0 && oc % 4 == 0 && oc <= 256)
-        tc_dw_finish_vec_kernel<<<d_out * (K / 4), 256, smem, st>>>(lw, logz, csum, dwt_workspace, dlw, d_out, K, oc, R);
+    if (smem > 200 * 1024) return SPN_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(tc_dw_finish_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_dw_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return spn_cuda_status(e);
+    }
+    if (R % 4 == 0)
+        tc_dw_finish_vec_kernel<<<nsd * (K / 4), 256, smem, st>>>(lw, logz, csum, dwt_workspace, dlw, c, oc, R, P);
     else
-        tc_dw_finish_kernel<<<d_out * (K / 4), 256, smem, st>>>(lw, logz, csum, dwt_workspace, dlw, d_out, K, oc, R);
+        tc_dw_finish_kernel<<<nsd * (K / 4), 256, smem, st>>>(lw, logz, csum, dwt_workspace, dlw, c, oc, R, P);
     return spn_launch_status();
 }
 

@@ -6,6 +6,12 @@
 
 #include "common.cuh"
 
+// suspend-time hint of mbarrier.try_wait (ns) and the number of tries before a wait gives up (~2 s in total)
+#ifndef SPN_MBAR_HINT_NS
+#define SPN_MBAR_HINT_NS 100000
+#endif
+#define SPN_MBAR_TRIES (2000000000ull / (SPN_MBAR_HINT_NS > 1000 ? SPN_MBAR_HINT_NS : 1000))
+
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -54,6 +60,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
 // instructions, ~56 clk).  A timeout (protocol bug; ~2 s) raises the CTA-wide abort flag in shared memory; from then on
 // every wait falls through at once, the kernel drains with garbage results and the host sees the abort count.
 __device__ __forceinline__ void mbar_wait_sticky(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
+#if SPN_MBAR_HINT_NS > 0
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -71,8 +78,35 @@ __device__ __forceinline__ void mbar_wait_sticky(uint64_t* bar, uint32_t parity,
         "st.volatile.shared.u32 [%3], 1;\n\t"
         "LAB_DONE:\n\t"
         "}" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(100000u), "r"(smem_u32((const void*)abort_flag)), "r"(20000u)
+        "r"(parity), "r"((uint32_t)SPN_MBAR_HINT_NS), "r"(smem_u32((const void*)abort_flag)), "r"((uint32_t)SPN_MBAR_TRIES)
         : "memory");
+#else
+    // No suspend-time hint: with a hint ptxas follows a failed TRYWAIT by NANOSLEEP.SYNCS, whose wake-up granularity is far
+    // coarser than the hand-off latencies of these pipelines.  The plain try_wait still parks the warp for the hardware's own
+    // (short) window, so the loop does not flood the issue slots; the abort flag is polled every 64 rounds.
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 cnt, flg, low;\n\t"
+        "mov.u32 cnt, 0;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LAB_DONE;\n\t"
+        "add.u32 cnt, cnt, 1;\n\t"
+        "and.b32 low, cnt, 63;\n\t"
+        "setp.ne.u32 p, low, 0;\n\t"
+        "@p bra LAB_WAIT;\n\t"
+        "ld.volatile.shared.u32 flg, [%2];\n\t"
+        "setp.ne.u32 p, flg, 0;\n\t"
+        "@p bra LAB_DONE;\n\t"
+        "setp.lt.u32 p, cnt, %3;\n\t"
+        "@p bra LAB_WAIT;\n\t"
+        "st.volatile.shared.u32 [%2], 1;\n\t"
+        "LAB_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(smem_u32((const void*)abort_flag)), "r"(1u << 26)
+        : "memory");
+#endif
 }
 
 // Teardown check of the tensor-core kernels: a CTA whose abort flag is up (timed-out wait, or a TMEM allocation that did
@@ -189,15 +223,21 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
         "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
-// store NCOLS (multiple of 8, <= 64) consecutive columns
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3])
+                 : "memory");
+}
+// store NCOLS (multiple of 4, <= 64) consecutive columns
 template <int NCOLS>
 __device__ __forceinline__ void tmem_store_cols(uint32_t taddr, const uint32_t* r) {
-    static_assert(NCOLS % 8 == 0 && NCOLS <= 64, "unsupported column count");
+    static_assert(NCOLS % 4 == 0 && NCOLS <= 64, "unsupported column count");
     int done = 0;
     if constexpr (NCOLS >= 32) { tmem_st32(taddr, r); done = 32; }
     if constexpr (NCOLS >= 64) { tmem_st32(taddr + 32, r + 32); done = 64; }
     if constexpr ((NCOLS % 32) >= 16) { tmem_st16(taddr + done, r + done); done += 16; }
     if constexpr ((NCOLS % 16) >= 8) { tmem_st8(taddr + done, r + done); done += 8; }
+    if constexpr ((NCOLS % 8) >= 4) { tmem_st4(taddr + done, r + done); done += 4; }
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -213,6 +253,63 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr)
                  : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+// load NCOLS (even, <= 32) consecutive columns of this thread's TMEM lane (asynchronous: tmem_wait_ld before use)
+template <int NCOLS>
+__device__ __forceinline__ void tmem_load_cols(uint32_t taddr, uint32_t* r) {
+    static_assert(NCOLS % 2 == 0 && NCOLS <= 32, "unsupported column count");
+    int done = 0;
+    if constexpr (NCOLS == 32) { tmem_ld32(taddr, r); done = 32; }
+    if constexpr (NCOLS < 32 && NCOLS >= 16) { tmem_ld16(taddr, r); done = 16; }
+    if constexpr (NCOLS < 32 && (NCOLS % 16) >= 8) { tmem_ld8(taddr + done, r + done); done += 8; }
+    if constexpr (NCOLS < 32 && (NCOLS % 8) >= 4) { tmem_ld4(taddr + done, r + done); done += 4; }
+    if constexpr (NCOLS < 32 && (NCOLS % 4) >= 2) { tmem_ld2(taddr + done, r + done); done += 2; }
+}
+
+// ------------------------------------------------------------------------------------------------ packed fp32 (FFMA2)
+// Blackwell issues two fp32 FMAs per lane and instruction on 64-bit register pairs (fma.rn.f32x2); a scalar operand is
+// expressed as a pair with both halves equal, which ptxas turns into the broadcast form of FFMA2.
+__device__ __forceinline__ uint64_t f2pack(float lo, float hi) {
+    uint64_t v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+__device__ __forceinline__ uint64_t u2pack(uint32_t lo, uint32_t hi) {
+    uint64_t v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi));
+    return v;
+}
+__device__ __forceinline__ void f2unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
 }
 
 // ------------------------------------------------------------------------------------------------ descriptors

@@ -266,7 +266,8 @@ def sum_forward_raw(x, raw):
 
 
 class SumTcFn(torch.autograd.Function):
-    """Shared-weight fused CrossProduct + Sum on the tensor cores; activations in the internal [d, R, B, c] layout.
+    """Fused CrossProduct + Sum on the tensor cores for weights shared by many rows; activations in the internal
+    [d, R, rows, c] layout with the rows of one weight set contiguous (``w.shape[0]`` sets of equal size).
 
     ``raw = False``: ``w`` holds log-weights.  ``raw = True``: ``w`` is the unnormalised parameter tensor and the
     ``F.log_softmax(dim=2)`` of layers.py:85 (forward and backward) is fused into the operand-image / dW-epilogue
@@ -287,16 +288,17 @@ class SumTcFn(torch.autograd.Function):
     def backward(ctx, g):
         x, w, out, wimg, logz, fhand = ctx.saved_tensors
         logz = logz if ctx.raw else None
-        fhand = fhand if ctx.has_fhand else None
         g = _f32c(g)
         # forward -> dX -> dW hand-offs: the dX kernel takes exp(x - max) from the forward and passes G on to the dW
         # kernel, which recomputes nothing
         need_dw = ctx.needs_input_grad[1]
-        if need_dw and fhand is None:
-            raise RuntimeError("the weight gradient needs the forward's hand-off buffer (forward ran without grad inputs)")
-        hand = tc_hand_buffer(x, out) if need_dw else None
-        dx = tc_sum_backward_x(x, out, g, wimg, w, fhand, hand) if (ctx.needs_input_grad[0] or need_dw) else None
-        dw = tc_sum_backward_w(fhand, hand, x, out, g, w, logz) if need_dw else None
+        if not ctx.has_fhand:
+            raise RuntimeError("the backward kernels need the forward's hand-off buffer (forward ran without grad inputs)")
+        hand = tc_hand_buffer(x, w)
+        work = tc_dw_workspace(x, w) if need_dw else None
+        csum = tc_csum_view(work, x, w) if (need_dw and logz is not None) else None   # filled by the G pre-pass of dX
+        dx = tc_sum_backward_x(x, out, g, wimg, w, fhand, hand, csum)
+        dw = tc_sum_backward_w(fhand, hand, x, out, g, w, logz, work, csum is not None) if need_dw else None
         return (dx if ctx.needs_input_grad[0] else None), dw, None, None
 
 
@@ -563,26 +565,38 @@ def launches() -> int:
 # Tensor-core path (shared weights, internal activation layout [scope][repetition][batch][channel])
 # --------------------------------------------------------------------------------------------------------------
 def tc_supported(c: int, oc: int, R: int) -> bool:
+    """Channel counts the tensor-core kernels take: c (per child) and oc multiples of 4, at most 64."""
     return bool(_abi.lib().spn_sum_tc_supported(int(c), int(oc), int(R)))
 
 
+def _tc_dims(x, w):
+    """(nsets, Bs, d_in, d_out, c, oc, R) of an internal-layout activation x [d_in, R, nsets*Bs, c] and weights
+    w [nsets, d_out, c*c, oc, R]."""
+    d_in, R, Btot, c = x.shape
+    nsets, d_out, ic, oc, Rw = w.shape
+    assert ic == c * c and Rw == R and _pow2_ceil(d_in) == 2 * d_out and Btot % nsets == 0, \
+        f"input {tuple(x.shape)} does not fit weights {tuple(w.shape)}"
+    return nsets, Btot // nsets, d_in, d_out, c, oc, R
+
+
 def tc_prepare(w: torch.Tensor, raw: bool = False):
-    """fp32 weights [1, d, c*c, oc, R] -> bf16 exp() operand image for spn_sum_tc_fwd (uint8 buffer).
-    raw = False: ``w`` are log-weights, returns the image.  raw = True: ``w`` are unnormalised parameters, returns
-    (image of softmax(w), logz [d, oc, R])."""
+    """fp32 weights [nsets, d, c*c, oc, R] -> bf16 exp() operand images for the tensor-core kernels (uint8 buffer).
+    raw = False: ``w`` are log-weights, returns the images.  raw = True: ``w`` are unnormalised parameters, returns
+    (images of softmax(w), logz [nsets*d, oc, R])."""
     require_cuda(w)
     w = _f32c(w)
-    _, d, ic, oc, R = w.shape
+    nsets, d, ic, oc, R = w.shape
     c = int(round(math.sqrt(ic)))
     assert c * c == ic
-    wimg = torch.empty(_abi.lib().spn_sum_tc_image_bytes(d, c, oc, R), device=w.device, dtype=torch.uint8)
-    logz = torch.empty(d, oc, R, device=w.device, dtype=torch.float32) if raw else None
-    call("spn_sum_tc_prepare", ptr(w), d, c, oc, R, ptr(logz), ptr(wimg), stream_ptr(w.device))
+    nsd = nsets * d
+    wimg = torch.empty(_abi.lib().spn_sum_tc_image_bytes(nsd, c, oc, R), device=w.device, dtype=torch.uint8)
+    logz = torch.empty(nsd, oc, R, device=w.device, dtype=torch.float32) if raw else None
+    call("spn_sum_tc_prepare", ptr(w), nsd, c, oc, R, ptr(logz), ptr(wimg), stream_ptr(w.device))
     return (wimg, logz) if raw else wimg
 
 
 def tc_prepare_cached(w: torch.Tensor, raw: bool, cache):
-    """(wimg, logz) for ``w``; re-used from ``cache`` while the tensor (storage, version) is unchanged."""
+    """(wimg, logz) for ``w``; re-used from ``cache`` while the tensor (storage, version, parameter epoch) is unchanged."""
     if torch.cuda.is_current_stream_capturing():
         cache = None  # a captured graph must rebuild the image on every replay (the weights change between replays)
     key = (w.data_ptr(), w._version, tuple(w.shape), bool(raw), PARAM_EPOCH)
@@ -595,58 +609,70 @@ def tc_prepare_cached(w: torch.Tensor, raw: bool, cache):
     return wimg, logz
 
 
-def tc_fhand_buffer(x, lw):
+def tc_fhand_buffer(x, w):
     """Scratch through which tc_sum_forward hands exp(x - max) (packed bf16) and the row shifts to the backward kernels."""
-    d_in, R, B, c = x.shape
-    return torch.empty(_abi.lib().spn_sum_tc_fhand_bytes(B, lw.shape[1], c, R), device=x.device, dtype=torch.uint8)
+    nsets, Bs, d_in, d_out, c, oc, R = _tc_dims(x, w)
+    return torch.empty(_abi.lib().spn_sum_tc_fhand_bytes(Bs, nsets * d_out, c, oc, R), device=x.device, dtype=torch.uint8)
 
 
 def tc_sum_forward(x: torch.Tensor, wimg: torch.Tensor, lw: torch.Tensor, logz: torch.Tensor = None,
                    fhand: torch.Tensor = None) -> torch.Tensor:
-    """x [d_in, R, B, c] -> out [d_out, R, B, oc] (fused CrossProduct + Sum on tcgen05)."""
+    """x [d_in, R, nsets*Bs, c] -> out [d_out, R, nsets*Bs, oc] (fused CrossProduct + Sum on tcgen05)."""
     require_cuda(x, wimg, lw, logz, fhand)
     x, lw = _f32c(x), _f32c(lw)
-    d_in, R, B, c = x.shape
-    _, d_out, ic, oc, Rw = lw.shape
-    assert ic == c * c and Rw == R and _pow2_ceil(d_in) == 2 * d_out
-    out = torch.empty(d_out, R, B, oc, device=x.device, dtype=torch.float32)
-    call("spn_sum_tc_fwd", ptr(x), ptr(wimg), ptr(lw), ptr(logz), B, d_in, d_out, c, oc, R, ptr(out), ptr(fhand),
+    nsets, Bs, d_in, d_out, c, oc, R = _tc_dims(x, lw)
+    out = torch.empty(d_out, R, nsets * Bs, oc, device=x.device, dtype=torch.float32)
+    call("spn_sum_tc_fwd", ptr(x), ptr(wimg), ptr(lw), ptr(logz), Bs, nsets, d_in, d_out, c, oc, R, ptr(out), ptr(fhand),
          stream_ptr(x.device))
     return out
 
 
-def tc_hand_buffer(x, out):
+def tc_hand_buffer(x, w):
     """Scratch through which tc_sum_backward_x hands the packed G tiles to tc_sum_backward_w."""
-    d_in, R, B, c = x.shape
-    return torch.empty(_abi.lib().spn_sum_tc_hand_bytes(B, out.shape[0], c, R), device=x.device, dtype=torch.uint8)
+    nsets, Bs, d_in, d_out, c, oc, R = _tc_dims(x, w)
+    return torch.empty(_abi.lib().spn_sum_tc_hand_bytes(Bs, nsets * d_out, c, oc, R), device=x.device, dtype=torch.uint8)
 
 
-def tc_sum_backward_x(x, out, g, wimg, lw, fhand=None, hand=None):
-    """dL/dx of tc_sum_forward, [d_in, R, B, c]: two forward-shaped tensor-core GEMMs (one per child).  ``fhand``: the
-    forward's hand-off (optional; without it exp(x - max) is recomputed); ``hand`` (tc_hand_buffer) receives the packed
-    G tiles that tc_sum_backward_w consumes."""
-    require_cuda(x, out, g, wimg, fhand, hand)
+def tc_dw_workspace(x, lw):
+    """Scratch of tc_sum_backward_w: padded linear-domain gradient followed by the column sums of the softmax backward."""
+    nsets, Bs, d_in, d_out, c, oc, R = _tc_dims(x, lw)
+    return torch.empty(_abi.lib().spn_sum_tc_dw_workspace_floats(nsets * d_out, c, oc, R), device=x.device, dtype=torch.float32)
+
+
+def tc_csum_view(work, x, lw):
+    nsets, Bs, d_in, d_out, c, oc, R = _tc_dims(x, lw)
+    n = nsets * d_out * oc * R
+    return work[work.numel() - n:]
+
+
+def tc_sum_backward_x(x, out, g, wimg, lw, fhand, hand=None, csum=None):
+    """dL/dx of tc_sum_forward, [d_in, R, rows, c]: dE = G W^T as one small-K tensor-core GEMM per row tile, contracted with
+    the children's exp vectors out of tensor memory.  ``fhand``: the forward's hand-off (required); ``hand``
+    (tc_hand_buffer) receives the packed G tiles (written by a pre-pass, read by this kernel and by tc_sum_backward_w);
+    ``csum`` (tc_csum_view of the dW workspace) receives the column sums of g for the fused softmax backward."""
+    require_cuda(x, out, g, wimg, fhand, hand, csum)
     x, out, g = _f32c(x), _f32c(out), _f32c(g)
-    d_in, R, B, c = x.shape
-    d_out, oc = out.shape[0], out.shape[3]
+    nsets, Bs, d_in, d_out, c, oc, R = _tc_dims(x, lw)
+    if hand is None:
+        hand = tc_hand_buffer(x, lw)
     dx = torch.empty_like(x)
-    call("spn_sum_tc_bwd_x", ptr(x), ptr(out), ptr(g), ptr(wimg), ptr(fhand), B, d_in, d_out, c, oc, R, ptr(dx), ptr(hand),
-         stream_ptr(x.device))
+    call("spn_sum_tc_bwd_x", ptr(x), ptr(out), ptr(g), ptr(wimg), ptr(fhand), Bs, nsets, d_in, d_out, c, oc, R, ptr(dx),
+         ptr(hand), ptr(csum), stream_ptr(x.device))
     return dx
 
 
-def tc_sum_backward_w(fhand, hand, x, out, g, lw, logz=None):
-    """Gradient of tc_sum_forward w.r.t. the weight tensor it was given, [1, d_out, c*c, oc, R] (tensor-core GEMM over
-    the batch) from the hand-off buffers filled by tc_sum_forward(..., fhand) and tc_sum_backward_x(..., hand); with
-    ``logz`` the tensor is the unnormalised parameter and the softmax backward is fused."""
+def tc_sum_backward_w(fhand, hand, x, out, g, lw, logz=None, work=None, csum_ready=False):
+    """Gradient of tc_sum_forward w.r.t. the weight tensor it was given, [nsets, d_out, c*c, oc, R] (tensor-core GEMM over
+    the rows of each set) from the hand-off buffers filled by tc_sum_forward(..., fhand) and tc_sum_backward_x(..., hand);
+    with ``logz`` the tensor is the unnormalised parameter and the softmax backward is fused."""
     require_cuda(fhand, hand, x, out, g, lw, logz)
     out, g, lw = _f32c(out), _f32c(g), _f32c(lw)
-    d_in, R, B, c = x.shape
-    d_out, oc = out.shape[0], out.shape[3]
-    work = torch.empty(d_out * R * (c * c + 1) * oc, device=x.device, dtype=torch.float32)
+    nsets, Bs, d_in, d_out, c, oc, R = _tc_dims(x, lw)
+    if work is None:
+        work = tc_dw_workspace(x, lw)
     dlw = torch.empty_like(lw)
-    call("spn_sum_tc_bwd_w", ptr(fhand), ptr(hand), ptr(out), ptr(g), ptr(lw), ptr(logz), B, d_in, d_out, c, oc, R, ptr(work),
-         ptr(dlw), stream_ptr(x.device))
+    call("spn_sum_tc_bwd_w", ptr(fhand), ptr(hand), ptr(out), ptr(g), ptr(lw), ptr(logz), Bs, nsets, d_in, d_out, c, oc, R,
+         ptr(work), int(bool(csum_ready)), ptr(dlw), stream_ptr(x.device))
     return dlw
 
 

@@ -227,43 +227,57 @@ int spn_sample_leaf_bwd(const float* mu, const float* sigma, int Wsets, int w, i
                         float* dsigma, float* g0, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * Tensor-core path (tcgen05 + TMEM) for SHARED-weight layers: fused CrossProduct + Sum forward as a bf16 GEMM with
- * fp32 accumulation; replaces the same reference lines as spn_sum_fwd(xprod = 1) for RatSpn models whose channel
- * counts are supported (spn_sum_tc_supported).  Activations use the internal layout [scope][repetition][batch][channel]:
- *   x [d_in, R, B, c] contiguous, out [d_out, R, B, oc] contiguous.
- * spn_sum_tc_prepare turns fp32 log-weights lw [1, d_out, c*c, oc, R] into the bf16 operand images
- * (spn_sum_tc_image_bytes() bytes, caller-allocated: the core-matrix image used by the forward and the right-child
- * gradient, followed by its pair-transposed copy used by the left-child gradient) that the kernels stream through
- * shared memory with the TMA engine.
+ * Tensor-core path (tcgen05 + TMEM) for layers whose weights are shared by MANY rows: fused CrossProduct + Sum as bf16
+ * GEMMs with fp32 accumulation and fp32 contraction epilogues; replaces the same reference lines as
+ * spn_sum_fwd(xprod = 1) (layers.py:90-128, :419-440) for
+ *   - RatSpn models: nsets = 1, every row uses the one weight set;
+ *   - CSPN layers with many rows per conditional (recursive entropy, rat_spn.py:625-750; cfg 5): nsets = number of
+ *     conditionals, Bs rows per set.
+ * Channel counts: c (per child) and oc multiples of 4 up to 64 (spn_sum_tc_supported); internally both are padded to
+ * P = spn_sum_tc_padded_channels(c, oc) = max(c, oc) rounded up to a multiple of 8.
+ * Activations use the internal layout [scope][repetition][row][channel] with the rows of one weight set contiguous:
+ *   x [d_in, R, nsets*Bs, c] contiguous, out [d_out, R, nsets*Bs, oc] contiguous.
+ * Weights lw [nsets, d_out, c*c, oc, R] (in-channel k = l*c + r'); nsd = nsets * d_out below.
+ * spn_sum_tc_prepare turns them into two bf16 operand images (spn_sum_tc_image_bytes() bytes, caller-allocated) of exp(lw):
+ * the k-major core-matrix image used by dX and its chunk-major permutation used by the forward; the kernels copy them
+ * into shared memory with the TMA engine (resident per work item up to 128 KB, streamed in chunks above).
  * Weight normalisation (layers.py:85, F.log_softmax over the in-channels on every read) is fused: when `logz`
- * ([d_out, oc, R], caller-allocated) is non-NULL, `lw` is the UNNORMALISED parameter tensor, spn_sum_tc_prepare writes
+ * ([nsd, oc, R], caller-allocated) is non-NULL, `lw` is the UNNORMALISED parameter tensor, spn_sum_tc_prepare writes
  * logz = logsumexp_k lw and every consumer uses lw - logz; with logz == NULL, lw must already be normalised.
  * Outputs whose linear-domain sum underflows are recomputed exactly in fp32 from lw (logsumexp semantics are kept).
+ * A protocol fault inside the kernels (timed-out mbarrier wait) traps the launch: the next CUDA call reports an error.
  * ------------------------------------------------------------------------------------------------------------- */
 int spn_sum_tc_supported(int c, int oc, int R);
-int64_t spn_sum_tc_image_bytes(int d_out, int c, int oc, int R);
-int spn_sum_tc_prepare(const float* lw, int d_out, int c, int oc, int R, float* logz, void* wimg, void* stream);
-/* `fhand` (optional, spn_sum_tc_fhand_bytes() bytes): receives, per (scope, repetition, 128-row tile), the packed bf16 row
- * vectors exp(xL - mL), exp(xR - mR) and the shifts; the backward kernels then load no activations and exponentiate nothing. */
-int64_t spn_sum_tc_fhand_bytes(int B, int d_out, int c, int R);
-int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw, const float* logz, int B, int d_in, int d_out,
-                   int c, int oc, int R, float* out, void* fhand, void* stream);
-/* Backward of spn_sum_tc_fwd (SURVEY A.5 as tensor-core GEMMs; layouts as in the forward).
- *   spn_sum_tc_bwd_x: dx [d_in, R, B, c] fully overwritten (two forward-shaped outer-product GEMMs, one per child).
- *                     `fhand` (optional): the forward's hand-off; without it the row vectors are recomputed from x.
- *                     `hand` (optional, spn_sum_tc_hand_bytes() bytes): receives, per (scope, repetition, 128-row tile),
- *                     G = g * exp(mL + mR - out) as a packed bf16 tile in the layout of spn_sum_tc_bwd_w's B operand.
+int spn_sum_tc_padded_channels(int c, int oc);
+int64_t spn_sum_tc_image_bytes(int nsd, int c, int oc, int R);
+int spn_sum_tc_prepare(const float* lw, int nsd, int c, int oc, int R, float* logz, void* wimg, void* stream);
+/* Forward.  `fhand` (optional, spn_sum_tc_fhand_bytes() bytes): receives, per (set, scope, repetition, 128-row tile), the
+ * packed bf16 row vectors exp(xL - mL), exp(xR - mR) and the shifts mL, mR; the backward kernels then load no activations
+ * and exponentiate nothing. */
+int64_t spn_sum_tc_fhand_bytes(int Bs, int nsd, int c, int oc, int R);
+int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw, const float* logz, int Bs, int nsets, int d_in,
+                   int d_out, int c, int oc, int R, float* out, void* fhand, void* stream);
+/* Backward of spn_sum_tc_fwd (layouts as in the forward).
+ *   spn_sum_tc_bwd_x: dx [d_in, R, nsets*Bs, c] fully overwritten: dE = G W^T as one small-K GEMM per row tile, contracted
+ *                     with exp(xL - mL) / exp(xR - mR) straight out of tensor memory.  `fhand` (required): the forward's
+ *                     hand-off (`x` itself is not read and may be NULL).  `hand` (required, spn_sum_tc_hand_bytes() bytes):
+ *                     receives, per (set, scope, repetition, 128-row tile), G = g * exp(mL + mR - out) as a packed bf16 tile
+ *                     (written by a G pre-pass, read back by TMA as this kernel's A operand and by spn_sum_tc_bwd_w as its
+ *                     B operand).  `csum` (optional, [nsd, oc, R] floats): receives the column sums of g that the fused
+ *                     softmax backward of spn_sum_tc_bwd_w needs (pass the tail of its workspace and csum_ready = 1 there).
  *   spn_sum_tc_bwd_w: needs `fhand` (from spn_sum_tc_fwd) and `hand` (from spn_sum_tc_bwd_x) of the same (x, out, g), same
  *                     stream; it recomputes nothing.
- *                     dlw [1, d_out, c*c, oc, R] = gradient w.r.t. the tensor passed as lw, fully overwritten: the
+ *                     dlw [nsets, d_out, c*c, oc, R] = gradient w.r.t. the tensor passed as lw, fully overwritten: the
  *                     log-weights (logz == NULL) or the unnormalised parameters (logz from spn_sum_tc_prepare; the
  *                     softmax backward is fused); dwt_workspace: caller-provided scratch of
- *                     d_out * R * (c*c + 1) * oc floats. */
-int64_t spn_sum_tc_hand_bytes(int B, int d_out, int c, int R);
-int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g, const void* wimg, const void* fhand, int B, int d_in,
-                     int d_out, int c, int oc, int R, float* dx, void* hand, void* stream);
+ *                     spn_sum_tc_dw_workspace_floats() floats. */
+int64_t spn_sum_tc_hand_bytes(int Bs, int nsd, int c, int oc, int R);
+int64_t spn_sum_tc_dw_workspace_floats(int nsd, int c, int oc, int R);
+int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g, const void* wimg, const void* fhand, int Bs, int nsets,
+                     int d_in, int d_out, int c, int oc, int R, float* dx, void* hand, float* csum, void* stream);
 int spn_sum_tc_bwd_w(const void* fhand, const void* hand, const float* out, const float* g, const float* lw, const float* logz,
-                     int B, int d_in, int d_out, int c, int oc, int R, float* dwt_workspace, float* dlw, void* stream);
+                     int Bs, int nsets, int d_in, int d_out, int c, int oc, int R, float* dwt_workspace, int csum_ready,
+                     float* dlw, void* stream);
 /* ---------------------------------------------------------------------------------------------------------------
  * Root sum layer for SHARED weights on the internal layout: merges the repetitions into the channel axis and sums over
  * all of them, fused with the last CrossProduct.  Replaces rat_spn.py:230-236 + layers.py:110-128 for a RatSpn.
@@ -280,8 +294,9 @@ int spn_root_shared_bwd(const float* x, int d_in, const float* lw, const float* 
 
 /* Debug aid (synchronises): number of CTAs that gave up on an mbarrier wait since the library was loaded. */
 int spn_debug_tc_aborts(int* out_host);
-/* Debug aid (synchronises): with SPN_TC_DEBUG=9 in the environment one thread per warpgroup of CTA 0 accumulates clock64
- * deltas per pipeline phase of the spn_sum_tc_fwd / _bwd_x kernels; copies the 24 counters to out_host (host pointer) and optionally resets. */
+/* Debug aid (synchronises): in builds with SPN_TC_PROFILE=1 one warp per role of CTA 0 of the spn_sum_tc_fwd / _bwd_x kernels
+ * accumulates clock64 deltas per pipeline phase; copies the 24 counters to out_host (host pointer) and optionally resets them
+ * (all zero in the product build). */
 int spn_debug_tc_prof(unsigned long long* out_host, int reset);
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -21,19 +21,32 @@ fl = 2 * B * 16 * 1600 * 40 * R
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "fwd"): timeit("tc fwd S_1", lambda: ops.tc_sum_forward(x, wimg, lw), fl)
 if which in ("all", "fwd"): timeit("tc fwd S_1 + hand-off", lambda: ops.tc_sum_forward(x, wimg, lw, None, fhand), fl)
-hand = ops.tc_hand_buffer(x, out)
+hand = ops.tc_hand_buffer(x, lw)
 if which in ("all", "bwdx", "bwdw"): timeit("tc bwd_x S_1", lambda: ops.tc_sum_backward_x(x, out, go, wimg, lw, fhand, hand), 2 * fl)
 if which in ("all", "bwdw"): timeit("tc bwd_w S_1", lambda: ops.tc_sum_backward_w(fhand, hand, x, out, go, lw), fl)
 if which in ("all",): timeit("prepare", lambda: ops.tc_prepare(lw))
 print("aborts", ops.tc_aborts())
+if "kern" in sys.argv[1:] or which == "all":
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            ops.tc_sum_forward(x, wimg, lw, None, fhand)
+            ops.tc_sum_backward_x(x, out, go, wimg, lw, fhand, hand)
+            ops.tc_sum_backward_w(fhand, hand, x, out, go, lw)
+        torch.cuda.synchronize()
+    for e in sorted(prof.key_averages(), key=lambda e: -e.device_time_total):
+        if e.device_type.name == "CUDA":
+            print(f"  {e.device_time_total / e.count / 1e3:8.3f} ms x{e.count:3d}  {e.key[:90]}")
 import os, ctypes
-if os.environ.get("SPN_TC_DEBUG"):
+if os.environ.get("SPN_TC_PROFILE"):
     from ratspn_b200 import _abi
     buf = (ctypes.c_ulonglong * 24)()
-    _abi.lib().spn_debug_tc_prof(buf, 1)
-    ops.tc_sum_forward(x, wimg, lw); torch.cuda.synchronize()
-    _abi.lib().spn_debug_tc_prof(buf, 0)
-    n = max(1, buf[5])
-    names = ["g.wait_vec", "g.wait_empty", "g.gen", "g.wait_st", "g.stages", "g.tiles", "l.prologue", "l.wait_acc", "l.epilogue",
-             "-", "-", "-", "m.wait_acc_empty", "m.wait_full", "m.issue", "m.wait_w", "-", "m.tiles"]
-    print(" ".join(f"{names[i]}={buf[i]/n:.0f}" for i in range(18) if names[i] != "-"))
+    names = ["e.wait_vec", "e.wait_acc", "e.chunks", "e.finalize", "e.wait_ld", "e.tiles", "p.wait_x", "p.compute", "p.bar", "p.wait_vec_empty",
+             "p.write", "p.tiles", "m.wait_w", "m.wait_vec", "m.wait_acc_empty", "m.wait_w_chunk", "m.issue", "m.tiles"]
+    for tag, fn in (("fwd", lambda: ops.tc_sum_forward(x, wimg, lw, None, fhand)),
+                    ("dx", lambda: ops.tc_sum_backward_x(x, out, go, wimg, lw, fhand, hand))):
+        _abi.lib().spn_debug_tc_prof(buf, 1)
+        fn(); torch.cuda.synchronize()
+        _abi.lib().spn_debug_tc_prof(buf, 0)
+        n = max(1, buf[5])
+        print(tag, "clk per tile (CTA 0):", " ".join(f"{names[i]}={buf[i]/n:.0f}" for i in range(18) if names[i] != "-"))

@@ -67,7 +67,7 @@ void frun(const char* name, float* o, long long* c, int per_iter) {
 // ---------------------------------------------------------------------------------------------------------------- TMEM
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int X, bool STORE>
+template <int X, bool STORE, bool VARY>
 __global__ void tbench(uint32_t* out, long long* clk, int iters) {
     __shared__ uint32_t slot;
     const int warp = threadIdx.x >> 5;
@@ -78,7 +78,8 @@ __global__ void tbench(uint32_t* out, long long* clk, int iters) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t base = slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * X) % 512u;
+    const uint32_t base0 = slot + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t woff = (uint32_t)((warp >> 2) * 128);   // warps of one quadrant start in different column ranges
     uint32_t r[X];
 #pragma unroll
     for (int i = 0; i < X; ++i) r[i] = threadIdx.x + i;
@@ -86,6 +87,7 @@ __global__ void tbench(uint32_t* out, long long* clk, int iters) {
     long long t0 = clock64();
     uint32_t acc = 0;
     for (int it = 0; it < iters; ++it) {
+        const uint32_t base = base0 + (VARY ? (woff + (uint32_t)it * X) % (512u - X) : woff % (512u - X));
         if (STORE) {
             if constexpr (X == 32) {
                 asm volatile(
@@ -136,11 +138,11 @@ __global__ void tbench(uint32_t* out, long long* clk, int iters) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(slot), "r"(512u) : "memory");
 }
 
-template <int X, bool STORE>
+template <int X, bool STORE, bool VARY>
 void trun(const char* name, uint32_t* o, long long* c) {
     for (int warps = 4; warps <= 16; warps *= 2) {
         const int iters = 2000;
-        tbench<X, STORE><<<1, warps * 32>>>(o, c, iters);
+        tbench<X, STORE, VARY><<<1, warps * 32>>>(o, c, iters);
         cudaError_t e = cudaDeviceSynchronize();
         long long h;
         cudaMemcpy(&h, c, 8, cudaMemcpyDeviceToHost);
@@ -160,8 +162,11 @@ int main() {
     frun<2>("mul.f32x2", o, c, 16);
     frun<4>("mul.f32", o, c, 32);
     frun<5>("ex2.approx.f32", o, c, 32);
-    trun<32, false>("tcgen05.ld 32x32b", (uint32_t*)o, c);
-    trun<16, false>("tcgen05.ld 32x32b", (uint32_t*)o, c);
-    trun<32, true>("tcgen05.st 32x32b", (uint32_t*)o, c);
+    trun<32, false, false>("tcgen05.ld same addr", (uint32_t*)o, c);
+    trun<32, false, true>("tcgen05.ld moving addr", (uint32_t*)o, c);
+    trun<16, false, false>("tcgen05.ld same addr", (uint32_t*)o, c);
+    trun<16, false, true>("tcgen05.ld moving addr", (uint32_t*)o, c);
+    trun<32, true, false>("tcgen05.st same addr", (uint32_t*)o, c);
+    trun<32, true, true>("tcgen05.st moving addr", (uint32_t*)o, c);
     return 0;
 }
