@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libspn_b200.so")
+# SPN_LIB_PATH: load another build of the same library (experiment builds of build.py; never a different implementation)
+LIB_PATH = os.environ.get("SPN_LIB_PATH") or os.path.join(_HERE, "lib", "libspn_b200.so")
 
 _c_int, _c_i64, _c_u64, _c_ptr = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_void_p
 
@@ -62,7 +63,6 @@ SIGNATURES = {
     "spn_sum_tc_bwd_x": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "spn_sum_tc_bwd_w": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     "spn_debug_tc_aborts": [_P],
-    "spn_debug_tc_prof": [_P, _I],
     "spn_root_shared_supported": [_I, _I, _I],
     "spn_root_shared_fwd": [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P],
     "spn_root_shared_bwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],

@@ -8,15 +8,18 @@
 // with eL = exp(xL - mL), eR = exp(xR - mR), G = g * exp(mL + mR - out).  Both are ONE small-K GEMM per 128-row tile
 // (M = 128 rows, K = c resp. oc, N = c*oc resp. c*c) whose result is consumed straight out of tensor memory by a
 // contraction epilogue on the CUDA cores:
-//   * A operand: the row vectors eR (forward) / G (dX) as packed bf16, written to TENSOR MEMORY by the prologue warps
-//     (tcgen05.st, lane = row) -- 20 to 32 columns per tile, no shared memory involved.
+//   * A operand: forward: the packed bf16 row vectors eR, written to TENSOR MEMORY by the prologue warps (tcgen05.st, lane =
+//     row); dX: the G tile the G pre-pass left in core-matrix layout, copied by the TMA engine into shared memory (SS MMA:
+//     the dX kernel has no prologue at all).
 //   * B operand: the bf16 weight image of (set, s, r) in shared memory, copied by the TMA engine (cp.async.bulk).  Forward
-//     reads the chunked image F (MN-major: K = r', N = (l, o)), dX the k-major image A (K-major: K = o, N = (l, r')).
-//     Images up to 128 KB stay resident for all row tiles of a work item; wider ones stream chunk by chunk through a ring.
-//   * accumulators: fp32 in TMEM, NL*P columns per chunk of NL left channels, NB chunk buffers in flight.
-//   * epilogue: tcgen05.ld (measured 1.6 KB/clk/SM on B200, profiles/r02_pipe_bench.txt) + packed fp32 FMAs (FFMA2,
-//     two per lane and instruction): forward 0.5 FMA per accumulator element, dX 2 (one per child), against
-//     M*N*K/8192 clk of tensor pipe -- the forward is bound by the tensor pipe, dX by the fp32 pipe.
+//     reads image F (MN-major: K = r', N = (l, o)), dX image A (K-major: K = o, N = (l, r')).  Images up to 128 KB stay
+//     resident for all row tiles of a work item; wider ones stream chunk by chunk through a ring.
+//   * accumulators: fp32 in TMEM, NL*P columns per chunk of NL left channels, NB chunk buffers in flight.  Inside a chunk the
+//     N axis is ordered so that the columns ONE epilogue thread consumes are consecutive (one or two wide tcgen05.ld).
+//   * epilogue: tcgen05.ld (measured 1.6 KB/clk/SM on B200, profiles/r02_pipe_bench.txt) + packed fp32 FMAs (FFMA2: 128
+//     FMA/clk/SM): forward 1 FMA per accumulator element (c*oc per row), dX 2 (one per child) on ONE load of the element,
+//     against M*N*K/8192 clk of tensor pipe -- both are bound by the fp32 pipe (1600 / 3200 clk per 128-row tile at
+//     c = oc = 40), not by the tensor pipe (1200 clk).
 // This replaces the round-1 formulation (outer-product operand eL (x) eR generated into TMEM, K = c*c, N = oc; dX as two
 // such GEMMs), which was chosen on the assumption that reading a 128 x c*c accumulator back costs 64 B/clk.
 //
@@ -32,39 +35,18 @@
 using namespace tc;
 
 __device__ int g_tc3_aborts = 0;
-__device__ unsigned long long g_tc3_prof[24];
-// Per-phase clock hooks (build with SPN_TC_PROFILE=1): every lane accumulates into registers, CTA 0 flushes once at the end.
-#ifdef SPN_TC_PROFILE
-#define TSP_DECL long long tsp_acc[6] = {0, 0, 0, 0, 0, 0}; long long tsp_t = 0
-#define TSP_START() tsp_t = clock64()
-#define TSP_LAP(slot) do { const long long tsp_n = clock64(); tsp_acc[slot] += tsp_n - tsp_t; tsp_t = tsp_n; } while (0)
-#define TSP_COUNT(slot) tsp_acc[slot] += 1
-#define TSP_T0() const long long tsp_t0 = clock64()
-#define TSP_ADD(slot) tsp_acc[slot] += clock64() - tsp_t0
-#define TSP_FLUSH(base)                                                                                          \
-    do {                                                                                                         \
-        if (blockIdx.x == 0 && lane == 0)                                                                        \
-            for (int q = 0; q < 6; ++q) atomicAdd(&g_tc3_prof[(base) + q], (unsigned long long)tsp_acc[q]);      \
-    } while (0)
-#else
-#define TSP_DECL do { } while (0)
-#define TSP_START() do { } while (0)
-#define TSP_LAP(slot) do { } while (0)
-#define TSP_COUNT(slot) do { } while (0)
-#define TSP_T0() do { } while (0)
-#define TSP_ADD(slot) do { } while (0)
-#define TSP_FLUSH(base) do { } while (0)
-#endif
 
 enum { TS_FWD = 0, TS_DX = 1 };
 
-// Experiment switches (timing only, results are garbage): exist only in builds with -DSPN_TC_DEBUGSW (SPN_TC_DEBUG env):
-//   1 no MMA issue (commits only), 2 epilogue skips loads and FMAs, 3 epilogue loads but no FMAs, 4 FMAs on stale registers (no loads)
-#ifdef SPN_TC_DEBUGSW
-#define TS_DBG(a) ((a).debug)
-#else
-#define TS_DBG(a) 0
+// Experiment switches (timing only, results are garbage): compile-time, -DSPN_TC_DEBUG_MODE=<n> (build.py):
+//   1 no MMA issue (commits only), 2 epilogue skips loads and FMAs, 3 epilogue loads but no FMAs, 4 FMAs on stale registers
+//   (no loads), 5 forward prologue skips the exp computation, 6 = 2 + 5
+#ifndef SPN_TC_DEBUG_MODE
+#define SPN_TC_DEBUG_MODE 0
 #endif
+#define TS_DBG SPN_TC_DEBUG_MODE
+#define TS_SKIP_EPI (SPN_TC_DEBUG_MODE == 2 || SPN_TC_DEBUG_MODE == 6)
+#define TS_SKIP_PRO (SPN_TC_DEBUG_MODE == 5 || SPN_TC_DEBUG_MODE == 6)
 
 struct TsArgs {
     unsigned int* counter;   // work counter of this launch (dynamic item scheduling), zeroed by the host
@@ -72,27 +54,23 @@ struct TsArgs {
     const uint8_t* wimg;     // FWD: image F, DX: image A; one image of P*P*P*2 bytes per (set, scope, repetition)
     const float* lw;         // fp32 weights [nsets][d_out][c*c][oc][R] (exact rescue path, FWD)
     const float* logz;       // NULL or [nsets*d_out][oc][R]
-    const float* out;        // DX: forward output [d_out][R][Btot][oc]
-    const float* g;          // DX: upstream gradient, same layout
-    float* y;                // FWD: out;  DX: dx [d_in][R][Btot][c]
+    float* y;                // FWD: out [d_out][R][Btot][oc];  DX: dx [d_in][R][Btot][c]
     uint8_t* fhand_w;        // FWD, optional: hand-off written per (set, s, r, row tile): packed bf16 eL, eR + row shifts
     const uint8_t* fhand_r;  // DX: the forward's hand-off
-    uint8_t* hand;           // DX, optional: G tiles in the dW kernel's B-operand layout
+    const uint8_t* hand;     // DX: G tiles (written by the G pre-pass) in core-matrix layout [row / 8][o / 8 (padded)][row % 8][8 o]
     int Bs, Btot, nsets, d_in, d_out, R, c, oc;
-    int ntiles, nsplit, debug;
+    int ntiles, nsplit;
 };
 
 // ---- compile-time geometry ---------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int ts_kp(int P) { return (P + 15) / 16 * 16; }
-// left channels per chunk: even, NL*P a multiple of 16, three chunk buffers next to the (single) A tile in 512 columns
+// left channels per chunk: even, a divisor of P, NL*P a multiple of 16, three chunk buffers next to the forward's A tile in
+// the 512 TMEM columns
 __host__ __device__ constexpr int ts_nl(int P) {
-    int best = 2, best_div = 2;
+    int best = 2;
     for (int nl = 2; nl <= P; nl += 2)
-        if (3 * nl * P + ts_kp(P) / 2 <= 512 && nl * P <= 256 && (nl * P) % 16 == 0) {
-            best = nl;
-            if (P % nl == 0) best_div = nl;
-        }
-    return 2 * best_div >= best ? best_div : best;   // prefer equal chunks
+        if (3 * nl * P + ts_kp(P) / 2 <= 512 && nl * P <= 256 && (nl * P) % 16 == 0 && P % nl == 0) best = nl;
+    return best;
 }
 __host__ __device__ constexpr int ts_nb(int P) {
     int nb = (512 - ts_kp(P) / 2) / (ts_nl(P) * P);
@@ -102,11 +80,20 @@ __host__ __device__ constexpr bool ts_resident(int P) { return P * P * P * 2 <= 
 __host__ __device__ constexpr int ts_nslot(int P) { return ts_resident(P) ? 1 : 4; }
 __host__ __device__ constexpr int ts_wbytes(int P) { return ts_resident(P) ? P * P * P * 2 : ts_nslot(P) * ts_nl(P) * P * P * 2; }
 constexpr int TS_ZERO = 4096;   // zeroed bytes behind the weights: target of padded K-halves / descriptor overruns
+constexpr int TS_NXS = 3;       // forward: ring of x stages (one child's 128 rows each)
+// Position of (left channel l, column v) on the N axis of a chunk.  The columns one epilogue thread consumes are consecutive:
+//   forward (v = output o):        thread = quarter of the outputs (QC = P/4), all NL left channels of the chunk
+//   dX      (v = right channel r'): thread = half of the right channels (HC = P/2) x half of the chunk's left channels
+// Both orders are "block index, then left channel inside the chunk, then position inside the block".
+__host__ __device__ constexpr int ts_ncol(int P, int blk_cols, int li, int v) {
+    return (v / blk_cols) * (ts_nl(P) * blk_cols) + li * blk_cols + v % blk_cols;
+}
 template <int P, int MODE>
 __host__ __device__ constexpr int ts_smem_bytes() {
-    const int vec = MODE == TS_FWD ? (2 * 128 * P * 4 /* x staging */ + 2 * P * 128 * 4 /* eL fp32 */ + (P / 2) * 512 /* packed eR */)
-                                   : (2 * 2 * (P / 2) * 512 /* packed eL, eR */ + 2 * P * 128 * 4 /* partial aL */ +
-                                      (P / 2) * 512 /* G tile staging */);
+    const int npair = P / 2;
+    const int vec = MODE == TS_FWD ? (TS_NXS * 128 * P * 4 /* x ring */ + 2 * npair * 512 /* packed eL, two tiles */)
+                                   : (2 * 16 * (ts_kp(P) / 8) * 128 /* G tiles (A operand), K padded */ + 2 * npair * 512 /* packed eL */ +
+                                      2 * P * 128 * 4 /* aL shares of the two halves */);
     return ts_wbytes(P) + TS_ZERO + vec + 2 * 2 * 128 * 4 /* shifts */ + 32 * 8 /* barriers */ + 16;
 }
 
@@ -146,34 +133,70 @@ __device__ __forceinline__ float lg2_approx(float x) {
     return y;
 }
 
-// Thread organisation (22 warps, 80 registers per thread):
-//   warps 0-3   PROLOGUE: one thread per row.  FWD: per child: row max, exp, pack; the right child's packed vector goes to the
-//               TMEM A tile, the left child's fp32 vector to shared memory; both are handed to the backward kernels.
-//               DX: the G tile (written by the G pre-pass, staged by TMA) goes to the TMEM A tile.
-//   warps 4-19  EPILOGUE: four threads per row (same lane, warps of one TMEM lane quadrant): "h" 0 / 1 = lower / upper half
-//               of the P columns of every left channel's block of the accumulator, times a role bit.  tcgen05.ld has more than
-//               100 clk of latency and is not double buffered here: four warps per scheduler hide it.
-//               FWD: role = lower / upper quarter of the half: acc[o] += eL[l] * T[l, o] for the thread's P/4 outputs.
-//               DX:  role 0: aR[r'] += eL[l] * dE[l, r'];  role 1: aL[l] += eR[r'] * dE[l, r'] (partial over the half, combined
-//               through smem) -- both roles read the same half of the accumulator.
-//   warp 20     MMA issuer.      warp 21     weight TMA (whole image per work item, or chunks through a ring).
-// The epilogue warps have scheduling priority (higher warp ids) over the prologue.
+// load N (even, <= 64) consecutive columns of this thread's TMEM lane with the widest instructions available
+template <int N>
+__device__ __forceinline__ void ts_tmem_load(uint32_t taddr, uint32_t* r) {
+    static_assert(N % 2 == 0 && N <= 64, "unsupported column count");
+    int done = 0;
+    if constexpr (N >= 32) { tmem_ld32(taddr, r); done = 32; }
+    if constexpr (N >= 64) { tmem_ld32(taddr + 32, r + 32); done = 64; }
+    if constexpr ((N % 32) >= 16) { tmem_ld16(taddr + done, r + done); done += 16; }
+    if constexpr ((N % 16) >= 8) { tmem_ld8(taddr + done, r + done); done += 8; }
+    if constexpr ((N % 8) >= 4) { tmem_ld4(taddr + done, r + done); done += 4; }
+    if constexpr ((N % 4) >= 2) { tmem_ld2(taddr + done, r + done); done += 2; }
+}
+
+// work item of the persistent kernels: (weight set, scope, repetition, row-tile range)
+struct TsItem {
+    int sr, sg, s, r, tile_begin, nt;
+    bool has_l, has_r;
+    int64_t row0;
+};
+__device__ __forceinline__ TsItem ts_item(const TsArgs& a, int item) {
+    TsItem it;
+    const int tiles_per_split = (a.ntiles + a.nsplit - 1) / a.nsplit;
+    const int split = item % a.nsplit;
+    it.sr = item / a.nsplit;                    // (set, scope, repetition) index: also the image / hand-off index
+    it.r = it.sr % a.R;
+    it.sg = it.sr / a.R;                        // set * d_out + s
+    it.s = it.sg % a.d_out;
+    it.tile_begin = split * tiles_per_split;
+    it.nt = min(a.ntiles, it.tile_begin + tiles_per_split) - it.tile_begin;
+    it.has_l = 2 * it.s < a.d_in;
+    it.has_r = 2 * it.s + 1 < a.d_in;
+    it.row0 = (int64_t)(it.sg / a.d_out) * a.Bs;   // first row of this weight set in the [Btot] row axis
+    return it;
+}
+
+// ====================================================================================================================
+// forward
+// ====================================================================================================================
+// Thread organisation (27 warps, <= 72 registers per thread):
+//   warps 0-7   PROLOGUE: one thread per (row, child) -- warps 0-3 the left child, 4-7 the right child.  Row max, exp, pack to
+//               bf16; the right child's packed vector goes to the TMEM A tile, the left child's to shared memory (epilogue);
+//               both are handed to the backward kernels through `fhand`.  The x rows arrive through a 3-deep ring of TMA
+//               stages (one child's 128 rows each), so the HBM latency of a stage is covered by two stages of compute.
+//   warps 8-23  EPILOGUE: four threads per row (same lane, warps of one TMEM lane quadrant), each a quarter of the outputs:
+//               acc[o] += eL[l] * T[l, o] over the NL left channels of a chunk -- one tcgen05.ld of NL*P/4 consecutive
+//               columns and NL*P/8 FFMA2 per chunk.  tcgen05.ld has > 100 clk of latency and is not double buffered here:
+//               four warps per scheduler hide it.
+//   warp 24     MMA issuer.    warp 25   weight TMA (whole image per work item, or chunks through a ring).
+//   warp 26     x TMA.
 // TMEM: NB chunk buffers (accumulators) + ONE A tile; the prologue writes the next tile's A operand when the MMAs of the
 // current one have completed, while the epilogue still has up to NB chunks to consume.
 // All hand-offs are mbarriers (producer arrive = release, consumer try_wait = acquire).
-template <int P, int MODE>
-__global__ void __launch_bounds__(704, 1) tsum_kernel(TsArgs a) {
+template <int P>
+__global__ void __launch_bounds__(864, 1) tsum_fwd_kernel(TsArgs a) {
     constexpr int CG = P / 8;                  // 8-channel groups
     constexpr int KP = ts_kp(P);               // K extent of the GEMM (padded to the MMA's K = 16)
     constexpr int KSTEPS = KP / 16;
     constexpr int ACOLS = KP / 2;              // A tile: packed bf16 pairs, one 32-bit column per two K values
     constexpr int NL = ts_nl(P);               // left channels per chunk
-    constexpr int NCH = (P + NL - 1) / NL;     // chunks per row tile
+    constexpr int NCH = P / NL;                // chunks per row tile
     constexpr int NCOLS = NL * P;              // accumulator columns per chunk buffer
     constexpr int NB = ts_nb(P);               // chunk buffers
-    constexpr int HC = P / 2;                  // columns per epilogue half
-    constexpr int QC = P / 4;                  // FWD: columns per epilogue thread
-    constexpr int DL = HC <= 20 ? 2 : 1;       // DX: left channels per load step (register budget)
+    constexpr int QC = P / 4;                  // outputs per epilogue thread
+    constexpr int TC = NL * QC;                // accumulator columns per epilogue thread and chunk
     constexpr int NPAIR = P / 2;               // packed words per vector
     constexpr bool RESIDENT = ts_resident(P);
     constexpr int NSLOT = ts_nslot(P);
@@ -182,34 +205,26 @@ __global__ void __launch_bounds__(704, 1) tsum_kernel(TsArgs a) {
     constexpr int W_BYTES = ts_wbytes(P);
     constexpr int A_COL0 = NB * NCOLS;
     constexpr int FH_BYTES = 2 * NPAIR * 512 + 1024;   // forward hand-off per (item, tile): eL, eR packed + shifts
-    constexpr int G_BYTES = NPAIR * 512;               // G tile per (item, tile): [16 row groups][CG][8 rows][8 bf16]
-    static_assert(P % 8 == 0 && P >= 8 && P <= 64 && NL % 2 == 0 && P % NL % 2 == 0, "unsupported channel count");
-    static_assert(NB >= 2 && A_COL0 + ACOLS <= 512 && ACOLS % 4 == 0 && QC % 2 == 0 && NL * QC <= 40, "TMEM / register budget");
+    constexpr int XS_FLOATS = 128 * P;                 // one x stage
+    static_assert(P % 8 == 0 && P >= 8 && P <= 64 && NL % 2 == 0 && P % NL == 0, "unsupported channel count");
+    static_assert(NB >= 2 && A_COL0 + ACOLS <= 512 && ACOLS % 4 == 0 && QC % 2 == 0 && TC <= 64, "TMEM / register budget");
+    constexpr int W_MMA = 24, W_WTMA = 25, W_XTMA = 26;
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* wsm = smem;                                       // weights: resident image or ring of NSLOT chunks
     uint8_t* zero = smem + W_BYTES;                            // TS_ZERO bytes of zeros
-    uint8_t* vec = zero + TS_ZERO;
-    // FWD: Xs [2 children][128][c] fp32 staged by TMA, EL [2 buf][P][128] fp32, As [NPAIR][128] packed eR (thread-private staging)
-    float* Xs = reinterpret_cast<float*>(vec);
-    float* EL = Xs + 2 * 128 * P;
-    uint32_t* As = reinterpret_cast<uint32_t*>(EL + 2 * P * 128);
-    // DX: Us / Vs [2 buf][NPAIR][128] packed bf16 eL / eR (TMA from the forward's hand-off), PL [2 halves][P][128] fp32,
-    //     Gs: one G tile staged by TMA
-    uint32_t* Us = reinterpret_cast<uint32_t*>(vec);
-    uint32_t* Vs = Us + 2 * NPAIR * 128;
-    float* PL = reinterpret_cast<float*>(Vs + 2 * NPAIR * 128);
-    uint8_t* Gs = reinterpret_cast<uint8_t*>(PL + 2 * P * 128);
-    float* Ms = reinterpret_cast<float*>(vec + (MODE == TS_FWD ? (2 * 128 * P * 4 + 2 * P * 128 * 4 + NPAIR * 512)
-                                                               : (2 * 2 * NPAIR * 512 + 2 * P * 128 * 4 + G_BYTES)));   // [2 buf][2][128]
-    uint64_t* vec_full = reinterpret_cast<uint64_t*>(Ms + 2 * 2 * 128);   // [2]  FWD: prologue -> epilogue;  DX: TMA (hand-off) -> epilogue
+    float* Xr = reinterpret_cast<float*>(zero + TS_ZERO);      // [TS_NXS][128][c] fp32 rows staged by TMA
+    uint32_t* ELp = reinterpret_cast<uint32_t*>(Xr + TS_NXS * XS_FLOATS);   // [2 buf][NPAIR][128] packed eL
+    float* Ms = reinterpret_cast<float*>(ELp + 2 * NPAIR * 128);            // [2 buf][2][128] row shifts mL, mR
+    uint64_t* vec_full = reinterpret_cast<uint64_t*>(Ms + 2 * 2 * 128);   // [2]  prologue -> epilogue
     uint64_t* vec_empty = vec_full + 2;                                  // [2]  epilogue -> prologue
     uint64_t* acc_full = vec_empty + 2;                                  // [NB] MMA commit -> epilogue
     uint64_t* acc_empty = acc_full + 4;                                  // [NB] epilogue -> MMA
     uint64_t* w_full = acc_empty + 4;                                    // [NSLOT] TMA -> MMA
     uint64_t* w_empty = w_full + 4;                                      // [NSLOT] MMA commit -> TMA
-    uint64_t* x_full = w_empty + 4;                                      // [1]  TMA (FWD: x rows, DX: G tile) -> prologue
-    uint64_t* a_full = x_full + 1;                                       // [1]  prologue (A tile in TMEM) -> MMA
+    uint64_t* x_full = w_empty + 4;                                      // [TS_NXS] TMA -> prologue
+    uint64_t* x_empty = x_full + TS_NXS;                                 // [TS_NXS] prologue -> TMA
+    uint64_t* a_full = x_empty + TS_NXS;                                 // [1]  prologue (A tile in TMEM) -> MMA
     uint64_t* a_free = a_full + 1;                                       // [1]  MMA commit (last chunk of a tile) -> prologue
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_free + 1);
     volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
@@ -217,7 +232,7 @@ __global__ void __launch_bounds__(704, 1) tsum_kernel(TsArgs a) {
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(vec_full + i, MODE == TS_FWD ? 4 : 1);
+            mbar_init(vec_full + i, 8);
             mbar_init(vec_empty + i, 16);
         }
         for (int i = 0; i < 4; ++i) {
@@ -226,7 +241,10 @@ __global__ void __launch_bounds__(704, 1) tsum_kernel(TsArgs a) {
             mbar_init(w_full + i, 1);
             mbar_init(w_empty + i, 1);
         }
-        mbar_init(x_full, 1);
+        for (int i = 0; i < TS_NXS; ++i) {
+            mbar_init(x_full + i, 1);
+            mbar_init(x_empty + i, 8);
+        }
         mbar_init(a_full, 4);
         mbar_init(a_free, 1);
         *abort_flag = 0;
@@ -235,7 +253,7 @@ __global__ void __launch_bounds__(704, 1) tsum_kernel(TsArgs a) {
     // zero region (and, for streamed weights, the ring: descriptor overruns must only ever see finite values)
     for (int i = threadIdx.x; i < (TS_ZERO + (RESIDENT ? 0 : W_BYTES)) / 16; i += blockDim.x)
         reinterpret_cast<uint4*>(RESIDENT ? zero : wsm)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (warp == 20) tmem_alloc(tmem_slot, 512);
+    if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
@@ -246,9 +264,7 @@ __global__ void __launch_bounds__(704, 1) tsum_kernel(TsArgs a) {
 
     const int c = a.c, oc = a.oc;
     const int nitems = a.nsets * a.d_out * a.R * a.nsplit;
-    const int tiles_per_split = (a.ntiles + a.nsplit - 1) / a.nsplit;
-    uint32_t n_tile = 0, n_chunk = 0, n_wchunk = 0, items_done = 0;   // per-role ring positions (persist across items)
-    TSP_DECL;
+    uint32_t n_tile = 0, n_chunk = 0, n_wchunk = 0, n_x = 0, items_done = 0;   // per-role ring positions (persist across items)
 
     __shared__ int s_next[2];
     for (;; ++items_done) {
@@ -256,19 +272,12 @@ __global__ void __launch_bounds__(704, 1) tsum_kernel(TsArgs a) {
         __syncthreads();  // the previous item is finished by every role (its last epilogue waited for its last MMA)
         const int item = __shfl_sync(0xffffffffu, s_next[items_done & 1], 0);
         if (item >= nitems) break;
-        const int split = item % a.nsplit;
-        const int sr = item / a.nsplit;            // (set, scope, repetition) index: also the image / hand-off index
-        const int r = sr % a.R, sg = sr / a.R;     // sg = set * d_out + s
-        const int set = sg / a.d_out, s = sg % a.d_out;
-        const int tile_begin = split * tiles_per_split;
-        const int tile_end = min(a.ntiles, tile_begin + tiles_per_split);
-        const int nt = tile_end - tile_begin;
-        const bool has_l = 2 * s < a.d_in, has_r = 2 * s + 1 < a.d_in;
-        const int64_t row0 = (int64_t)set * a.Bs;  // first row of this weight set in the [Btot] row axis
+        const TsItem it = ts_item(a, item);
+        const int nt = it.nt;
         if (__shfl_sync(0xffffffffu, *abort_flag, 0)) break;
-        const uint8_t* img = a.wimg + (size_t)sr * IMG_BYTES;
+        const uint8_t* img = a.wimg + (size_t)it.sr * IMG_BYTES;
 
-        if (warp == 21) {
+        if (warp == W_WTMA) {
             // =============================================== weight TMA ===============================================
             if (RESIDENT) {
                 if (lane == 0) {
@@ -283,34 +292,50 @@ __global__ void __launch_bounds__(704, 1) tsum_kernel(TsArgs a) {
                         const uint32_t slot = n_wchunk % NSLOT, use = n_wchunk / NSLOT;
                         mbar_wait_sticky(w_empty + slot, (use & 1) ^ 1, abort_flag);   // the MMAs that read the slot are complete
                         if (lane == 0) {
-                            const int nlc = min(NL, P - ch * NL);
-                            const uint32_t bytes = (uint32_t)nlc * P * P * 2;
-                            mbar_arrive_expect_tx(w_full + slot, bytes);
-                            bulk_g2s(wsm + slot * CHUNK_BYTES, img + (size_t)ch * CHUNK_BYTES, bytes, w_full + slot);
+                            mbar_arrive_expect_tx(w_full + slot, CHUNK_BYTES);
+                            bulk_g2s(wsm + slot * CHUNK_BYTES, img + (size_t)ch * CHUNK_BYTES, CHUNK_BYTES, w_full + slot);
                         }
                         __syncwarp();
                     }
             }
-        } else if (warp == 20) {
+        } else if (warp == W_XTMA) {
+            // =============================================== x TMA ===============================================
+            for (int t = 0; t < nt; ++t, ++n_tile) {
+                const int tile = it.tile_begin + t;
+                const int rows = min(128, a.Bs - tile * 128);
+                const uint32_t bytes = (uint32_t)rows * c * 4;
+#pragma unroll
+                for (int child = 0; child < 2; ++child) {
+                    // a missing child (odd scope count) takes no stage: its prologue warps substitute zeros.  (A stage that is
+                    // completed without data would let those warps run two phases ahead of the barrier's parity.)
+                    if (!(child ? it.has_r : it.has_l)) continue;
+                    const uint32_t j = n_x++, slot = j % TS_NXS, use = j / TS_NXS;
+                    mbar_wait_sticky(x_empty + slot, (use & 1) ^ 1, abort_flag);   // the prologue has taken its rows out of the slot
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(x_full + slot, bytes);
+                        bulk_g2s(Xr + slot * XS_FLOATS,
+                                 a.x + (((int64_t)(2 * it.s + child) * a.R + it.r) * a.Btot + it.row0 + (int64_t)tile * 128) * c, bytes,
+                                 x_full + slot);
+                    }
+                    __syncwarp();
+                }
+            }
+        } else if (warp == W_MMA) {
             // =============================================== MMA issuer ===============================================
             const uint32_t wsm_addr = smem_u32(wsm), zero_addr = smem_u32(zero);
-            TSP_START();
             if (RESIDENT) {
                 mbar_wait_sticky(w_full, items_done & 1, abort_flag);
                 fence_after_sync();
             }
-            TSP_LAP(0);   // m.wait_w
+            constexpr uint32_t idesc = instr_desc_bf16(128, NCOLS, 0, 1);
             for (int t = 0; t < nt; ++t, ++n_tile) {
                 mbar_wait_sticky(a_full, n_tile & 1, abort_flag);   // A tile of this row tile is in TMEM
                 fence_after_sync();
-                TSP_LAP(1);   // m.wait_vec
-                TSP_COUNT(5);
                 const uint32_t a_col = tmem_base + A_COL0;
 #pragma unroll 1
                 for (int ch = 0; ch < NCH; ++ch, ++n_chunk) {
                     const uint32_t buf = n_chunk % NB, use = n_chunk / NB;
                     mbar_wait_sticky(acc_empty + buf, (use & 1) ^ 1, abort_flag);     // the epilogue has read this buffer
-                    TSP_LAP(2);   // m.wait_acc_empty
                     uint32_t base = wsm_addr + ch * CHUNK_BYTES;
                     uint32_t slot = 0;
                     if (!RESIDENT) {
@@ -320,53 +345,47 @@ __global__ void __launch_bounds__(704, 1) tsum_kernel(TsArgs a) {
                         ++n_wchunk;
                     }
                     fence_after_sync();
-                    TSP_LAP(3);   // m.wait_w_chunk
-                    const int nlc = min(NL, P - ch * NL);
-                    const uint32_t idesc = instr_desc_bf16(128, nlc * P, 0, MODE == TS_FWD ? 1 : 0);
                     const uint32_t acc = tmem_base + buf * NCOLS;
 #pragma unroll
                     for (int kk = 0; kk < KSTEPS; ++kk) {
-                        uint64_t desc;
-                        if (MODE == TS_FWD) {
-                            // B[K = r', N = (l, o)] MN-major: N groups 128 B apart, K groups (8 r') nlc*CG*128 B apart.  The
-                            // second K half of the last step does not exist when P % 16 == 8: it is read from the zero region.
-                            const uint32_t kstride = (uint32_t)nlc * CG * 128;
-                            const uint32_t start = base + 2 * kk * kstride;
-                            const uint32_t lbo = (KP > P && kk == KSTEPS - 1) ? zero_addr - start : kstride;
-                            desc = smem_desc(start, lbo, 128);
-                        } else {
-                            // B[K = o, N = (l, r')] K-major: N groups (8 consecutive k) CG*128 B apart, K halves 128 B apart; a
-                            // padded K half (P % 16 == 8) reads the next block -- finite image values times the A tile's zeros.
-                            desc = smem_desc(base + 2 * kk * 128, 128, CG * 128);
-                        }
-                        if (TS_DBG(a) != 1) mma_ts_uniform(acc, a_col + kk * 8, desc, idesc, kk ? 1u : 0u);
+                        // B[K = r', N] MN-major: N groups 128 B apart, K groups (8 r') NL*CG*128 B apart.  The second K half of
+                        // the last step does not exist when P % 16 == 8: it is read from the zero region.
+                        constexpr uint32_t kstride = (uint32_t)NL * CG * 128;
+                        const uint32_t start = base + 2 * kk * kstride;
+                        const uint32_t lbo = (KP > P && kk == KSTEPS - 1) ? zero_addr - start : kstride;
+                        const uint64_t desc = smem_desc(start, lbo, 128);
+                        if (TS_DBG != 1) mma_ts_uniform(acc, a_col + kk * 8, desc, idesc, kk ? 1u : 0u);
                     }
                     mma_commit_uniform(acc_full + buf);
                     if (!RESIDENT) mma_commit_uniform(w_empty + slot);
-                    TSP_LAP(4);   // m.issue
                 }
                 mma_commit_uniform(a_free);   // the A tile may be overwritten with the next tile's operand
             }
-        } else if (warp < 4) {
+        } else if (warp < 8) {
             // =============================================== prologue ===============================================
-            const int row = warp * 32 + lane;
-            const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-            const uint32_t a_addr = tmem_base + lane_base + A_COL0;
-            if (MODE == TS_FWD) {
-                auto stage_x = [&](int tile) {   // whole warp 0 (one elected lane issues)
-                    const int rows = min(128, a.Bs - tile * 128);
-                    const uint32_t bytes = (uint32_t)rows * c * 4;
-                    mbar_arrive_expect_tx_elect(x_full, (has_l ? bytes : 0u) + (has_r ? bytes : 0u));
-                    if (has_l)
-                        bulk_g2s_elect(Xs, a.x + (((int64_t)(2 * s) * a.R + r) * a.Btot + row0 + (int64_t)tile * 128) * c, bytes, x_full);
-                    if (has_r)
-                        bulk_g2s_elect(Xs + 128 * P, a.x + (((int64_t)(2 * s + 1) * a.R + r) * a.Btot + row0 + (int64_t)tile * 128) * c,
-                                       bytes, x_full);
-                };
-                // max-shifted exp of one child's row: ev = fp32 vector, returns the shift
-                auto child = [&](int half, bool valid, float* ev) -> float {
-                    const bool has_mine = half ? has_r : has_l;
-                    const float4* rowp = reinterpret_cast<const float4*>(Xs + half * 128 * P + row * c);
+            const int child = warp >> 2;                    // 0: left, 1: right
+            const int row = (warp & 3) * 32 + lane;
+            const uint32_t a_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + A_COL0;
+            const bool has_mine = child ? it.has_r : it.has_l;
+            for (int t = 0; t < nt; ++t, ++n_tile) {
+                const int tile = it.tile_begin + t;
+                const uint32_t vb = n_tile & 1;
+                const bool valid = (int64_t)tile * 128 + row < a.Bs;
+                // Stages are counted over the children that exist.  EVERY prologue warp passes EVERY stage barrier in order (and
+                // releases it), also the other child's: a warp that skipped a phase of a slot could not tell the phases
+                // two uses apart by their parity.
+                const uint32_t jl = n_x, jr = n_x + (it.has_l ? 1u : 0u);
+                n_x += (it.has_l ? 1u : 0u) + (it.has_r ? 1u : 0u);
+                const uint32_t j = child ? jr : jl, slot = j % TS_NXS;
+                if (child == 1 && it.has_l) {   // the left child's stage comes first
+                    mbar_wait_sticky(x_full + jl % TS_NXS, (jl / TS_NXS) & 1, abort_flag);
+                    if (lane == 0) mbar_arrive(x_empty + jl % TS_NXS);
+                }
+                if (has_mine) mbar_wait_sticky(x_full + slot, (j / TS_NXS) & 1, abort_flag);
+                float ev[P];
+                float m;
+                {
+                    const float4* rowp = reinterpret_cast<const float4*>(Xr + slot * XS_FLOATS + row * c);
                     float m4[P / 4];
 #pragma unroll
                     for (int q = 0; q < P / 4; ++q) {
@@ -375,333 +394,459 @@ __global__ void __launch_bounds__(704, 1) tsum_kernel(TsArgs a) {
                         ev[4 * q] = t4.x; ev[4 * q + 1] = t4.y; ev[4 * q + 2] = t4.z; ev[4 * q + 3] = t4.w;
                         m4[q] = fmaxf(fmaxf(t4.x, t4.y), fmaxf(t4.z, t4.w));
                     }
+                    // the rows are in registers: the TMA engine may refill the slot
+                    fence_proxy_async();   // ordinary loads of the slot are ordered before the TMA engine's next write into it
+                    __syncwarp();
+                    if (lane == 0 && has_mine) mbar_arrive(x_empty + slot);
 #pragma unroll
                     for (int st = 1; st < P / 4; st *= 2)   // tree reduction: short dependency chain
 #pragma unroll
                         for (int q = 0; q + st < P / 4; q += 2 * st) m4[q] = fmaxf(m4[q], m4[q + st]);
-                    float m = m4[0];
+                    m = m4[0];
                     m = (m == -CUDART_INF_F) ? 0.f : m;
+                }
+                uint32_t pk[NPAIR];
+                {
                     const float ms = m * 1.4426950408889634f;
 #pragma unroll
-                    for (int q = 0; q < P; ++q) ev[q] = ex2_approx(fmaf(ev[q], 1.4426950408889634f, -ms));
-                    return m;
-                };
-                if (warp == 0 && nt > 0) stage_x(tile_begin);
-                for (int t = 0; t < nt; ++t, ++n_tile) {
-                    const int tile = tile_begin + t;
-                    const uint32_t vb = n_tile & 1;
-                    const bool valid = (int64_t)tile * 128 + row < a.Bs;
-                    uint8_t* fh = a.fhand_w ? a.fhand_w + ((size_t)sr * a.ntiles + tile) * FH_BYTES : nullptr;
-                    TSP_START();
-                    mbar_wait_sticky(x_full, n_tile & 1, abort_flag);
-                    TSP_LAP(0);   // p.wait_x
-                    float ev[P];
-                    // right child: packed bf16 -> thread-private staging (goes to TMEM when the A tile is free) + hand-off
-                    const float mR = child(1, valid, ev);
-                    {
-                        uint32_t* as = As + row;
-                        uint32_t* dw = fh ? reinterpret_cast<uint32_t*>(fh + NPAIR * 512) + row : nullptr;
-#pragma unroll
-                        for (int q = 0; q < NPAIR; ++q) {
-                            const uint32_t w = pack_bf16(ev[2 * q], ev[2 * q + 1]);
-                            as[q * 128] = w;
-                            if (fh) dw[q * 128] = w;   // coalesced: lanes = consecutive rows of one packed word index
-                        }
+                    for (int q = 0; q < NPAIR; ++q) {
+                        const float e0 = TS_SKIP_PRO ? ev[2 * q] : ex2_approx(fmaf(ev[2 * q], 1.4426950408889634f, -ms));
+                        const float e1 = TS_SKIP_PRO ? ev[2 * q + 1] : ex2_approx(fmaf(ev[2 * q + 1], 1.4426950408889634f, -ms));
+                        pk[q] = pack_bf16(e0, e1);
                     }
-                    // left child: fp32 vector for the epilogue + packed hand-off
-                    const float mL = child(0, valid, ev);
-                    TSP_LAP(1);   // p.compute
-                    // every prologue thread has taken its rows out of the staging area: the TMA engine may refill it
-                    ts_named_bar(1, 128);
-                    if (warp == 0 && t + 1 < nt) stage_x(tile + 1);
-                    TSP_LAP(2);   // p.bar
-                    if (fh) {
-                        uint32_t* dw = reinterpret_cast<uint32_t*>(fh) + row;
+                }
+                if (a.fhand_w) {   // hand-off: coalesced (lanes = consecutive rows of one packed word index)
+                    uint8_t* fh = a.fhand_w + ((size_t)it.sr * a.ntiles + tile) * FH_BYTES;
+                    uint32_t* dw = reinterpret_cast<uint32_t*>(fh + child * NPAIR * 512) + row;
 #pragma unroll
-                        for (int q = 0; q < NPAIR; ++q) dw[q * 128] = pack_bf16(ev[2 * q], ev[2 * q + 1]);
-                        float* ms = reinterpret_cast<float*>(fh + 2 * NPAIR * 512);
-                        ms[row] = mL;
-                        ms[128 + row] = mR;
-                    }
-                    // buffer set vb: the epilogue (eL, shifts) of tile n - 2 is done with it
-                    mbar_wait_sticky(vec_empty + vb, ((n_tile >> 1) & 1) ^ 1, abort_flag);
-                    TSP_LAP(3);   // p.wait_vec_empty
-                    Ms[vb * 256 + row] = mL;
-                    Ms[vb * 256 + 128 + row] = mR;
-                    {
-                        float* el = EL + vb * P * 128 + row;
+                    for (int q = 0; q < NPAIR; ++q) dw[q * 128] = pk[q];
+                    reinterpret_cast<float*>(fh + 2 * NPAIR * 512)[child * 128 + row] = m;
+                }
+                // buffer set vb: the epilogue (eL, shifts) of tile n - 2 is done with it
+                mbar_wait_sticky(vec_empty + vb, ((n_tile >> 1) & 1) ^ 1, abort_flag);
+                Ms[vb * 256 + child * 128 + row] = m;
+                if (child == 0) {
+                    uint32_t* el = ELp + vb * NPAIR * 128 + row;
 #pragma unroll
-                        for (int q = 0; q < P; ++q) el[q * 128] = ev[q];
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(vec_full + vb);
+                    for (int q = 0; q < NPAIR; ++q) el[q * 128] = pk[q];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(vec_full + vb);
+                if (child == 0 && it.has_r) {   // pass the right child's stage (landed long ago)
+                    mbar_wait_sticky(x_full + jr % TS_NXS, (jr / TS_NXS) & 1, abort_flag);
+                    if (lane == 0) mbar_arrive(x_empty + jr % TS_NXS);
+                }
+                if (child == 1) {
                     // the A tile: the MMAs of the previous tile must have completed
                     mbar_wait_sticky(a_free, (n_tile & 1) ^ 1, abort_flag);
                     fence_after_sync();
                     {
                         uint32_t at[ACOLS];
 #pragma unroll
-                        for (int q = 0; q < ACOLS; ++q) at[q] = q < NPAIR ? As[q * 128 + row] : 0u;
+                        for (int q = 0; q < ACOLS; ++q) at[q] = q < NPAIR ? pk[q] : 0u;
                         tmem_store_cols<ACOLS>(a_addr, at);
                     }
                     tmem_wait_st();
                     fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(a_full);
-                    TSP_LAP(4);   // p.write
-                    TSP_COUNT(5);
-                }
-            } else {
-                auto stage_g = [&](int tile) {   // whole warp 0: the G tile written by the G pre-pass
-                    mbar_arrive_expect_tx_elect(x_full, G_BYTES);
-                    bulk_g2s_elect(Gs, a.hand + ((size_t)sr * a.ntiles + tile) * G_BYTES, G_BYTES, x_full);
-                };
-                if (warp == 0 && nt > 0) stage_g(tile_begin);
-                for (int t = 0; t < nt; ++t, ++n_tile) {
-                    const int tile = tile_begin + t;
-                    const uint32_t vb = n_tile & 1;
-                    TSP_START();
-                    if (warp == 0) {   // eL, eR (packed bf16) and the row shifts of this tile, straight from the forward's hand-off
-                        mbar_wait_sticky(vec_empty + vb, ((n_tile >> 1) & 1) ^ 1, abort_flag);
-                        const uint8_t* src = a.fhand_r + ((size_t)sr * a.ntiles + tile) * FH_BYTES;
-                        mbar_arrive_expect_tx_elect(vec_full + vb, FH_BYTES);
-                        bulk_g2s_elect(Us + vb * NPAIR * 128, src, NPAIR * 512, vec_full + vb);
-                        bulk_g2s_elect(Vs + vb * NPAIR * 128, src + NPAIR * 512, NPAIR * 512, vec_full + vb);
-                        bulk_g2s_elect(Ms + vb * 256, src + 2 * NPAIR * 512, 1024, vec_full + vb);
-                    }
-                    TSP_LAP(3);   // p.wait_vec_empty
-                    mbar_wait_sticky(x_full, n_tile & 1, abort_flag);
-                    TSP_LAP(0);   // p.wait_x (G tile)
-                    uint32_t at[ACOLS];
-                    {
-                        const uint4* gs = reinterpret_cast<const uint4*>(Gs) + (row >> 3) * (CG * 8) + (row & 7);
-#pragma unroll
-                        for (int og = 0; og < ACOLS / 4; ++og) {
-                            const uint4 v4 = og < CG ? gs[og * 8] : make_uint4(0u, 0u, 0u, 0u);
-                            at[4 * og] = v4.x; at[4 * og + 1] = v4.y; at[4 * og + 2] = v4.z; at[4 * og + 3] = v4.w;
-                        }
-                    }
-                    ts_named_bar(1, 128);   // every row has been taken out of the staging area
-                    if (warp == 0 && t + 1 < nt) stage_g(tile + 1);
-                    TSP_LAP(1);   // p.compute
-                    mbar_wait_sticky(a_free, (n_tile & 1) ^ 1, abort_flag);
-                    fence_after_sync();
-                    TSP_LAP(2);   // p.bar (wait for the A tile)
-                    tmem_store_cols<ACOLS>(a_addr, at);
-                    tmem_wait_st();
-                    fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(a_full);
-                    TSP_LAP(4);   // p.write
-                    TSP_COUNT(5);
                 }
             }
         } else {
             // =============================================== epilogue ===============================================
-            const int ew = warp - 4;
-            const int h = (ew >> 2) & 1, role = ew >> 3;
+            const int quarter = (warp - 8) >> 2;
             const int row = (warp & 3) * 32 + lane;
             const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+            const int col0 = quarter * QC;             // this thread's outputs: o in [col0, col0 + QC)
             for (int t = 0; t < nt; ++t, ++n_tile) {
-                const int tile = tile_begin + t;
+                const int tile = it.tile_begin + t;
                 const uint32_t vb = n_tile & 1;
                 const int64_t b = (int64_t)tile * 128 + row;
                 const bool valid = b < a.Bs;
-                TSP_START();
-                mbar_wait_sticky(vec_full + vb, (n_tile >> 1) & 1, abort_flag);   // eL / eR / shifts of this tile are in smem
-                TSP_LAP(0);   // e.wait_vec
-                TSP_COUNT(5);
-                if (MODE == TS_FWD) {
-                    // this thread's outputs: o in [col0, col0 + QC)
-                    const int col0 = h * HC + role * QC;
-                    uint64_t acc2[QC / 2];
+                mbar_wait_sticky(vec_full + vb, (n_tile >> 1) & 1, abort_flag);   // eL / shifts of this tile are in smem
+                uint64_t acc2[QC / 2];
 #pragma unroll
-                    for (int j = 0; j < QC / 2; ++j) acc2[j] = 0ull;
+                for (int j = 0; j < QC / 2; ++j) acc2[j] = 0ull;
+                const uint32_t* elp = ELp + vb * NPAIR * 128 + row;
 #pragma unroll 1
-                    for (int ch = 0; ch < NCH; ++ch, ++n_chunk) {
-                        const uint32_t buf = n_chunk % NB, use = n_chunk / NB;
-                        const int nlc = min(NL, P - ch * NL);
-                        {
-                            TSP_T0();
-                            mbar_wait_sticky(acc_full + buf, use & 1, abort_flag);
-                            fence_after_sync();
-                            TSP_ADD(1);   // e.wait_acc (also contained in e.chunks)
+                for (int ch = 0; ch < NCH; ++ch, ++n_chunk) {
+                    const uint32_t buf = n_chunk % NB, use = n_chunk / NB;
+                    mbar_wait_sticky(acc_full + buf, use & 1, abort_flag);
+                    fence_after_sync();
+                    uint32_t d[TC];
+                    if (!TS_SKIP_EPI && TS_DBG != 4) ts_tmem_load<TC>(tmem_base + lane_base + buf * NCOLS + quarter * TC, d);
+                    uint32_t elw[NL / 2];
+#pragma unroll
+                    for (int u = 0; u < NL / 2; ++u) elw[u] = elp[(ch * (NL / 2) + u) * 128];
+                    tmem_wait_ld();
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + buf);   // the accumulator may be overwritten
+                    if (!TS_SKIP_EPI && TS_DBG != 3) {
+#pragma unroll
+                        for (int li = 0; li < NL; ++li) {
+                            const float el = (li & 1) ? bf16_hi(elw[li >> 1]) : bf16_lo(elw[li >> 1]);
+                            const uint64_t e2 = f2pack(el, el);
+#pragma unroll
+                            for (int j = 0; j < QC / 2; ++j)
+                                acc2[j] = fma2(e2, u2pack(d[li * QC + 2 * j], d[li * QC + 2 * j + 1]), acc2[j]);
                         }
-                        const uint32_t cbase = tmem_base + lane_base + buf * NCOLS + col0;
-                        uint32_t d[NL * QC];
-                        float el[NL];
-#pragma unroll
-                        for (int li = 0; li < NL; ++li)
-                            if (li < nlc && TS_DBG(a) != 2 && TS_DBG(a) != 4) tmem_load_cols<QC>(cbase + li * P, d + li * QC);
-#pragma unroll
-                        for (int li = 0; li < NL; ++li) el[li] = li < nlc ? EL[vb * P * 128 + (ch * NL + li) * 128 + row] : 0.f;
-                        {
-                            TSP_T0();
-                            tmem_wait_ld();
-                            TSP_ADD(4);   // e.wait_ld (also contained in e.chunks)
-                        }
-                        fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(acc_empty + buf);   // the accumulator may be overwritten
-                        if (TS_DBG(a) != 2 && TS_DBG(a) != 3) {
-#pragma unroll
-                            for (int li = 0; li < NL; ++li) {
-                                if (li < nlc) {
-                                    const uint64_t e2 = f2pack(el[li], el[li]);
-#pragma unroll
-                                    for (int j = 0; j < QC / 2; ++j)
-                                        acc2[j] = fma2(e2, u2pack(d[li * QC + 2 * j], d[li * QC + 2 * j + 1]), acc2[j]);
-                                }
-                            }
-                        }
-                    }
-                    TSP_LAP(2);   // e.chunks
-                    const float* my_m = Ms + vb * 256 + row;
-                    const float shift = my_m[0] + my_m[128];
-                    float* op = a.y + (((int64_t)s * a.R + r) * a.Btot + row0 + (valid ? b : 0)) * oc + col0;
-                    bool bad = false;
-#pragma unroll
-                    for (int j = 0; j < QC / 2; ++j) {
-                        float s0, s1;
-                        f2unpack(acc2[j], s0, s1);
-                        const bool on = valid && col0 + 2 * j < oc;
-                        bad |= on && !(fminf(s0, s1) >= 1e-30f);
-                        if (on)
-                            *reinterpret_cast<float2*>(op + 2 * j) = make_float2(fmaf(lg2_approx(s0), 0.6931471805599453f, shift),
-                                                                                 fmaf(lg2_approx(s1), 0.6931471805599453f, shift));
-                    }
-                    if (bad && !TS_DBG(a)) ts_exact_row(a, sg, s, r, row0 + b, col0, QC, op);
-                } else {
-                    // both roles walk over this half's HC columns of every left channel
-                    uint64_t acc2[HC / 2];   // role 0: aR pairs;  role 1: this half's eR pairs as fp32
-#pragma unroll
-                    for (int j = 0; j < HC / 2; ++j) {
-                        if (role == 0) {
-                            acc2[j] = 0ull;
-                        } else {
-                            const uint32_t w = Vs[vb * NPAIR * 128 + (h * (HC / 2) + j) * 128 + row];
-                            acc2[j] = f2pack(bf16_lo(w), bf16_hi(w));
-                        }
-                    }
-#pragma unroll 1
-                    for (int ch = 0; ch < NCH; ++ch, ++n_chunk) {
-                        const uint32_t buf = n_chunk % NB, use = n_chunk / NB;
-                        const int nlc = min(NL, P - ch * NL);
-                        {
-                            TSP_T0();
-                            mbar_wait_sticky(acc_full + buf, use & 1, abort_flag);
-                            fence_after_sync();
-                            TSP_ADD(1);
-                        }
-                        const uint32_t cbase = tmem_base + lane_base + buf * NCOLS + h * HC;
-#pragma unroll 1
-                        for (int li = 0; li < nlc; li += DL) {
-                            const int l = ch * NL + li;
-                            uint32_t d[DL * HC];
-#pragma unroll
-                            for (int u = 0; u < DL; ++u)
-                                if (TS_DBG(a) != 2 && TS_DBG(a) != 4) tmem_load_cols<HC>(cbase + (li + u) * P, d + u * HC);
-                            const uint32_t wl = Us[vb * NPAIR * 128 + (l >> 1) * 128 + row];   // eL[l & ~1], eL[l | 1]
-                            {
-                                TSP_T0();
-                                tmem_wait_ld();
-                                TSP_ADD(4);
-                            }
-                            if (li + DL >= nlc) {   // last load of this chunk has completed
-                                fence_before_sync();
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(acc_empty + buf);
-                            }
-                            if (TS_DBG(a) == 2 || TS_DBG(a) == 3) continue;
-#pragma unroll
-                            for (int u = 0; u < DL; ++u) {
-                                if (role == 0) {
-                                    const float eu = ((l + u) & 1) ? bf16_hi(wl) : bf16_lo(wl);
-                                    const uint64_t e2 = f2pack(eu, eu);
-#pragma unroll
-                                    for (int j = 0; j < HC / 2; ++j) acc2[j] = fma2(e2, u2pack(d[u * HC + 2 * j], d[u * HC + 2 * j + 1]), acc2[j]);
-                                } else {
-                                    uint64_t s0 = 0ull, s1 = 0ull;
-#pragma unroll
-                                    for (int j = 0; j < HC / 2; ++j) {
-                                        const uint64_t d2 = u2pack(d[u * HC + 2 * j], d[u * HC + 2 * j + 1]);
-                                        if (j & 1) s1 = fma2(acc2[j], d2, s1); else s0 = fma2(acc2[j], d2, s0);
-                                    }
-                                    float p0, p1, p2, p3;
-                                    f2unpack(s0, p0, p1);
-                                    f2unpack(s1, p2, p3);
-                                    PL[(h * P + l + u) * 128 + row] = (p0 + p1) + (p2 + p3);
-                                }
-                            }
-                        }
-                    }
-                    TSP_LAP(2);   // e.chunks
-                    if (role == 0) {
-                        // dxR[r'] = eR[r'] * aR[r'] for this half's right channels
-                        if (valid && has_r) {
-                            float* dp = a.y + (((int64_t)(2 * s + 1) * a.R + r) * a.Btot + row0 + b) * c + h * HC;
-#pragma unroll
-                            for (int j4 = 0; j4 < HC / 4; ++j4) {
-                                const uint32_t w0 = Vs[vb * NPAIR * 128 + (h * (HC / 2) + 2 * j4) * 128 + row];
-                                const uint32_t w1 = Vs[vb * NPAIR * 128 + (h * (HC / 2) + 2 * j4 + 1) * 128 + row];
-                                float v0, v1, v2, v3;
-                                f2unpack(acc2[2 * j4], v0, v1);
-                                f2unpack(acc2[2 * j4 + 1], v2, v3);
-                                if (h * HC + 4 * j4 < c)
-                                    *reinterpret_cast<float4*>(dp + 4 * j4) = make_float4(bf16_lo(w0) * v0, bf16_hi(w0) * v1, bf16_lo(w1) * v2, bf16_hi(w1) * v3);
-                            }
-                        }
-                    } else {
-                        ts_named_bar(2, 256);   // both halves' partial aL of this tile are in shared memory (role-1 warps only)
-                        if (valid && has_l) {
-                            float* dp = a.y + (((int64_t)(2 * s) * a.R + r) * a.Btot + row0 + b) * c + h * HC;
-#pragma unroll
-                            for (int j4 = 0; j4 < HC / 4; ++j4) {
-                                float res[4];
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) {
-                                    const int l = h * HC + 4 * j4 + u;
-                                    const uint32_t wl = Us[vb * NPAIR * 128 + (l >> 1) * 128 + row];
-                                    const float el = (l & 1) ? bf16_hi(wl) : bf16_lo(wl);
-                                    res[u] = el * (PL[l * 128 + row] + PL[(P + l) * 128 + row]);
-                                }
-                                if (h * HC + 4 * j4 < c) *reinterpret_cast<float4*>(dp + 4 * j4) = make_float4(res[0], res[1], res[2], res[3]);
-                            }
-                        }
-                        ts_named_bar(2, 256);   // the partial sums have been read: the next tile may overwrite them
                     }
                 }
+                const float* my_m = Ms + vb * 256 + row;
+                const float shift = my_m[0] + my_m[128];
+                float* op = a.y + (((int64_t)it.s * a.R + it.r) * a.Btot + it.row0 + (valid ? b : 0)) * oc + col0;
+                bool bad = false;
+#pragma unroll
+                for (int j = 0; j < QC / 2; ++j) {
+                    float s0, s1;
+                    f2unpack(acc2[j], s0, s1);
+                    const bool on = valid && col0 + 2 * j < oc;
+                    bad |= on && !(fminf(s0, s1) >= 1e-30f);
+                    if (on && TS_DBG != 14)
+                        *reinterpret_cast<float2*>(op + 2 * j) = make_float2(fmaf(lg2_approx(s0), 0.6931471805599453f, shift),
+                                                                             fmaf(lg2_approx(s1), 0.6931471805599453f, shift));
+                }
+                if (bad && !TS_DBG) ts_exact_row(a, it.sg, it.s, it.r, it.row0 + b, col0, QC, op);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(vec_empty + vb);   // eL / eR / shifts of this buffer set are no longer read
-                TSP_LAP(3);   // e.finalize
+                if (lane == 0) mbar_arrive(vec_empty + vb);   // eL / shifts of this buffer set are no longer read
             }
         }
     }
     // teardown
-    if (warp == 4) TSP_FLUSH(0);
-    if (warp == 0) TSP_FLUSH(6);
-    if (warp == 20) TSP_FLUSH(12);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (warp == 20) tmem_dealloc(tmem_base, 512);
+    if (warp == W_MMA) tmem_dealloc(tmem_base, 512);
+    if (threadIdx.x == 0) tc_abort_trap(abort_flag, &g_tc3_aborts);
+}
+
+// ====================================================================================================================
+// dX
+// ====================================================================================================================
+// Thread organisation (11 warps, <= 184 registers per thread):
+//   warps 0-7   EPILOGUE: two threads per row (same lane, the two warps of one TMEM lane quadrant): h = lower / upper half of
+//               the right channels, all left channels.  Every accumulator element dE[l, r'] is loaded ONCE and used twice:
+//               aR[r'] += eL[l] * dE (kept in registers over the tile: complete when the tile ends) and
+//               aL[l] += eR[r'] * dE (a dot product over the thread's right channels; the two halves combine their partial
+//               sums through shared memory, plain stores -- shared-memory fp32 atomics are CAS loops).  The loads are
+//               software pipelined by half chunks: the tcgen05.ld of the next half chunk is in flight while the FFMA2s of
+//               the current one issue, so two warps per scheduler keep the fp32 pipe busy.
+//   warp 8      MMA issuer (SS: the G tile in shared memory is the A operand).
+//   warp 9      weight TMA.    warp 10   TMA of the per-tile operands: G tile (double buffered), packed eL (double
+//               buffered) and eR (single buffer: the epilogue threads take their values into registers at once).
+template <int P>
+__global__ void __launch_bounds__(352, 1) tsum_dx_kernel(TsArgs a) {
+    constexpr int CG = P / 8;
+    constexpr int KP = ts_kp(P);
+    constexpr int KSTEPS = KP / 16;
+    constexpr int KG = KP / 8;                 // K groups of the (padded) A operand tile
+    constexpr int NL = ts_nl(P);
+    constexpr int NCH = P / NL;
+    constexpr int NCOLS = NL * P;
+    constexpr int NB = ts_nb(P);
+    constexpr int HC = P / 2;                  // right channels per epilogue thread
+    constexpr int NLH = NL / 2;                // left channels per load step (half chunk)
+    constexpr int TC = NLH * HC;               // accumulator columns per epilogue thread and load step
+    constexpr int NPAIR = P / 2;
+    constexpr bool RESIDENT = ts_resident(P);
+    constexpr int NSLOT = ts_nslot(P);
+    constexpr int CHUNK_BYTES = NL * P * P * 2;
+    constexpr int IMG_BYTES = P * P * P * 2;
+    constexpr int W_BYTES = ts_wbytes(P);
+    constexpr int FH_BYTES = 2 * NPAIR * 512 + 1024;
+    constexpr int GS_BYTES = 16 * KG * 128;            // G tile: [16 row groups][KG][8 rows][8 bf16], pad K groups are zero
+    static_assert(P % 8 == 0 && P >= 8 && P <= 64 && NL % 2 == 0 && P % NL == 0, "unsupported channel count");
+    static_assert(NB >= 2 && NB * NCOLS <= 512 && HC % 4 == 0 && TC <= 64, "TMEM / register budget");
+    constexpr int W_MMA = 8, W_WTMA = 9, W_VTMA = 10;
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* wsm = smem;
+    uint8_t* zero = smem + W_BYTES;
+    uint8_t* Gs = zero + TS_ZERO;                                             // [2][GS_BYTES]
+    uint32_t* Us = reinterpret_cast<uint32_t*>(Gs + 2 * GS_BYTES);            // [2][NPAIR][128] packed eL
+    float* SL = reinterpret_cast<float*>(Us + 2 * NPAIR * 128);               // [2 halves][P][128] partial aL sums
+    uint64_t* u_full = reinterpret_cast<uint64_t*>(SL + 2 * P * 128);         // [2] TMA -> epilogue
+    uint64_t* u_empty = u_full + 2;                                           // [2] epilogue -> TMA
+    uint64_t* g_full = u_empty + 2;                                           // [2] TMA -> MMA
+    uint64_t* g_empty = g_full + 2;                                           // [2] MMA commit -> TMA
+    uint64_t* acc_full = g_empty + 2;                                         // [NB]
+    uint64_t* acc_empty = acc_full + 4;                                       // [NB]
+    uint64_t* w_full = acc_empty + 4;                                         // [NSLOT]
+    uint64_t* w_empty = w_full + 4;                                           // [NSLOT]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + 4);
+    volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(u_full + i, 1);
+            mbar_init(u_empty + i, 8);
+            mbar_init(g_full + i, 1);
+            mbar_init(g_empty + i, 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(acc_full + i, 1);
+            mbar_init(acc_empty + i, 8);
+            mbar_init(w_full + i, 1);
+            mbar_init(w_empty + i, 1);
+        }
+        *abort_flag = 0;
+        mbar_fence_init();
+    }
+    // zero: the zero region and, for streamed weights, the ring (descriptor overruns must only ever see finite values)
+    for (int i = threadIdx.x; i < TS_ZERO / 16; i += blockDim.x) reinterpret_cast<uint4*>(zero)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (!RESIDENT)
+        for (int i = threadIdx.x; i < W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(wsm)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (threadIdx.x == 0 && *tmem_slot != 0) *abort_flag = 1;
+    constexpr uint32_t tmem_base = 0;
+    __syncthreads();
+
+    const int c = a.c;
+    const int nitems = a.nsets * a.d_out * a.R * a.nsplit;
+    uint32_t n_tile = 0, n_chunk = 0, n_wchunk = 0, items_done = 0;
+
+    __shared__ int s_next[2];
+    for (;; ++items_done) {
+        if (threadIdx.x == 0) s_next[items_done & 1] = (int)atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const int item = __shfl_sync(0xffffffffu, s_next[items_done & 1], 0);
+        if (item >= nitems) break;
+        const TsItem it = ts_item(a, item);
+        const int nt = it.nt;
+        if (__shfl_sync(0xffffffffu, *abort_flag, 0)) break;
+        const uint8_t* img = a.wimg + (size_t)it.sr * IMG_BYTES;
+
+        if (warp == W_WTMA) {
+            // =============================================== weight TMA ===============================================
+            if (RESIDENT) {
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(w_full, IMG_BYTES);
+                    constexpr int CH = 16384;
+                    for (int off = 0; off < IMG_BYTES; off += CH) bulk_g2s(wsm + off, img + off, min(CH, IMG_BYTES - off), w_full);
+                }
+                __syncwarp();
+            } else {
+                for (int t = 0; t < nt; ++t)
+                    for (int ch = 0; ch < NCH; ++ch, ++n_wchunk) {
+                        const uint32_t slot = n_wchunk % NSLOT, use = n_wchunk / NSLOT;
+                        mbar_wait_sticky(w_empty + slot, (use & 1) ^ 1, abort_flag);
+                        if (lane == 0) {
+                            mbar_arrive_expect_tx(w_full + slot, CHUNK_BYTES);
+                            bulk_g2s(wsm + slot * CHUNK_BYTES, img + (size_t)ch * CHUNK_BYTES, CHUNK_BYTES, w_full + slot);
+                        }
+                        __syncwarp();
+                    }
+            }
+        } else if (warp == W_VTMA) {
+            // =============================================== per-tile operand TMA ===============================================
+            for (int t = 0; t < nt; ++t, ++n_tile) {
+                const int tile = it.tile_begin + t;
+                const uint32_t vb = n_tile & 1;
+                const size_t ti = (size_t)it.sr * a.ntiles + tile;
+                const uint8_t* fh = a.fhand_r + ti * FH_BYTES;
+                // G tile (A operand): the MMAs of tile n - 2 are complete
+                mbar_wait_sticky(g_empty + vb, ((n_tile >> 1) & 1) ^ 1, abort_flag);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(g_full + vb, GS_BYTES);
+                    bulk_g2s(Gs + vb * GS_BYTES, a.hand + ti * GS_BYTES, GS_BYTES, g_full + vb);
+                }
+                __syncwarp();
+                // packed eL (read all through the tile; the epilogue threads fetch their eR values themselves)
+                mbar_wait_sticky(u_empty + vb, ((n_tile >> 1) & 1) ^ 1, abort_flag);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(u_full + vb, NPAIR * 512);
+                    bulk_g2s(Us + vb * NPAIR * 128, fh, NPAIR * 512, u_full + vb);
+                }
+                __syncwarp();
+            }
+        } else if (warp == W_MMA) {
+            // =============================================== MMA issuer ===============================================
+            const uint32_t wsm_addr = smem_u32(wsm), gs_addr = smem_u32(Gs);
+            if (RESIDENT) {
+                mbar_wait_sticky(w_full, items_done & 1, abort_flag);
+                fence_after_sync();
+            }
+            constexpr uint32_t idesc = instr_desc_bf16(128, NCOLS, 0, 0);
+            for (int t = 0; t < nt; ++t, ++n_tile) {
+                const uint32_t vb = n_tile & 1;
+                mbar_wait_sticky(g_full + vb, (n_tile >> 1) & 1, abort_flag);   // G tile of this row tile is in shared memory
+                fence_after_sync();
+                const uint32_t ga = gs_addr + vb * GS_BYTES;
+#pragma unroll 1
+                for (int ch = 0; ch < NCH; ++ch, ++n_chunk) {
+                    const uint32_t buf = n_chunk % NB, use = n_chunk / NB;
+                    mbar_wait_sticky(acc_empty + buf, (use & 1) ^ 1, abort_flag);
+                    uint32_t base = wsm_addr + ch * CHUNK_BYTES;
+                    uint32_t slot = 0;
+                    if (!RESIDENT) {
+                        slot = n_wchunk % NSLOT;
+                        mbar_wait_sticky(w_full + slot, (n_wchunk / NSLOT) & 1, abort_flag);
+                        base = wsm_addr + slot * CHUNK_BYTES;
+                        ++n_wchunk;
+                    }
+                    fence_after_sync();
+                    const uint32_t acc = tmem_base + buf * NCOLS;
+#pragma unroll
+                    for (int kk = 0; kk < KSTEPS; ++kk) {
+                        // A[M = row, K = o] K-major: K halves 128 B apart, 8-row groups KG*128 B apart (pad K group = zeros).
+                        // B[K = o, N] K-major: N groups (8 consecutive n) CG*128 B apart, K halves 128 B apart; a padded K half
+                        // (P % 16 == 8) reads the next block -- finite image values times the A tile's zeros.
+                        const uint64_t adesc = smem_desc(ga + 2 * kk * 128, 128, KG * 128);
+                        const uint64_t bdesc = smem_desc(base + 2 * kk * 128, 128, CG * 128);
+                        if (TS_DBG != 1) mma_ss_uniform(acc, adesc, bdesc, idesc, kk ? 1u : 0u);
+                    }
+                    mma_commit_uniform(acc_full + buf);
+                    if (!RESIDENT) mma_commit_uniform(w_empty + slot);
+                }
+                mma_commit_uniform(g_empty + vb);   // the G stage may be refilled
+            }
+        } else {
+            // =============================================== epilogue ===============================================
+            const int h = warp >> 2;
+            const int row = (warp & 3) * 32 + lane;
+            const uint32_t my_col = ((uint32_t)((warp & 3) * 32) << 16) + h * (NL * HC);
+            // This half's eR values come straight from the forward's hand-off in global memory (coalesced: lanes = consecutive
+            // rows of one packed word), one tile ahead: the loads of tile t + 1 are in flight during tile t.
+            auto er_ptr = [&](int tile) {
+                return reinterpret_cast<const uint32_t*>(a.fhand_r + ((size_t)it.sr * a.ntiles + tile) * FH_BYTES + NPAIR * 512) +
+                       (h * (HC / 2)) * 128 + row;
+            };
+            uint32_t er_next[HC / 2];
+            if (nt > 0) {
+                const uint32_t* ep = er_ptr(it.tile_begin);
+#pragma unroll
+                for (int j = 0; j < HC / 2; ++j) er_next[j] = __ldg(ep + j * 128);
+            }
+            for (int t = 0; t < nt; ++t, ++n_tile) {
+                const int tile = it.tile_begin + t;
+                const uint32_t vb = n_tile & 1;
+                const int64_t b = (int64_t)tile * 128 + row;
+                const bool valid = b < a.Bs;
+                uint64_t er2[HC / 2];
+#pragma unroll
+                for (int j = 0; j < HC / 2; ++j) er2[j] = f2pack(bf16_lo(er_next[j]), bf16_hi(er_next[j]));
+                if (t + 1 < nt) {
+                    const uint32_t* ep = er_ptr(tile + 1);
+#pragma unroll
+                    for (int j = 0; j < HC / 2; ++j) er_next[j] = __ldg(ep + j * 128);
+                }
+                mbar_wait_sticky(u_full + vb, (n_tile >> 1) & 1, abort_flag);
+                const uint32_t* up = Us + vb * NPAIR * 128 + row;
+                float* slp = SL + h * P * 128 + row;
+                uint64_t ar2[HC / 2];
+#pragma unroll
+                for (int j = 0; j < HC / 2; ++j) ar2[j] = 0ull;
+                // load steps k = 0 .. 2 NCH - 1 (two per chunk), register double buffer
+                uint32_t d[2][TC];
+                {
+                    const uint32_t buf = n_chunk % NB;
+                    mbar_wait_sticky(acc_full + buf, (n_chunk / NB) & 1, abort_flag);
+                    fence_after_sync();
+                    if (!TS_SKIP_EPI && TS_DBG != 4) ts_tmem_load<TC>(tmem_base + buf * NCOLS + my_col, d[0]);
+                }
+#pragma unroll 1
+                for (int ch = 0; ch < NCH; ++ch, ++n_chunk) {
+                    const uint32_t buf = n_chunk % NB;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        tmem_wait_ld();   // load step (ch, half) is in d[half]
+                        if (half == 1) {   // both halves of the chunk have been read: the accumulator may be overwritten
+                            fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(acc_empty + buf);
+                        }
+                        // next load step
+                        if (half == 0) {
+                            if (!TS_SKIP_EPI && TS_DBG != 4) ts_tmem_load<TC>(tmem_base + buf * NCOLS + my_col + NLH * HC, d[1]);
+                        } else if (ch + 1 < NCH) {
+                            const uint32_t nbuf = (n_chunk + 1) % NB;
+                            mbar_wait_sticky(acc_full + nbuf, ((n_chunk + 1) / NB) & 1, abort_flag);
+                            fence_after_sync();
+                            if (!TS_SKIP_EPI && TS_DBG != 4) ts_tmem_load<TC>(tmem_base + nbuf * NCOLS + my_col, d[0]);
+                        }
+                        if (TS_SKIP_EPI || TS_DBG == 3) continue;
+                        const int l0 = ch * NL + half * NLH;
+#pragma unroll
+                        for (int u = 0; u < NLH; ++u) {
+                            const uint32_t w = up[((l0 + u) >> 1) * 128];
+                            const float el = ((l0 + u) & 1) ? bf16_hi(w) : bf16_lo(w);
+                            const uint64_t e2 = f2pack(el, el);
+                            uint64_t s0 = 0ull, s1 = 0ull;
+#pragma unroll
+                            for (int j = 0; j < HC / 2; ++j) {
+                                const uint64_t d2 = u2pack(d[half][u * HC + 2 * j], d[half][u * HC + 2 * j + 1]);
+                                ar2[j] = fma2(e2, d2, ar2[j]);
+                                if (j & 1) s1 = fma2(er2[j], d2, s1); else s0 = fma2(er2[j], d2, s0);
+                            }
+                            float p0, p1, p2, p3;
+                            f2unpack(s0, p0, p1);
+                            f2unpack(s1, p2, p3);
+                            slp[(l0 + u) * 128] = (p0 + p1) + (p2 + p3);   // this half's share of aL[l]
+                        }
+                    }
+                }
+                // dxR[r'] = eR[r'] * aR[r'] for this half's right channels
+                {
+                    float* dp = a.y + (((int64_t)(2 * it.s + 1) * a.R + it.r) * a.Btot + it.row0 + b) * c + h * HC;
+#pragma unroll
+                    for (int j4 = 0; j4 < HC / 4; ++j4) {
+                        const uint64_t p0 = mul2(er2[2 * j4], ar2[2 * j4]), p1 = mul2(er2[2 * j4 + 1], ar2[2 * j4 + 1]);
+                        float v0, v1, v2, v3;
+                        f2unpack(p0, v0, v1);
+                        f2unpack(p1, v2, v3);
+                        if (valid && it.has_r && h * HC + 4 * j4 < c && TS_DBG != 14) *reinterpret_cast<float4*>(dp + 4 * j4) = make_float4(v0, v1, v2, v3);
+                    }
+                }
+                ts_named_bar(1, 256);   // both halves' shares of aL are in shared memory
+                {
+                    // dxL[l] = eL[l] * aL[l] for the left channels of this half
+                    float* dp = a.y + (((int64_t)(2 * it.s) * a.R + it.r) * a.Btot + it.row0 + b) * c + h * HC;
+#pragma unroll
+                    for (int j4 = 0; j4 < HC / 4; ++j4) {
+                        const int l = h * HC + 4 * j4;
+                        const float* sp = SL + l * 128 + row;
+                        const uint32_t w0 = up[(l >> 1) * 128], w1 = up[((l >> 1) + 1) * 128];
+                        const float4 v = make_float4(bf16_lo(w0) * (sp[0] + sp[P * 128]), bf16_hi(w0) * (sp[128] + sp[P * 128 + 128]),
+                                                     bf16_lo(w1) * (sp[256] + sp[P * 128 + 256]), bf16_hi(w1) * (sp[384] + sp[P * 128 + 384]));
+                        if (valid && it.has_l && l < c && TS_DBG != 14) *reinterpret_cast<float4*>(dp + 4 * j4) = v;
+                    }
+                }
+                fence_proxy_async();    // ordinary loads of eL are ordered before the TMA engine's next write into the buffer
+                ts_named_bar(1, 256);   // the shares have been read: the next tile may overwrite them
+                if (lane == 0) mbar_arrive(u_empty + vb);
+            }
+        }
+    }
+    // teardown
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (warp == W_MMA) tmem_dealloc(tmem_base, 512);
     if (threadIdx.x == 0) tc_abort_trap(abort_flag, &g_tc3_aborts);
 }
 
 // G pre-pass of the backward (one block per (set, scope, repetition, 128-row tile)): G = g * exp(mL + mR - out) = g / (linear
 // -domain sum) as packed bf16 in the core-matrix layout [row / 8][o / 8][row % 8][8 o] that both the dX kernel (A operand,
-// via TMA + tcgen05.st) and the dW kernel (B operand) consume; out = -inf (impossible row): no gradient; the exponent is
-// capped so that rows whose sum underflowed in the forward (rescue path) stay finite.  Also accumulates the column sums
-// csum[sg][o][r] = sum_b g[b, o] over the rows with out > -inf, which the fused softmax backward of dW needs (the rows of a
-// tile are contiguous, so the loads are coalesced 16-byte accesses; the shifts come from the forward's hand-off).
+// K-major) and the dW kernel (B operand, MN-major) read straight from shared memory after ONE bulk copy per tile; the o-groups
+// are padded to KG = (multiple of 16) / 8 with zero groups (the MMAs' K resp. N extent).  out = -inf (impossible row): no
+// gradient; the exponent is capped so that rows whose sum underflowed in the forward (rescue path) stay finite.  Also
+// accumulates the column sums csum[sg][o][r] = sum_b g[b, o] over the rows with out > -inf, which the fused softmax backward
+// of dW needs (the rows of a tile are contiguous, so the loads are coalesced 16-byte accesses; the shifts come from the
+// forward's hand-off).
 __global__ void __launch_bounds__(128) tc_gprep_kernel(const float* __restrict__ out, const float* __restrict__ g,
                                                       const uint8_t* __restrict__ fhand, uint8_t* __restrict__ hand,
                                                       float* __restrict__ csum, int Bs, int Btot, int d_out, int oc, int R,
                                                       int P, int ntiles) {
     extern __shared__ __align__(16) uint8_t gsm[];
-    const int NPAIR = P / 2, CG = P / 8;
-    uint4* Gt = reinterpret_cast<uint4*>(gsm);                          // [16][CG][8] 16-byte rows
-    float* sh = reinterpret_cast<float*>(gsm + NPAIR * 512);            // [128] mL + mR (in log2 units)
+    const int NPAIR = P / 2, KG = ts_kp(P) / 8;
+    uint4* Gt = reinterpret_cast<uint4*>(gsm);                          // [16][KG][8] 16-byte rows
+    float* sh = reinterpret_cast<float*>(gsm + 16 * KG * 128);          // [128] mL + mR (in log2 units)
     float* cs = sh + 128;                                               // [P] column sums of this tile
     const int tile = blockIdx.x % ntiles;
     const int sr = blockIdx.x / ntiles;
@@ -712,7 +857,7 @@ __global__ void __launch_bounds__(128) tc_gprep_kernel(const float* __restrict__
     const float* shp = reinterpret_cast<const float*>(fhand + ((size_t)sr * ntiles + tile) * FH_BYTES + 2 * NPAIR * 512);
     sh[threadIdx.x] = (shp[threadIdx.x] + shp[128 + threadIdx.x]) * 1.4426950408889634f;
     for (int i = threadIdx.x; i < P; i += 128) cs[i] = 0.f;
-    for (int i = threadIdx.x; i < 16 * CG * 8; i += 128) Gt[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < 16 * KG * 8; i += 128) Gt[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     const int64_t base = (((int64_t)s * R + r) * Btot + (int64_t)set * Bs + (int64_t)tile * 128) * oc;
     const float4* op = reinterpret_cast<const float4*>(out + base);
@@ -732,11 +877,11 @@ __global__ void __launch_bounds__(128) tc_gprep_kernel(const float* __restrict__
             if (csum && live) atomicAdd(cs + o + u, g_[u]);
         }
         // 8-byte half of the 16-byte row (row, o / 8)
-        Gt2[(((row >> 3) * CG + (o >> 3)) * 8 + (row & 7)) * 2 + ((o >> 2) & 1)] = make_uint2(tc::pack_bf16(G[0], G[1]), tc::pack_bf16(G[2], G[3]));
+        Gt2[(((row >> 3) * KG + (o >> 3)) * 8 + (row & 7)) * 2 + ((o >> 2) & 1)] = make_uint2(tc::pack_bf16(G[0], G[1]), tc::pack_bf16(G[2], G[3]));
     }
     __syncthreads();
-    uint4* dst = reinterpret_cast<uint4*>(hand + ((size_t)sr * ntiles + tile) * (size_t)(NPAIR * 512));
-    for (int i = threadIdx.x; i < 16 * CG * 8; i += 128) dst[i] = Gt[i];
+    uint4* dst = reinterpret_cast<uint4*>(hand + ((size_t)sr * ntiles + tile) * (size_t)(16 * KG * 128));
+    for (int i = threadIdx.x; i < 16 * KG * 8; i += 128) dst[i] = Gt[i];
     if (csum)
         for (int o = threadIdx.x; o < oc; o += 128) atomicAdd(csum + ((int64_t)sg * oc + o) * R + r, cs[o]);
 }
@@ -806,6 +951,14 @@ __global__ void __launch_bounds__(256) tc_logz_kernel(const float* __restrict__ 
     }
 }
 
+// 16-byte row (8 outputs o = 8 og .. 8 og + 7 of in-channel pair (l, r')) of image A inside one (set, scope, repetition):
+// chunk-major; inside a chunk the K-major core-matrix grid [n / 8][og][n % 8] with n = the dX kernel's column order.
+__host__ __device__ __forceinline__ int ts_image_a_row(int P, int NL, int l, int rp, int og) {
+    const int CG = P / 8, HC = P / 2;
+    const int n = (rp / HC) * (NL * HC) + (l % NL) * HC + rp % HC;
+    return (l / NL) * (NL * P * CG) + ((n >> 3) * CG + og) * 8 + (n & 7);
+}
+
 // Image A: fp32 (log-)weights [S][K = c*c][oc][R] (S = weight sets x scopes) -> bf16 exp() core-matrix image
 // [S][R][kg = l*CG + rg][og][8 (k = r' % 8)][8 (o)], CG = P / 8 groups per padded channel axis.  Fast variant for c and oc
 // multiples of 8: one block per (scope, group of 8 consecutive k): the [8][oc][R] slab is read with coalesced float4 loads
@@ -814,7 +967,7 @@ __global__ void __launch_bounds__(256) tc_logz_kernel(const float* __restrict__ 
 // shared-memory reads (conflict free) and the global stores (contiguous per repetition) are efficient.  Padding blocks
 // (P > c or P > oc) are zero-filled by a memset before the launch.
 __global__ void __launch_bounds__(256) tc_wimage_kernel(const float* __restrict__ lw, const float* __restrict__ logz,
-                                                       uint8_t* __restrict__ wimg, int c, int OC, int R, int P, int RP,
+                                                       uint8_t* __restrict__ wimg, int c, int OC, int R, int P, int NL, int RP,
                                                        int KS) {
     extern __shared__ float tile[];  // [8][KS], row (kk, o) at kk * KS + o * RP
     const int K = c * c, CG = P / 8, cg = c / 8;
@@ -840,7 +993,6 @@ __global__ void __launch_bounds__(256) tc_wimage_kernel(const float* __restrict_
     __syncthreads();
     const int NOG = OC / 8;
     uint4* dst = reinterpret_cast<uint4*>(wimg);
-    const int64_t kg = (int64_t)l * CG + rg;
     // work item = (r, og, kk) with kk fastest: chunk index inside (s, r) is (kg * CG + og) * 8 + kk
     for (int i = threadIdx.x; i < NOG * 8 * R; i += blockDim.x) {
         const int kk = i & 7, og = (i >> 3) % NOG, r = i / (8 * NOG);
@@ -850,13 +1002,13 @@ __global__ void __launch_bounds__(256) tc_wimage_kernel(const float* __restrict_
         uint4 v;
         v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
         v.z = *reinterpret_cast<uint32_t*>(&p2); v.w = *reinterpret_cast<uint32_t*>(&p3);
-        dst[(((int64_t)s * R + r) * ((int64_t)P * CG) + kg) * (CG * 8) + og * 8 + kk] = v;
+        dst[((int64_t)s * R + r) * ((int64_t)P * CG * CG * 8) + ts_image_a_row(P, NL, l, rg * 8 + kk, og)] = v;
     }
 }
 
 // Image A for channel counts that are multiples of 4 only: one thread per 16-byte image row (strided reads; such layers are small).
 __global__ void __launch_bounds__(256) tc_wimage_generic_kernel(const float* __restrict__ lw, const float* __restrict__ logz,
-                                                               uint4* __restrict__ wimg, int S, int c, int OC, int R, int P) {
+                                                               uint4* __restrict__ wimg, int S, int c, int OC, int R, int P, int NL) {
     const int CG = P / 8;
     const int64_t per_sr = (int64_t)P * CG * CG * 8;   // 16-byte rows per (s, r)
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -882,27 +1034,38 @@ __global__ void __launch_bounds__(256) tc_wimage_generic_kernel(const float* __r
     uint4 q;
     q.x = *reinterpret_cast<uint32_t*>(&p0); q.y = *reinterpret_cast<uint32_t*>(&p1);
     q.z = *reinterpret_cast<uint32_t*>(&p2); q.w = *reinterpret_cast<uint32_t*>(&p3);
-    wimg[i] = q;
+    wimg[srr * per_sr + ts_image_a_row(P, NL, l, rp, og)] = q;
 }
 
-// Image F (forward): the same 128-byte blocks, chunk-major: [chunk][rg][l in chunk][og][8][8] so that within a chunk of NL
-// left channels the (l, o) pairs form ONE uniformly strided N axis of the GEMM.  One thread per 16-byte row of the destination.
-__global__ void __launch_bounds__(256) tc_wimage_f_kernel(const uint4* __restrict__ img, uint4* __restrict__ imgf, int P, int NL,
-                                                         int64_t nrows) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nrows) return;
-    const int CG = P / 8;
-    const int per_sr = P * CG * CG * 8;      // 16-byte rows per (s, r)
-    const int64_t srr = i / per_sr;
-    const int e = (int)(i % per_sr);
-    const int per_l = CG * CG * 8;           // rows per left channel
-    const int ch = e / (NL * per_l);
-    const int ec = e - ch * NL * per_l;
-    const int nlc = min(NL, P - ch * NL);
-    // inside the chunk: [rg][li][og][kk]
-    const int kk = ec % 8, og = (ec / 8) % CG, li = (ec / (8 * CG)) % nlc, rg = ec / (8 * CG * nlc);
-    const int l = ch * NL + li;
-    imgf[i] = img[srr * per_sr + (((int64_t)l * CG + rg) * CG + og) * 8 + kk];
+// Image F (forward) from image A: per chunk the MN-major core-matrix grid [rg = r' / 8][n / 8][r' % 8][8 n] with n = the
+// forward kernel's column order (quarter of the outputs, left channel inside the chunk, output inside the quarter), so
+// one 16-byte row of F gathers 8 single elements of A.  One block per (set, scope, repetition, chunk): the A chunk goes
+// through shared memory, both global sides are coalesced 16-byte accesses.
+__global__ void __launch_bounds__(256) tc_wimage_f_kernel(const uint4* __restrict__ img, uint4* __restrict__ imgf, int P, int NL) {
+    extern __shared__ uint4 achunk[];
+    const int CG = P / 8, HC = P / 2, QC = P / 4, NCOLS = NL * P;
+    const int rows = NCOLS * CG;                       // 16-byte rows per chunk
+    const int64_t base = (int64_t)blockIdx.x * rows;   // chunks are contiguous: blockIdx.x = (s, r) * NCH + chunk
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) achunk[i] = img[base + i];
+    __syncthreads();
+    const unsigned short* a16 = reinterpret_cast<const unsigned short*>(achunk);
+    for (int f = threadIdx.x; f < rows; f += blockDim.x) {
+        const int kk = f & 7, ng = (f >> 3) % (NCOLS / 8), rg = f / (NCOLS);
+        const int rp = rg * 8 + kk;
+        unsigned short e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = ng * 8 + j;
+            const int quarter = n / (NL * QC), rem = n % (NL * QC);
+            const int li = rem / QC, o = quarter * QC + rem % QC;
+            const int na = (rp / HC) * (NL * HC) + li * HC + rp % HC;
+            e[j] = a16[(((na >> 3) * CG + (o >> 3)) * 8 + (na & 7)) * 8 + (o & 7)];
+        }
+        uint4 v;
+        v.x = e[0] | ((uint32_t)e[1] << 16); v.y = e[2] | ((uint32_t)e[3] << 16);
+        v.z = e[4] | ((uint32_t)e[5] << 16); v.w = e[6] | ((uint32_t)e[7] << 16);
+        imgf[base + f] = v;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -951,9 +1114,10 @@ static int launch_tsum(const TsArgs& a, cudaStream_t st) {
     constexpr int SMEM = ts_smem_bytes<P, MODE>();
     static_assert(SMEM <= 232448, "shared memory budget");
     static std::atomic<unsigned long long> configured{0};
+    auto kernel = MODE == TS_FWD ? tsum_fwd_kernel<P> : tsum_dx_kernel<P>;
     int dev = 0, sms = 148;
     if (!tc_configured_on_device(configured, &dev)) {
-        cudaError_t e = cudaFuncSetAttribute(tsum_kernel<P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return spn_cuda_status(e);
         if (dev < 64) configured.fetch_or(1ull << dev);
     }
@@ -962,7 +1126,7 @@ static int launch_tsum(const TsArgs& a, cudaStream_t st) {
     TsArgs b = a;
     b.counter = tc_next_counter(st);
     if (!b.counter) return SPN_ERR_ARG;
-    tsum_kernel<P, MODE><<<nitems < sms ? nitems : sms, 704, SMEM, st>>>(b);
+    kernel<<<nitems < sms ? nitems : sms, MODE == TS_FWD ? 864 : 352, SMEM, st>>>(b);
     return spn_launch_status();
 }
 
@@ -994,10 +1158,6 @@ static void ts_split(TsArgs& a) {
     if (nsplit > a.ntiles / 4) nsplit = a.ntiles / 4;
     if (nsplit < 1) nsplit = 1;
     a.nsplit = nsplit;
-#ifdef SPN_TC_DEBUGSW
-    const char* dbg = getenv("SPN_TC_DEBUG");
-    a.debug = dbg ? atoi(dbg) : 0;
-#endif
 }
 
 extern "C" int spn_sum_tc_supported(int c, int oc, int R) {
@@ -1036,14 +1196,14 @@ extern "C" int spn_sum_tc_prepare(const float* lw, int nsd, int c, int oc, int R
             cudaError_t e = cudaFuncSetAttribute(tc_wimage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return spn_cuda_status(e);
         }
-        tc_wimage_kernel<<<nsd * (K / 8), 256, smem, st>>>(lw, logz, (uint8_t*)wimg, c, oc, R, P, RP, KS);
+        tc_wimage_kernel<<<nsd * (K / 8), 256, smem, st>>>(lw, logz, (uint8_t*)wimg, c, oc, R, P, ts_nl(P), RP, KS);
     } else {
-        tc_wimage_generic_kernel<<<spn_blocks(img_bytes / 16, 256), 256, 0, st>>>(lw, logz, (uint4*)wimg, nsd, c, oc, R, P);
+        tc_wimage_generic_kernel<<<spn_blocks(img_bytes / 16, 256), 256, 0, st>>>(lw, logz, (uint4*)wimg, nsd, c, oc, R, P, ts_nl(P));
     }
     int rc = spn_launch_status();
     if (rc != SPN_OK) return rc;
-    const int64_t nrows = img_bytes / 16;
-    tc_wimage_f_kernel<<<spn_blocks(nrows, 256), 256, 0, st>>>((const uint4*)wimg, (uint4*)((uint8_t*)wimg + img_bytes), P, ts_nl(P), nrows);
+    const int NL = ts_nl(P);
+    tc_wimage_f_kernel<<<nsd * R * (P / NL), 256, NL * P * P * 2, st>>>((const uint4*)wimg, (uint4*)((uint8_t*)wimg + img_bytes), P, NL);
     return spn_launch_status();
 }
 
@@ -1054,7 +1214,7 @@ extern "C" int64_t spn_sum_tc_fhand_bytes(int Bs, int nsd, int c, int oc, int R)
 }
 extern "C" int64_t spn_sum_tc_hand_bytes(int Bs, int nsd, int c, int oc, int R) {
     const int64_t P = ts_padded(c, oc);
-    return (int64_t)nsd * R * ((Bs + 127) / 128) * (P / 2) * 512 + 1024;
+    return (int64_t)nsd * R * ((Bs + 127) / 128) * (16 * (ts_kp((int)P) / 8) * 128) + 1024;
 }
 
 extern "C" int spn_sum_tc_fwd(const float* x, const void* wimg, const float* lw, const float* logz, int Bs, int nsets, int d_in,
@@ -1080,7 +1240,7 @@ extern "C" int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g
     cudaStream_t st = (cudaStream_t)stream;
     TsArgs a{};
     a.wimg = (const uint8_t*)wimg;   // image A
-    a.out = out; a.g = g; a.y = dx; a.hand = (uint8_t*)hand; a.fhand_r = (const uint8_t*)fhand;
+    a.y = dx; a.hand = (const uint8_t*)hand; a.fhand_r = (const uint8_t*)fhand;
     a.Bs = Bs; a.nsets = nsets; a.Btot = Bs * nsets; a.d_in = d_in; a.d_out = d_out; a.R = R; a.c = c; a.oc = oc;
     ts_split(a);
     // G pre-pass: G tiles (read by this call's kernel and by spn_sum_tc_bwd_w) and, optionally, the column sums of g
@@ -1088,25 +1248,12 @@ extern "C" int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g
         cudaError_t e = cudaMemsetAsync(csum, 0, (size_t)nsets * d_out * oc * R * sizeof(float), st);
         if (e != cudaSuccess) return spn_cuda_status(e);
     }
-    const size_t gsmem = (size_t)(P / 2) * 512 + 128 * 4 + P * 4;
+    const size_t gsmem = (size_t)16 * (ts_kp(P) / 8) * 128 + 128 * 4 + P * 4;
     tc_gprep_kernel<<<nsets * d_out * R * a.ntiles, 128, gsmem, st>>>(out, g, (const uint8_t*)fhand, (uint8_t*)hand, csum, Bs,
                                                                   Bs * nsets, d_out, oc, R, P, a.ntiles);
     int rc = spn_launch_status();
     if (rc != SPN_OK) return rc;
     return dispatch_tsum<TS_DX>(P, a, st);
-}
-
-extern "C" int spn_debug_tc_prof(unsigned long long* out_host, int reset) {
-    unsigned long long v[24] = {0};
-    cudaError_t e = cudaMemcpyFromSymbol(v, g_tc3_prof, sizeof(v));
-    if (e != cudaSuccess) return spn_cuda_status(e);
-    if (out_host) for (int i = 0; i < 24; ++i) out_host[i] = v[i];
-    if (reset) {
-        unsigned long long z[24] = {0};
-        e = cudaMemcpyToSymbol(g_tc3_prof, z, sizeof(z));
-        if (e != cudaSuccess) return spn_cuda_status(e);
-    }
-    return SPN_OK;
 }
 
 // debug: number of CTAs that hit the bounded-wait timeout since the library was loaded (synchronises).  A non-zero count

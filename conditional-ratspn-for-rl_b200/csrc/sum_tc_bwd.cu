@@ -14,11 +14,10 @@ using namespace tc;
 
 __device__ int g_tc_bwd_aborts = 0;
 
-#ifdef SPN_TC_DEBUGSW
-#define BWD_DEBUG(a) ((a).debug)
-#else
-#define BWD_DEBUG(a) 0   // experiment switches exist only in the profiling build
+#ifndef SPN_TC_BWD_DEBUG_MODE
+#define SPN_TC_BWD_DEBUG_MODE 0   // compile-time experiment switch (timing only): 1 no MMA issue, 3 generators idle
 #endif
+#define BWD_DEBUG(a) SPN_TC_BWD_DEBUG_MODE
 
 struct TcBwdArgs {
     unsigned int* counter;   // work counter of this launch (dynamic item scheduling), zeroed by the host
@@ -26,7 +25,7 @@ struct TcBwdArgs {
     const uint8_t* hand;  // per (set, s, r, row tile): G tile (B-operand layout), written by the dX kernel
     float* dwt;           // [nsd][R][P*P][P] linear-domain weight gradient (padded channel counts)
     int B, d_in, d_out, R;   // B = rows per weight set, d_out = weight sets x scopes (the hand-off index does not separate them)
-    int ntiles, debug;    // debug (SPN_TC_DEBUG, timing experiments only): 1 no MMA issue, 3 generators idle
+    int ntiles;
 };
 
 // Issues the 8 MMAs (K = 16 rows each) of one (tile, chunk): D[128 k x NPAD] (+)= A[128 k x 128 rows] * B[128 rows x NPAD],
@@ -75,8 +74,9 @@ __global__ void __launch_bounds__(320, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
     constexpr int NCHUNK = (NBLK + 1) / 2;
     constexpr int NPAIR = C / 2;
     constexpr int A_BYTES = 128 * 128 * 2;     // [16 row-groups][16 m-groups][8][8] bf16
-    constexpr int V_BYTES = NPAIR * 512;       // one hand-off tile: eL / eR as [pair][128 rows] words, G as [16][CB][8][8] bf16
-    constexpr int G_BYTES = V_BYTES + 1024;    // + aliased N-group overrun (N = NPAD > OC reads one block past the tile)
+    constexpr int V_BYTES = NPAIR * 512;       // one hand-off vector tile: eL / eR as [pair][128 rows] words
+    constexpr int KG = NPAD / 8;               // o-groups of the G tile, padded to the MMA's N (zero pad groups)
+    constexpr int G_BYTES = 16 * KG * 128;     // G tile: [16 row groups][KG][8 rows][8 bf16]
     static_assert(GC * NPAD <= 512 && OC == C && NSTA >= 2 && NSTA <= 4, "unsupported shape");   // NSTA: A ring depth
     constexpr uint32_t IDESC = instr_desc_bf16(128, NPAD, 1, 1);
 
@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(320, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
                 const uint32_t vb = m_tile & 1;
                 mbar_wait_sticky(vec_full + vb, (m_tile >> 1) & 1, abort_flag);   // G operand tile of this row tile
                 fence_after_sync();
-                // B[K = row, N = o] MN-major: 8-element groups along N 128 B apart, 8-row groups CB*128 B
-                const uint64_t bdesc = smem_desc(gbuf_addr + vb * G_BYTES, CB * 128, 128);
+                // B[K = row, N = o] MN-major: 8-element groups along N 128 B apart, 8-row groups KG*128 B
+                const uint64_t bdesc = smem_desc(gbuf_addr + vb * G_BYTES, KG * 128, 128);
 #pragma unroll 1
                 for (int ch = 0; ch < nch; ++ch, ++m_stage) {
                     const uint32_t st = m_stage % NSTA, par = (m_stage / NSTA) & 1;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(320, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
                     fence_after_sync();
                     // A[M = k, K = row] MN-major: 8-element groups along M are 128 B apart, 8-row groups along K 2048 B
                     const uint64_t adesc = smem_desc(abuf_addr + st * A_BYTES, 2048, 128);
-                    if (BWD_DEBUG(a) != 1) dw_issue_chunk(tmem_base + ch * NPAD, adesc, bdesc, IDESC, tile ? 1u : 0u, (2 * CB * 128) >> 4);
+                    if (BWD_DEBUG(a) != 1) dw_issue_chunk(tmem_base + ch * NPAD, adesc, bdesc, IDESC, tile ? 1u : 0u, (2 * KG * 128) >> 4);
                     mma_commit_uniform(a_empty + st);
                 }
                 mma_commit_uniform(g_empty + vb);
@@ -166,10 +166,10 @@ __global__ void __launch_bounds__(320, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
                 mbar_wait_sticky(g_empty + vb, ((n_tile >> 1) & 1) ^ 1, abort_flag);
                 if (lane == 0) {
                     const uint8_t* src = a.fhand + ((size_t)sr * a.ntiles + tile) * (2 * V_BYTES + 1024);
-                    mbar_arrive_expect_tx(vec_full + vb, 3 * V_BYTES);
+                    mbar_arrive_expect_tx(vec_full + vb, 2 * V_BYTES + G_BYTES);
                     bulk_g2s(Ls + vb * NPAIR * 128, src, V_BYTES, vec_full + vb);
                     bulk_g2s(Rs + vb * NPAIR * 128, src + V_BYTES, V_BYTES, vec_full + vb);
-                    bulk_g2s(gbuf + vb * G_BYTES, a.hand + ((size_t)sr * a.ntiles + tile) * V_BYTES, V_BYTES, vec_full + vb);
+                    bulk_g2s(gbuf + vb * G_BYTES, a.hand + ((size_t)sr * a.ntiles + tile) * G_BYTES, G_BYTES, vec_full + vb);
                 }
                 __syncwarp();
             }
@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(320, 1) sum_tc_bwd_w_kernel(TcBwdArgs a, int n
                     if (lane == 0) mbar_arrive(a_full + st);
                 }
                 n_stage += nch;
+                fence_proxy_async();   // ordinary loads of eL / eR are ordered before the TMA engine's next write into the buffers
                 __syncwarp();
                 if (lane == 0) mbar_arrive(vec_empty + vb);  // eL / eR of this tile are no longer read by this warp
             }
@@ -388,7 +389,7 @@ template <int C, int OC, int NPAD, int GC, int NSTA>
 static int launch_bwd_w(const TcBwdArgs& a, cudaStream_t st) {
     constexpr int NCHUNK = ((C / 8) * (C / 8) + 1) / 2;
     constexpr int NGROUPS = (NCHUNK + GC - 1) / GC;
-    constexpr int SMEM = NSTA * 128 * 128 * 2 + 2 * ((C / 2) * 512 + 1024) + 2 * 2 * (C / 2) * 512 + (2 * 4 + 7) * 8 + 16;
+    constexpr int SMEM = NSTA * 128 * 128 * 2 + 2 * NPAD * 256 + 2 * 2 * (C / 2) * 512 + (2 * 4 + 7) * 8 + 16;
     static_assert(SMEM <= 232448, "shared memory budget");
     static std::atomic<unsigned long long> configured{0};
     int dev = 0, sms = 148;
@@ -424,12 +425,6 @@ extern "C" int spn_sum_tc_bwd_w(const void* fhand, const void* hand, const float
     a.fhand = (const uint8_t*)fhand; a.hand = (const uint8_t*)hand; a.dwt = dwt_workspace;
     a.B = Bs; a.d_in = d_in; a.d_out = nsd; a.R = R;
     a.ntiles = (Bs + 127) / 128;
-#ifdef SPN_TC_DEBUGSW
-    {
-        const char* dbg = getenv("SPN_TC_DEBUG");
-        a.debug = dbg ? atoi(dbg) : 0;
-    }
-#endif
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     switch (P) {   // <P, P, N = P padded to 16, chunks per item (GC * N <= 512 TMEM columns), A ring depth>

@@ -8,7 +8,7 @@
 
 // suspend-time hint of mbarrier.try_wait (ns) and the number of tries before a wait gives up (~2 s in total)
 #ifndef SPN_MBAR_HINT_NS
-#define SPN_MBAR_HINT_NS 100000
+#define SPN_MBAR_HINT_NS 0   // measured: no hint is 3 - 10 % faster on every tensor-core kernel (profiles/README.md, round 2)
 #endif
 #define SPN_MBAR_TRIES (2000000000ull / (SPN_MBAR_HINT_NS > 1000 ? SPN_MBAR_HINT_NS : 1000))
 

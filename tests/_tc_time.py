@@ -37,16 +37,3 @@ if "kern" in sys.argv[1:] or which == "all":
     for e in sorted(prof.key_averages(), key=lambda e: -e.device_time_total):
         if e.device_type.name == "CUDA":
             print(f"  {e.device_time_total / e.count / 1e3:8.3f} ms x{e.count:3d}  {e.key[:90]}")
-import os, ctypes
-if os.environ.get("SPN_TC_PROFILE"):
-    from ratspn_b200 import _abi
-    buf = (ctypes.c_ulonglong * 24)()
-    names = ["e.wait_vec", "e.wait_acc", "e.chunks", "e.finalize", "e.wait_ld", "e.tiles", "p.wait_x", "p.compute", "p.bar", "p.wait_vec_empty",
-             "p.write", "p.tiles", "m.wait_w", "m.wait_vec", "m.wait_acc_empty", "m.wait_w_chunk", "m.issue", "m.tiles"]
-    for tag, fn in (("fwd", lambda: ops.tc_sum_forward(x, wimg, lw, None, fhand)),
-                    ("dx", lambda: ops.tc_sum_backward_x(x, out, go, wimg, lw, fhand, hand))):
-        _abi.lib().spn_debug_tc_prof(buf, 1)
-        fn(); torch.cuda.synchronize()
-        _abi.lib().spn_debug_tc_prof(buf, 0)
-        n = max(1, buf[5])
-        print(tag, "clk per tile (CTA 0):", " ".join(f"{names[i]}={buf[i]/n:.0f}" for i in range(18) if names[i] != "-"))

@@ -1,7 +1,7 @@
 #!/bin/bash
+# tensor-core kernel cycle: parity tests of the tcgen05 path, then kernel timings (product build + any experiment builds)
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_tc.py tests/test_gpu_tc_general.py -q -x > gpurun_out/r02_tc_tests_v8.log 2>&1; echo "tc pytest rc=$?"
-tail -5 gpurun_out/r02_tc_tests_v8.log
-timeout 300 python tests/_tc_time.py > gpurun_out/r02_tc_time_v8.txt 2>&1; echo "tc_time rc=$?"; cat gpurun_out/r02_tc_time_v8.txt
-SPN_TC_PROFILE=1 python conditional-ratspn-for-rl_b200/build.py --force > /dev/null 2>&1; echo "profile build rc=$?"
-SPN_TC_PROFILE=1 timeout 300 python tests/_tc_time.py > gpurun_out/r02_tc_prof_v8.txt 2>&1; echo "rc=$?"; tail -3 gpurun_out/r02_tc_prof_v8.txt
+TAG=${1:-r02_tc}
+timeout 900 python -m pytest tests/test_gpu_tc.py tests/test_gpu_tc_general.py -q -x > gpurun_out/${TAG}_tests.log 2>&1; echo "tc pytest rc=$?"
+tail -5 gpurun_out/${TAG}_tests.log
+bash tools/gpu_variants.sh ${TAG}_time all
