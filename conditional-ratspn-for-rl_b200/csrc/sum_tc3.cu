@@ -91,7 +91,7 @@ __host__ __device__ constexpr int ts_ncol(int P, int blk_cols, int li, int v) {
 template <int P, int MODE>
 __host__ __device__ constexpr int ts_smem_bytes() {
     const int npair = P / 2;
-    const int vec = MODE == TS_FWD ? (TS_NXS * 128 * P * 4 /* x ring */ + 2 * npair * 512 /* packed eL, two tiles */)
+    const int vec = MODE == TS_FWD ? (TS_NXS * 128 * P * 4 /* x ring */ + 2 * npair * 512 /* packed eL, two tiles */ + npair * 512 /* output staging */)
                                    : (2 * 16 * (ts_kp(P) / 8) * 128 /* G tiles (A operand), K padded */ + 2 * npair * 512 /* packed eL */ +
                                       2 * P * 128 * 4 /* aL shares of the two halves */);
     return ts_wbytes(P) + TS_ZERO + vec + 2 * 2 * 128 * 4 /* shifts */ + 32 * 8 /* barriers */ + 16;
@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(864, 1) tsum_fwd_kernel(TsArgs a) {
     float* Xr = reinterpret_cast<float*>(zero + TS_ZERO);      // [TS_NXS][128][c] fp32 rows staged by TMA
     uint32_t* ELp = reinterpret_cast<uint32_t*>(Xr + TS_NXS * XS_FLOATS);   // [2 buf][NPAIR][128] packed eL
     float* Ms = reinterpret_cast<float*>(ELp + 2 * NPAIR * 128);            // [2 buf][2][128] row shifts mL, mR
-    uint64_t* vec_full = reinterpret_cast<uint64_t*>(Ms + 2 * 2 * 128);   // [2]  prologue -> epilogue
+    float* OST = Ms + 2 * 2 * 128;                                          // [64][oc] staging of the upper half of an output tile
+    uint64_t* vec_full = reinterpret_cast<uint64_t*>(OST + NPAIR * 128);  // [2]  prologue -> epilogue
     uint64_t* vec_empty = vec_full + 2;                                  // [2]  epilogue -> prologue
     uint64_t* acc_full = vec_empty + 2;                                  // [NB] MMA commit -> epilogue
     uint64_t* acc_empty = acc_full + 4;                                  // [NB] epilogue -> MMA
@@ -495,22 +496,38 @@ __global__ void __launch_bounds__(864, 1) tsum_fwd_kernel(TsArgs a) {
                 }
                 const float* my_m = Ms + vb * 256 + row;
                 const float shift = my_m[0] + my_m[128];
-                float* op = a.y + (((int64_t)it.s * a.R + it.r) * a.Btot + it.row0 + (valid ? b : 0)) * oc + col0;
+                // ---- the output tile [rows][oc] is staged in shared memory and written by the TMA engine (one thread per row
+                // writing 8-byte pieces of a strided row straight to global memory costs 32 sectors per instruction: measured
+                // 0.3 ms of a 0.6 ms kernel).  Rows 0..63 go to this tile's (no longer needed) packed-eL buffer, rows 64..127
+                // to a buffer of their own.
+                ts_named_bar(1, 512);   // every epilogue warp is done with eL of this tile
+                float* st = (row < 64 ? reinterpret_cast<float*>(ELp + vb * NPAIR * 128) + row * oc : OST + (row - 64) * oc) + col0;
                 bool bad = false;
 #pragma unroll
                 for (int j = 0; j < QC / 2; ++j) {
                     float s0, s1;
                     f2unpack(acc2[j], s0, s1);
-                    const bool on = valid && col0 + 2 * j < oc;
-                    bad |= on && !(fminf(s0, s1) >= 1e-30f);
-                    if (on && TS_DBG != 14)
-                        *reinterpret_cast<float2*>(op + 2 * j) = make_float2(fmaf(lg2_approx(s0), 0.6931471805599453f, shift),
+                    const bool on = col0 + 2 * j < oc;
+                    bad |= on && valid && !(fminf(s0, s1) >= 1e-30f);
+                    if (on)
+                        *reinterpret_cast<float2*>(st + 2 * j) = make_float2(fmaf(lg2_approx(s0), 0.6931471805599453f, shift),
                                                                              fmaf(lg2_approx(s1), 0.6931471805599453f, shift));
                 }
-                if (bad && !TS_DBG) ts_exact_row(a, it.sg, it.s, it.r, it.row0 + b, col0, QC, op);
+                if (bad && !TS_DBG) ts_exact_row(a, it.sg, it.s, it.r, it.row0 + b, col0, QC, st);
+                fence_proxy_async();    // staging writes -> visible to the TMA engine
+                ts_named_bar(1, 512);
+                if (warp == 8 && lane == 0 && TS_DBG != 14) {
+                    const int rows = min(128, a.Bs - tile * 128);
+                    float* op = a.y + (((int64_t)it.s * a.R + it.r) * a.Btot + it.row0 + (int64_t)tile * 128) * oc;
+                    bulk_s2g(op, ELp + vb * NPAIR * 128, (uint32_t)min(rows, 64) * oc * 4);
+                    if (rows > 64) bulk_s2g(op + 64 * oc, OST, (uint32_t)(rows - 64) * oc * 4);
+                    bulk_commit_group();
+                    bulk_wait_group_read<0>();   // both staging buffers have been read
+                }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(vec_empty + vb);   // eL / shifts of this buffer set are no longer read
+                if (lane == 0) mbar_arrive(vec_empty + vb);   // eL / shifts / staging of this buffer set are free
             }
+            if (warp == 8 && lane == 0) bulk_wait_group<0>();
         }
     }
     // teardown
@@ -726,8 +743,6 @@ __global__ void __launch_bounds__(352, 1) tsum_dx_kernel(TsArgs a) {
             for (int t = 0; t < nt; ++t, ++n_tile) {
                 const int tile = it.tile_begin + t;
                 const uint32_t vb = n_tile & 1;
-                const int64_t b = (int64_t)tile * 128 + row;
-                const bool valid = b < a.Bs;
                 uint64_t er2[HC / 2];
 #pragma unroll
                 for (int j = 0; j < HC / 2; ++j) er2[j] = f2pack(bf16_lo(er_next[j]), bf16_hi(er_next[j]));
@@ -750,6 +765,9 @@ __global__ void __launch_bounds__(352, 1) tsum_dx_kernel(TsArgs a) {
                     fence_after_sync();
                     if (!TS_SKIP_EPI && TS_DBG != 4) ts_tmem_load<TC>(tmem_base + buf * NCOLS + my_col, d[0]);
                 }
+                // the previous tile's bulk stores have read the staging area: its owner (the share buffer) may be written again
+                if (threadIdx.x == 0) bulk_wait_group_read<0>();
+                ts_named_bar(1, 256);
 #pragma unroll 1
                 for (int ch = 0; ch < NCH; ++ch, ++n_chunk) {
                     const uint32_t buf = n_chunk % NB;
@@ -791,36 +809,51 @@ __global__ void __launch_bounds__(352, 1) tsum_dx_kernel(TsArgs a) {
                         }
                     }
                 }
-                // dxR[r'] = eR[r'] * aR[r'] for this half's right channels
+                // ---- tile results: dxR[r'] = eR[r'] * aR[r'], dxL[l] = eL[l] * aL[l] (this half's channels), staged in shared
+                // memory as two contiguous [rows][c] tiles and written by the TMA engine (one thread per row writing 16-byte
+                // pieces of a strided row straight to global memory costs 32 sectors per instruction: measured 0.37 ms of a
+                // 0.8 ms kernel).  The staging area is the share buffer, so: shares complete -> everybody reads its sums ->
+                // everybody writes results -> bulk stores -> (next tile) the stores have read the buffer.
+                ts_named_bar(1, 256);   // both halves' shares of aL are in shared memory
+                float xl[HC];
+#pragma unroll
+                for (int j2 = 0; j2 < HC / 2; ++j2) {
+                    const int l = h * HC + 2 * j2;
+                    const float* sp = SL + l * 128 + row;
+                    const uint32_t w = up[(l >> 1) * 128];
+                    xl[2 * j2] = bf16_lo(w) * (sp[0] + sp[P * 128]);
+                    xl[2 * j2 + 1] = bf16_hi(w) * (sp[128] + sp[P * 128 + 128]);
+                }
+                fence_proxy_async();    // ordinary loads of eL are ordered before the TMA engine's next write into the buffer
+                ts_named_bar(1, 256);   // the shares (and eL) have been read
+                if (lane == 0) mbar_arrive(u_empty + vb);
                 {
-                    float* dp = a.y + (((int64_t)(2 * it.s + 1) * a.R + it.r) * a.Btot + it.row0 + b) * c + h * HC;
+                    float* ol = SL + row * c + h * HC;              // staging: [2 children][128 rows][c]
+                    float* orr = ol + 128 * c;
 #pragma unroll
                     for (int j4 = 0; j4 < HC / 4; ++j4) {
                         const uint64_t p0 = mul2(er2[2 * j4], ar2[2 * j4]), p1 = mul2(er2[2 * j4 + 1], ar2[2 * j4 + 1]);
                         float v0, v1, v2, v3;
                         f2unpack(p0, v0, v1);
                         f2unpack(p1, v2, v3);
-                        if (valid && it.has_r && h * HC + 4 * j4 < c && TS_DBG != 14) *reinterpret_cast<float4*>(dp + 4 * j4) = make_float4(v0, v1, v2, v3);
+                        if (h * HC + 4 * j4 < c) {
+                            *reinterpret_cast<float4*>(orr + 4 * j4) = make_float4(v0, v1, v2, v3);
+                            *reinterpret_cast<float4*>(ol + 4 * j4) = make_float4(xl[4 * j4], xl[4 * j4 + 1], xl[4 * j4 + 2], xl[4 * j4 + 3]);
+                        }
                     }
                 }
-                ts_named_bar(1, 256);   // both halves' shares of aL are in shared memory
-                {
-                    // dxL[l] = eL[l] * aL[l] for the left channels of this half
-                    float* dp = a.y + (((int64_t)(2 * it.s) * a.R + it.r) * a.Btot + it.row0 + b) * c + h * HC;
-#pragma unroll
-                    for (int j4 = 0; j4 < HC / 4; ++j4) {
-                        const int l = h * HC + 4 * j4;
-                        const float* sp = SL + l * 128 + row;
-                        const uint32_t w0 = up[(l >> 1) * 128], w1 = up[((l >> 1) + 1) * 128];
-                        const float4 v = make_float4(bf16_lo(w0) * (sp[0] + sp[P * 128]), bf16_hi(w0) * (sp[128] + sp[P * 128 + 128]),
-                                                     bf16_lo(w1) * (sp[256] + sp[P * 128 + 256]), bf16_hi(w1) * (sp[384] + sp[P * 128 + 384]));
-                        if (valid && it.has_l && l < c && TS_DBG != 14) *reinterpret_cast<float4*>(dp + 4 * j4) = v;
-                    }
+                fence_proxy_async();    // staging writes -> visible to the TMA engine
+                ts_named_bar(1, 256);
+                if (threadIdx.x == 0 && TS_DBG != 14) {
+                    const int rows = min(128, a.Bs - tile * 128);
+                    const uint32_t bytes = (uint32_t)rows * c * 4;
+                    const int64_t r0 = it.row0 + (int64_t)tile * 128;
+                    if (it.has_l) bulk_s2g(a.y + (((int64_t)(2 * it.s) * a.R + it.r) * a.Btot + r0) * c, SL, bytes);
+                    if (it.has_r) bulk_s2g(a.y + (((int64_t)(2 * it.s + 1) * a.R + it.r) * a.Btot + r0) * c, SL + 128 * c, bytes);
+                    bulk_commit_group();
                 }
-                fence_proxy_async();    // ordinary loads of eL are ordered before the TMA engine's next write into the buffer
-                ts_named_bar(1, 256);   // the shares have been read: the next tile may overwrite them
-                if (lane == 0) mbar_arrive(u_empty + vb);
             }
+            if (threadIdx.x == 0) bulk_wait_group<0>();   // results of this item are in global memory before the kernel can end
         }
     }
     // teardown
