@@ -591,11 +591,12 @@ def main():
         traffic_src = ncu.get("_source", None)
         kernels = {}
         # algorithmic flops per call: forward, dX, dW = one [B x 1600] x [1600 x 40] contraction per (scope,
-        # repetition) each.  The dX call EXECUTES two forward-shaped GEMMs (one per child, opg_kernel<DXR> + <DXL>): that
-        # figure is reported separately and is not what `frac` is computed from.
-        for key, name, t, executed in (("fwd", "opg_kernel<FWD> (spn_sum_tc_fwd)", t_fwd, 1),
-                                       ("dx", "opg_kernel<DXL>+<DXR> (spn_sum_tc_bwd_x)", t_bx, 2),
-                                       ("dw", "sum_tc_bwd_w_kernel (spn_sum_tc_bwd_w, incl. gsum + finish)", t_bw, 1)):
+        # repetition) each.  Executed = algorithmic for all three: forward and dX run ONE small-K GEMM per row tile on the
+        # tensor cores (M = 128, K = 40 padded to 48, N = 1600) plus the contraction over the left channels on the fp32
+        # pipe out of tensor memory.
+        for key, name, t, executed in (("fwd", "tsum_fwd_kernel (spn_sum_tc_fwd)", t_fwd, 1),
+                                       ("dx", "tsum_dx_kernel (spn_sum_tc_bwd_x, incl. the G pre-pass)", t_bx, 1),
+                                       ("dw", "sum_tc_bwd_w_kernel (spn_sum_tc_bwd_w, incl. finish)", t_bw, 1)):
             ach = fl / (t / 1e3) / 1e12
             kernels[key] = {"call": name, "layer": "S_1 (d=16, K=1600, N=40, R=40)", "ms": t, "algorithmic_flops": fl,
                             "achieved_tflops": ach, "frac": ach / peak, "executed_flops": executed * fl,

@@ -500,19 +500,20 @@ __global__ void __launch_bounds__(864, 1) tsum_fwd_kernel(TsArgs a) {
                 // writing 8-byte pieces of a strided row straight to global memory costs 32 sectors per instruction: measured
                 // 0.3 ms of a 0.6 ms kernel).  Rows 0..63 go to this tile's (no longer needed) packed-eL buffer, rows 64..127
                 // to a buffer of their own.
-                ts_named_bar(1, 512);   // every epilogue warp is done with eL of this tile
-                float* st = (row < 64 ? reinterpret_cast<float*>(ELp + vb * NPAIR * 128) + row * oc : OST + (row - 64) * oc) + col0;
+                float2 ov[QC / 2];
                 bool bad = false;
 #pragma unroll
-                for (int j = 0; j < QC / 2; ++j) {
+                for (int j = 0; j < QC / 2; ++j) {   // before the barrier: the MUFU work overlaps the wait for the slowest warp
                     float s0, s1;
                     f2unpack(acc2[j], s0, s1);
-                    const bool on = col0 + 2 * j < oc;
-                    bad |= on && valid && !(fminf(s0, s1) >= 1e-30f);
-                    if (on)
-                        *reinterpret_cast<float2*>(st + 2 * j) = make_float2(fmaf(lg2_approx(s0), 0.6931471805599453f, shift),
-                                                                             fmaf(lg2_approx(s1), 0.6931471805599453f, shift));
+                    bad |= valid && col0 + 2 * j < oc && !(fminf(s0, s1) >= 1e-30f);
+                    ov[j] = make_float2(fmaf(lg2_approx(s0), 0.6931471805599453f, shift), fmaf(lg2_approx(s1), 0.6931471805599453f, shift));
                 }
+                ts_named_bar(1, 512);   // every epilogue warp is done with eL of this tile
+                float* st = (row < 64 ? reinterpret_cast<float*>(ELp + vb * NPAIR * 128) + row * oc : OST + (row - 64) * oc) + col0;
+#pragma unroll
+                for (int j = 0; j < QC / 2; ++j)
+                    if (col0 + 2 * j < oc) *reinterpret_cast<float2*>(st + 2 * j) = ov[j];
                 if (bad && !TS_DBG) ts_exact_row(a, it.sg, it.s, it.r, it.row0 + b, col0, QC, st);
                 fence_proxy_async();    // staging writes -> visible to the TMA engine
                 ts_named_bar(1, 512);

@@ -32,6 +32,10 @@ class Leaf(AbstractLayer):
         self.out_shape = f"(N, {in_features}, {out_channels})"
         self.marginalization_constant = nn.Parameter(th.zeros(1), requires_grad=False)
 
+    def __setstate__(self, state):
+        super().__setstate__(state)   # a pickle written by the reference lacks the host copy of the dropout probability
+        self.__dict__.setdefault("_dropout_p", float(self.dropout.detach().cpu()) if "dropout" in self._parameters else 0.0)
+
     def _apply_dropout(self, x: th.Tensor) -> th.Tensor:
         if self._dropout_p > 0.0 and self.training:
             x = x.masked_fill(th.rand_like(x) < self._dropout_p, 0.0)

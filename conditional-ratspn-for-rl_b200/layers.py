@@ -56,6 +56,16 @@ class Sum(AbstractLayer):
         state["_tc_cache"] = {}  # derived device buffers are not part of a checkpoint
         return state
 
+    def __setstate__(self, state):
+        """Also accepts a pickle written by the reference implementation (th.save(model), rat_spn.py:1046-1047): its
+        Sum layers carry none of this implementation's host-side attributes, which get their defaults here."""
+        super().__setstate__(state)
+        d = self.__dict__
+        d.setdefault("_dropout_p", float(self.dropout.detach().cpu()) if "dropout" in self._parameters else 0.0)
+        d.setdefault("_input_cache_fused", None)
+        d.setdefault("_raw_weights", False)
+        d["_tc_cache"] = {}
+
     def invalidate_weight_cache(self):
         """Drop the cached operand image (needed only after writing to ``weight_param.data`` behind autograd's back;
         in-place updates of the Parameter itself are detected through its version counter)."""

@@ -99,6 +99,15 @@ class RatSpn(nn.Module):
         self._test_noise = None
 
     # ------------------------------------------------------------------------------------------ construction
+
+    def __setstate__(self, state):
+        """Also accepts a whole-model pickle written by the reference implementation (rat_spn.py:1046-1047,
+        cspn.py:324-327) once ``install_as_reference_modules()`` has mapped its module names onto this package."""
+        super().__setstate__(state)
+        self.__dict__.setdefault("_perm_cache", None)
+        self.__dict__.setdefault("_test_noise", None)
+        self.__dict__["_perm_cache"] = None
+
     def _build(self):
         """leaf -> X_0 -> [S_j -> X_j] for j = 1..D-1 -> root   (rat_spn.py:246-300)."""
         cfg = self.config
@@ -226,6 +235,8 @@ class RatSpn(nn.Module):
         caching = self.root._is_input_cache_enabled
         if self._tensor_core_path_ok(x, caching):
             return self._forward_tensor_core(x, layer_index, perm32, detach_params)
+        if self._tensor_core_sets_path_ok(x, caching, layer_index):
+            return self._forward_tensor_core_sets(x, perm32, detach_params)
         h = self._leaf(x, detach_params=detach_params, perm32=perm32)
         for li in range(1, min(layer_index, self.max_layer_index - 1) + 1):
             layer = self._inner_layers[li - 1]
@@ -261,6 +272,42 @@ class RatSpn(nn.Module):
         if cfg.D > 2 and cfg.I != cfg.S:
             pass  # S_1 pairs leaf channels (c = I), the layers above pair sum channels (c = S); both must be supported
         return ops.tc_supported(cfg.I, cfg.S, cfg.R) and (cfg.D == 2 or ops.tc_supported(cfg.S, cfg.S, cfg.R))
+
+    def _tensor_core_sets_path_ok(self, x: th.Tensor, caching: bool, layer_index: int) -> bool:
+        """Per-conditional weights (CSPN, cspn.py:254-301) with MANY rows per weight set -- the entropy estimate scores
+        K * n samples per conditional, a wide conditional circuit a whole batch: every inner Sum layer is then one dense
+        contraction per weight set and runs on the tcgen05 kernels batched over the sets."""
+        cfg = self.config
+        if cfg.is_ratspn or not self.use_tensor_cores or caching or cfg.D < 2 or layer_index != self.max_layer_index:
+            return False
+        w = x.shape[-4]
+        rows_per_set = x.numel() // (w * x.shape[-3] * x.shape[-2] * x.shape[-1])
+        if rows_per_set < self.tensor_core_min_rows:
+            return False
+        for layer in self._inner_layers:
+            if isinstance(layer, Sum) and (layer.weight_param is None or layer.weight_param.shape[0] != w):
+                return False
+        return ops.tc_supported(cfg.I, cfg.S, cfg.R) and (cfg.D == 2 or ops.tc_supported(cfg.S, cfg.S, cfg.R))
+
+    def _forward_tensor_core_sets(self, x, perm32, detach_params):
+        """Leaf and root on the per-conditional fp32 kernels (reference layout), the inner Sum layers on the tensor-core
+        kernels with the activations in the internal layout [scope, repetition, set-major rows, channel]."""
+        batch_shape, w = x.shape[:-4], x.shape[-4]
+        h = self._leaf(x, detach_params=detach_params, perm32=perm32)               # [*batch, w, d0, I, R]
+        d0, I, R = h.shape[-3:]
+        h = h.reshape(-1, w, d0, I, R).permute(2, 4, 1, 0, 3)                       # [d0, R, w, rows, I]
+        rows = h.shape[3]
+        h = h.reshape(d0, R, w * rows, I)
+        for li in range(2, self.max_layer_index, 2):
+            layer = self._inner_layers[li - 1]
+            if layer._raw_weights:   # fused weight normalisation: the raw head outputs go in
+                wt = layer.weight_param.detach() if detach_params else layer.weight_param
+                h = ops.sum_forward_tc(h, wt, True, None)
+            else:
+                h = ops.sum_forward_tc(h, layer._weights_for(detach_params), False, None)
+        d, c = h.shape[0], h.shape[3]
+        h = h.reshape(d, R, w, rows, c).permute(3, 2, 0, 4, 1).reshape(*batch_shape, w, d, c, R)
+        return ops.sum_forward(h, self.root._weights_for(detach_params), "xroot")
 
     def _forward_tensor_core(self, x, layer_index, perm32, detach_params):
         """Same evaluation with activations in the internal [scope, repetition, row, channel] layout and every inner
@@ -312,8 +359,13 @@ class RatSpn(nn.Module):
 
     def sample(self, mode: str = None, n: Union[int, Tuple] = 1, class_index=None, evidence: th.Tensor = None,
                is_mpe: bool = False, layer_index: int = None, do_sample_postprocessing: bool = True,
-               post_processing_kwargs: dict = None, noise: Optional[List[th.Tensor]] = None) -> Sample:
+               post_processing_kwargs: dict = None, noise: Optional[List[th.Tensor]] = None,
+               seed: Optional[int] = None, sample_offset: int = 0) -> Sample:
         """Ancestral sampling; arguments and the returned ``Sample`` follow rat_spn.py:348-498.
+
+        ``seed`` / ``sample_offset`` (extension, index mode, batch-sharded sampling over several GPUs): the in-kernel
+        Philox noise is keyed by (seed, global sample index), so a rank that draws samples [sample_offset, sample_offset
+        + n) of a job with the job's common ``seed`` gets exactly the rows the single-GPU call with that seed returns.
 
         ``noise`` (extension, used by the parity tests): list of noise tensors consumed in the reference's draw
         order -- one Gumbel tensor [nodes, *n, w, d, ic, r] per Sum layer top-down, then the leaf's standard-normal
@@ -340,7 +392,8 @@ class RatSpn(nn.Module):
                          sampled_with_evidence=evidence is not None)
             fuse_post = do_sample_postprocessing and not post_processing_kwargs
             if mode == 'index':
-                ctx, fused = self._sample_index(ctx, class_index, evidence, layer_index, fuse_post, noise)
+                ctx, fused = self._sample_index(ctx, class_index, evidence, layer_index, fuse_post, noise, seed,
+                                                sample_offset)
             elif mode == 'onehot':
                 from .diffsample import sample_onehot
                 ctx, fused = sample_onehot(self, ctx, class_index, evidence, layer_index, noise, fuse_post)
@@ -353,7 +406,8 @@ class RatSpn(nn.Module):
     def _num_weight_sets(self) -> int:
         return self._leaf.base_leaf.mean_param.shape[0]
 
-    def _sample_index(self, ctx: Sample, class_index, evidence, layer_index, fuse_post, noise):
+    def _sample_index(self, ctx: Sample, class_index, evidence, layer_index, fuse_post, noise, user_seed=None,
+                      sample_offset=0):
         cfg = self.config
         dev = self.device
         n = tuple(ctx.n)
@@ -366,6 +420,14 @@ class RatSpn(nn.Module):
             Qe = 1
         is_mpe = ctx.is_mpe
         seed = ops.new_seed(dev, is_mpe or noise is not None)  # host integer; a device word under graph capture
+        if user_seed is not None and not is_mpe and noise is None:
+            seed = int(user_seed)
+        q_off = 0
+        if sample_offset:
+            # items are enumerated (node, *n, conditional): a constant shift only when there is a single root node
+            assert len(n) == 1 and (class_index is not None or cfg.C == 1) and layer_index == self.max_layer_index, \
+                "sample_offset needs a one-dimensional sample count and a single root node (C = 1 or class_index)"
+            q_off = int(sample_offset) * w
 
         def take(shape):
             if is_mpe or noise is None:
@@ -401,7 +463,7 @@ class RatSpn(nn.Module):
             g = take((*lead, 1, K, 1))
             xc = self.root._input_cache_fused if self.root._is_input_cache_enabled else None
             lwt, tr = column_major(lwr)
-            k0 = ops.sample_sum(lwt, cfg.R, Q, 1, 1, pa, (1, 0, 0), False, None, xc, Qe, g, is_mpe, seed, transposed=tr)
+            k0 = ops.sample_sum(lwt, cfg.R, Q, 1, 1, pa, (1, 0, 0), False, None, xc, Qe, g, is_mpe, seed, q_offset=q_off, transposed=tr)
             k0 = k0.view(Q)
             rep = th.div(k0, ic_top, rounding_mode='floor').to(th.int32)
             parent = (k0 - rep * ic_top).to(th.int32).view(Q, 1, 1)
@@ -430,7 +492,7 @@ class RatSpn(nn.Module):
                 xc = layer._input_cache_fused if layer._is_input_cache_enabled else None
                 lwt, tr = column_major(layer.weights)
                 parent = ops.sample_sum(lwt, 0, Q, d, Rs, pa, (1, 0, 0), False, None, xc, Qe, g, is_mpe, seed,
-                                        transposed=tr)
+                                        q_offset=q_off, transposed=tr)
                 parent_strides = (d * Rs, Rs, 1)
                 start = layer_index - 1
 
@@ -444,7 +506,7 @@ class RatSpn(nn.Module):
             xc = layer._input_cache_fused if layer._is_input_cache_enabled else None
             lwt, tr = column_major(layer.weights)
             parent = ops.sample_sum(lwt, 0, Q, d, Rs, parent, parent_strides, True, rep, xc, Qe, g, is_mpe,
-                                    seed, transposed=tr)
+                                    seed, q_offset=q_off, transposed=tr)
             parent_strides = (d * Rs, Rs, 1)
 
         base = self._leaf.base_leaf
@@ -458,7 +520,7 @@ class RatSpn(nn.Module):
             ev_strides = (cfg.F * ev.shape[-2] * r_ev, ev.shape[-2] * r_ev, 1 if r_ev > 1 else 0)
         squash = bool(fuse_post and cfg.tanh_squash and ctx.needs_squashing)
         y, ch = ops.sample_leaf(base.means, base.stds, Q, self._leaf.cardinality, Rs, parent, parent_strides, rep, eps,
-                                is_mpe, inv32, ev, ev_strides, Qe, squash, True, seed)
+                                is_mpe, inv32, ev, ev_strides, Qe, squash, True, seed, q_offset=q_off)
         ctx.parent_indices = ch.view(*lead, cfg.F, Rs).long()
         if rep is not None:
             ctx.repetition_indices = rep.view(*lead).long()

@@ -146,4 +146,47 @@ def test_model_with_unequal_leaf_and_sum_channels_takes_the_tensor_core_path():
     (-out.mean()).backward()
     for k, p in m.named_parameters():
         if p.requires_grad:
-            check(p.grad, raw[k].grad, k, tol=1e-2, mean_tol=1e-3)
+            # weight parameters are stored unnormalised: their gradient is the difference of two nearly equal terms (softmax
+            # backward), which doubles the bf16 operand error of the activations below them
+            tol = 2e-2 if k.endswith("weight_param") else 1e-2
+            check(p.grad, raw[k].grad, k, tol=tol, mean_tol=1e-3)
+
+
+@pytest.mark.parametrize("fuse", [False, True])
+def test_cspn_with_many_rows_per_conditional_takes_the_tensor_core_path(fuse):
+    """CSPN (gating net -> per-conditional weights, cspn.py:254-301) evaluated on 300 rows per conditional: the inner Sum
+    layers run on the tcgen05 kernels batched over the weight sets.  LL and the gradients w.r.t. the gating network
+    against the same model on the exact fp32 kernels (which are pinned to the reference's golden vectors)."""
+    import ratspn_b200 as rb
+    torch.manual_seed(5)
+    np.random.seed(5)
+    cfg = rb.CspnConfig()
+    cfg.F_cond = (6,)
+    cfg.F, cfg.R, cfg.D, cfg.I, cfg.S, cfg.C = 32, 3, 3, 8, 16, 1
+    cfg.dropout = 0.0
+    cfg.leaf_base_class = rb.RatNormal
+    cfg.leaf_base_kwargs = {"min_sigma": 0.05, "max_sigma": 1.0}
+    cfg.tanh_squash = False
+    cfg.feat_layers, cfg.sum_param_layers, cfg.dist_param_layers = [8], [8], [8]
+    cfg.cond_layers_inner_act = torch.nn.LeakyReLU
+    cfg.fuse_weight_norm = fuse
+    m = rb.CSPN(cfg).to(DEV)
+    w, n = 3, 300
+    cond = torch.randn(w, 6, device=DEV)
+    x = torch.randn(n, w, 32, 1, 1, device=DEV)
+    x[7, 1, ::5] = float("nan")
+    res = []
+    for tc in (True, False):
+        m.use_tensor_cores = tc
+        m.zero_grad(set_to_none=True)
+        m.set_params(cond)
+        assert m._tensor_core_sets_path_ok(x, False, m.max_layer_index) == tc
+        ll = m(x, condition=None)
+        (-ll.mean()).backward()
+        res.append((ll.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+    (ll_t, g_t), (ll_e, g_e) = res
+    rel = ((ll_t - ll_e).abs() / ll_e.abs().clamp_min(1.0)).max().item()
+    assert rel < 1e-4, f"relative LL error {rel}"
+    assert set(g_t) == set(g_e)
+    for k in g_e:
+        check(g_t[k], g_e[k].cpu(), k, tol=2e-2, mean_tol=2e-3)
