@@ -63,6 +63,7 @@ SIGNATURES = {
     "spn_sum_tc_bwd_x": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "spn_sum_tc_bwd_w": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     "spn_debug_tc_aborts": [_P],
+    "spn_debug_tc_prof": [_P, _I],
     "spn_root_shared_supported": [_I, _I, _I],
     "spn_root_shared_fwd": [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P],
     "spn_root_shared_bwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],

@@ -35,6 +35,17 @@
 using namespace tc;
 
 __device__ int g_tc3_aborts = 0;
+// Per-phase clock hooks of the dX epilogue (build with SPN_TC_PROFILE=1; warp 0 of CTA 0 accumulates, see spn_debug_tc_prof)
+__device__ unsigned long long g_tc3_prof[12];
+#ifdef SPN_TC_PROFILE
+#define TSP_DECL long long tsp_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tsp_t = clock64()
+#define TSP_LAP(slot) do { const long long tsp_n = clock64(); tsp_acc[slot] += tsp_n - tsp_t; tsp_t = tsp_n; } while (0)
+#define TSP_FLUSH() do { if (blockIdx.x == 0 && threadIdx.x == 0) for (int q = 0; q < 12; ++q) atomicAdd(&g_tc3_prof[q], (unsigned long long)tsp_acc[q]); } while (0)
+#else
+#define TSP_DECL do { } while (0)
+#define TSP_LAP(slot) do { } while (0)
+#define TSP_FLUSH() do { } while (0)
+#endif
 
 enum { TS_FWD = 0, TS_DX = 1 };
 
@@ -136,10 +147,12 @@ __device__ __forceinline__ float lg2_approx(float x) {
 // load N (even, <= 64) consecutive columns of this thread's TMEM lane with the widest instructions available
 template <int N>
 __device__ __forceinline__ void ts_tmem_load(uint32_t taddr, uint32_t* r) {
-    static_assert(N % 2 == 0 && N <= 64, "unsupported column count");
+    static_assert(N % 2 == 0 && N <= 128, "unsupported column count");
     int done = 0;
     if constexpr (N >= 32) { tmem_ld32(taddr, r); done = 32; }
     if constexpr (N >= 64) { tmem_ld32(taddr + 32, r + 32); done = 64; }
+    if constexpr (N >= 96) { tmem_ld32(taddr + 64, r + 64); done = 96; }
+    if constexpr (N >= 128) { tmem_ld32(taddr + 96, r + 96); done = 128; }
     if constexpr ((N % 32) >= 16) { tmem_ld16(taddr + done, r + done); done += 16; }
     if constexpr ((N % 16) >= 8) { tmem_ld8(taddr + done, r + done); done += 8; }
     if constexpr ((N % 8) >= 4) { tmem_ld4(taddr + done, r + done); done += 4; }
@@ -547,9 +560,7 @@ __global__ void __launch_bounds__(864, 1) tsum_fwd_kernel(TsArgs a) {
 //               the right channels, all left channels.  Every accumulator element dE[l, r'] is loaded ONCE and used twice:
 //               aR[r'] += eL[l] * dE (kept in registers over the tile: complete when the tile ends) and
 //               aL[l] += eR[r'] * dE (a dot product over the thread's right channels; the two halves combine their partial
-//               sums through shared memory, plain stores -- shared-memory fp32 atomics are CAS loops).  The loads are
-//               software pipelined by half chunks: the tcgen05.ld of the next half chunk is in flight while the FFMA2s of
-//               the current one issue, so two warps per scheduler keep the fp32 pipe busy.
+//               sums through shared memory, plain stores -- shared-memory fp32 atomics are CAS loops).
 //   warp 8      MMA issuer (SS: the G tile in shared memory is the A operand).
 //   warp 9      weight TMA.    warp 10   TMA of the per-tile operands: G tile (double buffered), packed eL (double
 //               buffered) and eR (single buffer: the epilogue threads take their values into registers at once).
@@ -564,8 +575,7 @@ __global__ void __launch_bounds__(352, 1) tsum_dx_kernel(TsArgs a) {
     constexpr int NCOLS = NL * P;
     constexpr int NB = ts_nb(P);
     constexpr int HC = P / 2;                  // right channels per epilogue thread
-    constexpr int NLH = NL / 2;                // left channels per load step (half chunk)
-    constexpr int TC = NLH * HC;               // accumulator columns per epilogue thread and load step
+    constexpr int TC = NL * HC;                // accumulator columns per epilogue thread and chunk
     constexpr int NPAIR = P / 2;
     constexpr bool RESIDENT = ts_resident(P);
     constexpr int NSLOT = ts_nslot(P);
@@ -575,7 +585,7 @@ __global__ void __launch_bounds__(352, 1) tsum_dx_kernel(TsArgs a) {
     constexpr int FH_BYTES = 2 * NPAIR * 512 + 1024;
     constexpr int GS_BYTES = 16 * KG * 128;            // G tile: [16 row groups][KG][8 rows][8 bf16], pad K groups are zero
     static_assert(P % 8 == 0 && P >= 8 && P <= 64 && NL % 2 == 0 && P % NL == 0, "unsupported channel count");
-    static_assert(NB >= 2 && NB * NCOLS <= 512 && HC % 4 == 0 && TC <= 64, "TMEM / register budget");
+    static_assert(NB >= 2 && NB * NCOLS <= 512 && HC % 4 == 0 && TC <= 128, "TMEM / register budget");
     constexpr int W_MMA = 8, W_WTMA = 9, W_VTMA = 10;
 
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -724,11 +734,12 @@ __global__ void __launch_bounds__(352, 1) tsum_dx_kernel(TsArgs a) {
                 }
                 mma_commit_uniform(g_empty + vb);   // the G stage may be refilled
             }
-        } else {
+        } else if (warp < 8) {
             // =============================================== epilogue ===============================================
             const int h = warp >> 2;
             const int row = (warp & 3) * 32 + lane;
             const uint32_t my_col = ((uint32_t)((warp & 3) * 32) << 16) + h * (NL * HC);
+            TSP_DECL;
             // This half's eR values come straight from the forward's hand-off in global memory (coalesced: lanes = consecutive
             // rows of one packed word), one tile ahead: the loads of tile t + 1 are in flight during tile t.
             auto er_ptr = [&](int tile) {
@@ -752,70 +763,62 @@ __global__ void __launch_bounds__(352, 1) tsum_dx_kernel(TsArgs a) {
 #pragma unroll
                     for (int j = 0; j < HC / 2; ++j) er_next[j] = __ldg(ep + j * 128);
                 }
+                TSP_LAP(0);   // er unpack / prefetch issue
                 mbar_wait_sticky(u_full + vb, (n_tile >> 1) & 1, abort_flag);
+                TSP_LAP(1);   // wait for eL
                 const uint32_t* up = Us + vb * NPAIR * 128 + row;
                 float* slp = SL + h * P * 128 + row;
                 uint64_t ar2[HC / 2];
 #pragma unroll
                 for (int j = 0; j < HC / 2; ++j) ar2[j] = 0ull;
-                // load steps k = 0 .. 2 NCH - 1 (two per chunk), register double buffer
-                uint32_t d[2][TC];
-                {
-                    const uint32_t buf = n_chunk % NB;
-                    mbar_wait_sticky(acc_full + buf, (n_chunk / NB) & 1, abort_flag);
-                    fence_after_sync();
-                    if (!TS_SKIP_EPI && TS_DBG != 4) ts_tmem_load<TC>(tmem_base + buf * NCOLS + my_col, d[0]);
-                }
-                // the previous tile's bulk stores have read the staging area: its owner (the share buffer) may be written again
-                if (threadIdx.x == 0) bulk_wait_group_read<0>();
-                ts_named_bar(1, 256);
+                // Chunk loop.  tcgen05.ld has ~400 clk of latency and tcgen05.wait::ld waits for ALL loads of the thread, so
+                // the kernel is bound by the accumulator bytes in flight: every thread fetches its whole share of a chunk
+                // (NL x P/2 columns) with one batch of loads, then issues the FFMA2s; the two warps of a scheduler alternate.
 #pragma unroll 1
                 for (int ch = 0; ch < NCH; ++ch, ++n_chunk) {
                     const uint32_t buf = n_chunk % NB;
+                    mbar_wait_sticky(acc_full + buf, (n_chunk / NB) & 1, abort_flag);
+                    fence_after_sync();
+                    TSP_LAP(ch == 0 ? 8 : 2);   // wait for the accumulator (first chunk of the tile / others)
+                    uint32_t d[TC];
+                    if (!TS_SKIP_EPI && TS_DBG != 4) ts_tmem_load<TC>(tmem_base + buf * NCOLS + my_col, d);
+                    const int l0 = ch * NL;
+                    uint32_t elw[NL / 2];
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        tmem_wait_ld();   // load step (ch, half) is in d[half]
-                        if (half == 1) {   // both halves of the chunk have been read: the accumulator may be overwritten
-                            fence_before_sync();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(acc_empty + buf);
-                        }
-                        // next load step
-                        if (half == 0) {
-                            if (!TS_SKIP_EPI && TS_DBG != 4) ts_tmem_load<TC>(tmem_base + buf * NCOLS + my_col + NLH * HC, d[1]);
-                        } else if (ch + 1 < NCH) {
-                            const uint32_t nbuf = (n_chunk + 1) % NB;
-                            mbar_wait_sticky(acc_full + nbuf, ((n_chunk + 1) / NB) & 1, abort_flag);
-                            fence_after_sync();
-                            if (!TS_SKIP_EPI && TS_DBG != 4) ts_tmem_load<TC>(tmem_base + nbuf * NCOLS + my_col, d[0]);
-                        }
-                        if (TS_SKIP_EPI || TS_DBG == 3) continue;
-                        const int l0 = ch * NL + half * NLH;
+                    for (int u = 0; u < NL / 2; ++u) elw[u] = up[((l0 >> 1) + u) * 128];
+                    tmem_wait_ld();
+                    TSP_LAP(3);   // tcgen05.ld issue + latency
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + buf);   // the accumulator may be overwritten
+                    TSP_LAP(4);   // release
+                    if (TS_SKIP_EPI || TS_DBG == 3) continue;
 #pragma unroll
-                        for (int u = 0; u < NLH; ++u) {
-                            const uint32_t w = up[((l0 + u) >> 1) * 128];
-                            const float el = ((l0 + u) & 1) ? bf16_hi(w) : bf16_lo(w);
-                            const uint64_t e2 = f2pack(el, el);
-                            uint64_t s0 = 0ull, s1 = 0ull;
+                    for (int u = 0; u < NL; ++u) {
+                        const float el = (u & 1) ? bf16_hi(elw[u >> 1]) : bf16_lo(elw[u >> 1]);
+                        const uint64_t e2 = f2pack(el, el);
+                        uint64_t s0 = 0ull, s1 = 0ull;
 #pragma unroll
-                            for (int j = 0; j < HC / 2; ++j) {
-                                const uint64_t d2 = u2pack(d[half][u * HC + 2 * j], d[half][u * HC + 2 * j + 1]);
-                                ar2[j] = fma2(e2, d2, ar2[j]);
-                                if (j & 1) s1 = fma2(er2[j], d2, s1); else s0 = fma2(er2[j], d2, s0);
-                            }
-                            float p0, p1, p2, p3;
-                            f2unpack(s0, p0, p1);
-                            f2unpack(s1, p2, p3);
-                            slp[(l0 + u) * 128] = (p0 + p1) + (p2 + p3);   // this half's share of aL[l]
+                        for (int j = 0; j < HC / 2; ++j) {
+                            const uint64_t d2 = u2pack(d[u * HC + 2 * j], d[u * HC + 2 * j + 1]);
+                            ar2[j] = fma2(e2, d2, ar2[j]);
+                            if (j & 1) s1 = fma2(er2[j], d2, s1); else s0 = fma2(er2[j], d2, s0);
                         }
+                        float p0, p1, p2, p3;
+                        f2unpack(s0, p0, p1);
+                        f2unpack(s1, p2, p3);
+                        slp[(l0 + u) * 128] = (p0 + p1) + (p2 + p3);   // this half's share of aL[l]
                     }
+                    TSP_LAP(5);   // FFMA2s
                 }
-                // ---- tile results: dxR[r'] = eR[r'] * aR[r'], dxL[l] = eL[l] * aL[l] (this half's channels), staged in shared
-                // memory as two contiguous [rows][c] tiles and written by the TMA engine (one thread per row writing 16-byte
-                // pieces of a strided row straight to global memory costs 32 sectors per instruction: measured 0.37 ms of a
-                // 0.8 ms kernel).  The staging area is the share buffer, so: shares complete -> everybody reads its sums ->
-                // everybody writes results -> bulk stores -> (next tile) the stores have read the buffer.
+                // ---- tile results: dxR[r'] = eR[r'] * aR[r'], dxL[l] = eL[l] * aL[l] (this half's channels).  A thread owns 80-byte
+                // pieces of strided rows (32 sectors per store instruction if written directly: measured 0.37 ms of a 0.8 ms
+                // kernel), and a TMA bulk store or a single copy warp needs > 2000 clk for the 40 KB of a tile, so the two
+                // [rows][c] tiles are staged in shared memory (in the share buffer) and copied out by all epilogue threads
+                // with coalesced 16-byte accesses: shares complete -> everybody reads its sums -> everybody stages its results
+                // -> everybody copies -> the buffer is free for the next tile's shares.
                 ts_named_bar(1, 256);   // both halves' shares of aL are in shared memory
+                TSP_LAP(10);   // first tile-end barrier
                 float xl[HC];
 #pragma unroll
                 for (int j2 = 0; j2 < HC / 2; ++j2) {
@@ -843,18 +846,33 @@ __global__ void __launch_bounds__(352, 1) tsum_dx_kernel(TsArgs a) {
                         }
                     }
                 }
-                fence_proxy_async();    // staging writes -> visible to the TMA engine
-                ts_named_bar(1, 256);
-                if (threadIdx.x == 0 && TS_DBG != 14) {
+                ts_named_bar(1, 256);   // the results are staged
+                if (TS_DBG != 14) {
                     const int rows = min(128, a.Bs - tile * 128);
-                    const uint32_t bytes = (uint32_t)rows * c * 4;
+                    const int n4 = rows * c / 4;                   // float4 per child tile
                     const int64_t r0 = it.row0 + (int64_t)tile * 128;
-                    if (it.has_l) bulk_s2g(a.y + (((int64_t)(2 * it.s) * a.R + it.r) * a.Btot + r0) * c, SL, bytes);
-                    if (it.has_r) bulk_s2g(a.y + (((int64_t)(2 * it.s + 1) * a.R + it.r) * a.Btot + r0) * c, SL + 128 * c, bytes);
-                    bulk_commit_group();
+                    const int tid = threadIdx.x;                   // 0 .. 255
+#pragma unroll
+                    for (int child = 0; child < 2; ++child) {
+                        if (!(child ? it.has_r : it.has_l)) continue;
+                        const float4* src = reinterpret_cast<const float4*>(SL + child * 128 * c);
+                        float4* dst = reinterpret_cast<float4*>(a.y + (((int64_t)(2 * it.s + child) * a.R + it.r) * a.Btot + r0) * c);
+                        float4 v[P / 8];                           // 128 * P / 4 float4 over 256 threads
+#pragma unroll
+                        for (int k = 0; k < P / 8; ++k)
+                            if (tid + k * 256 < n4) v[k] = src[tid + k * 256];
+#pragma unroll
+                        for (int k = 0; k < P / 8; ++k)
+                            if (tid + k * 256 < n4) dst[tid + k * 256] = v[k];
+                    }
                 }
+                ts_named_bar(1, 256);   // the staging area (= the share buffer) may be written again
+                TSP_LAP(6);   // tile end
+#ifdef SPN_TC_PROFILE
+                tsp_acc[7] += 1;   // tiles
+#endif
             }
-            if (threadIdx.x == 0) bulk_wait_group<0>();   // results of this item are in global memory before the kernel can end
+            TSP_FLUSH();
         }
     }
     // teardown
@@ -1288,6 +1306,19 @@ extern "C" int spn_sum_tc_bwd_x(const float* x, const float* out, const float* g
     int rc = spn_launch_status();
     if (rc != SPN_OK) return rc;
     return dispatch_tsum<TS_DX>(P, a, st);
+}
+
+extern "C" int spn_debug_tc_prof(unsigned long long* out_host, int reset) {
+    unsigned long long v[12] = {0};
+    cudaError_t e = cudaMemcpyFromSymbol(v, g_tc3_prof, sizeof(v));
+    if (e != cudaSuccess) return spn_cuda_status(e);
+    if (out_host) for (int i = 0; i < 12; ++i) out_host[i] = v[i];
+    if (reset) {
+        unsigned long long z[12] = {0};
+        e = cudaMemcpyToSymbol(g_tc3_prof, z, sizeof(z));
+        if (e != cudaSuccess) return spn_cuda_status(e);
+    }
+    return SPN_OK;
 }
 
 // debug: number of CTAs that hit the bounded-wait timeout since the library was loaded (synchronises).  A non-zero count

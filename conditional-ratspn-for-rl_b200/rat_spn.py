@@ -578,7 +578,8 @@ class RatSpn(nn.Module):
             elif ctx.sampling_mode == 'onehot' and ctx.parent_indices is not None and not ctx.has_rep_dim:
                 sel = (inv * ctx.parent_indices.detach().sum(-2).long()).sum(-1)
             else:
-                sel = inv.view(*([1] * (sample.dim() - 2)), *inv.shape)
+                # one selector per repetition for every sample; the scope dim of split samples is added below
+                sel = inv.view(*([1] * (sample.dim() - 2 - int(ctx.is_split_by_scope))), *inv.shape)
             if ctx.is_split_by_scope:
                 sel = sel.unsqueeze(1)
             sample = th.gather(sample, dim=-2 if ctx.has_rep_dim else -1, index=sel.expand_as(sample))

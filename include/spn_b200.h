@@ -294,6 +294,10 @@ int spn_root_shared_bwd(const float* x, int d_in, const float* lw, const float* 
 
 /* Debug aid (synchronises): number of CTAs that gave up on an mbarrier wait since the library was loaded. */
 int spn_debug_tc_aborts(int* out_host);
+/* Debug aid (synchronises): in builds with SPN_TC_PROFILE=1 warp 0 of CTA 0 of the spn_sum_tc_bwd_x kernel accumulates clock64
+ * deltas per epilogue phase (see tests/_tc_time.py for the slot names); copies the 12 counters
+ * to out_host (host pointer) and optionally resets them (all zero in the product build). */
+int spn_debug_tc_prof(unsigned long long* out_host, int reset);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Sum-level combination of the recursive entropy approximation (rat_spn.py:661-746 with weigh_tensors :591-623):

@@ -37,3 +37,13 @@ if "kern" in sys.argv[1:] or which == "all":
     for e in sorted(prof.key_averages(), key=lambda e: -e.device_time_total):
         if e.device_type.name == "CUDA":
             print(f"  {e.device_time_total / e.count / 1e3:8.3f} ms x{e.count:3d}  {e.key[:90]}")
+import os, ctypes
+if os.environ.get("SPN_TC_PROFILE"):
+    from ratspn_b200 import _abi
+    buf = (ctypes.c_ulonglong * 12)()
+    names = ["er", "wait_eL", "wait_acc(ch>0)", "tmem_ld", "release", "ffma2", "tile_end_rest", "tiles", "wait_acc(ch=0)", "wait_stage", "tile_end_bar1"]
+    _abi.lib().spn_debug_tc_prof(buf, 1)
+    ops.tc_sum_backward_x(x, out, go, wimg, lw, fhand, hand); torch.cuda.synchronize()
+    _abi.lib().spn_debug_tc_prof(buf, 0)
+    n = max(1, buf[7])
+    print("dx epilogue clk per tile (CTA 0, warp 0):", " ".join(f"{names[i]}={buf[i]/n:.0f}" for i in (0, 1, 8, 2, 3, 4, 9, 5, 10, 6)), f"tiles={buf[7]}")
