@@ -1058,6 +1058,44 @@ __global__ void __launch_bounds__(256) tc_wimage_kernel(const float* __restrict_
     }
 }
 
+// Same for wide layers (the [8][oc][R] slab would need > 64 KB of shared memory: one block per SM, measured 0.56 TB/s at
+// oc = R = 64): a block takes a chunk of RC = 16 repetitions of the slab (64-byte runs: whole sectors), blockIdx.y = chunk.
+// Requires R % 4 == 0.
+__global__ void __launch_bounds__(256) tc_wimage_rchunk_kernel(const float* __restrict__ lw, const float* __restrict__ logz,
+                                                              uint8_t* __restrict__ wimg, int c, int OC, int R, int P, int NL) {
+    constexpr int RC = 16, RP = RC + 1;
+    extern __shared__ float tile[];  // [8][KS], row (kk, o) at kk * KS + o * RP
+    const int KS = OC * RP + ((9 - (OC * RP) % 32) + 32) % 32;
+    const int K = c * c, CG = P / 8, cg = c / 8;
+    const int kgr = blockIdx.x % (K / 8);
+    const int s = blockIdx.x / (K / 8);
+    const int l = kgr / cg, rg = kgr % cg;
+    const int r0 = blockIdx.y * RC, rc = min(RC, R - r0), q4 = rc / 4;
+    const float* src = lw + ((int64_t)s * K + (int64_t)kgr * 8) * OC * R + r0;
+    const float* zp = logz ? logz + (int64_t)s * OC * R + r0 : nullptr;
+    for (int i = threadIdx.x; i < 8 * OC * q4; i += blockDim.x) {
+        const int q = i % q4, ko = i / q4;          // ko = kk * OC + o
+        const int o = ko % OC, kk = ko / OC;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)ko * R) + q);
+        const float4 z = zp ? __ldg(reinterpret_cast<const float4*>(zp + (int64_t)o * R) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float* t = tile + kk * KS + o * RP + 4 * q;
+        t[0] = __expf(v.x - z.x); t[1] = __expf(v.y - z.y); t[2] = __expf(v.z - z.z); t[3] = __expf(v.w - z.w);
+    }
+    __syncthreads();
+    const int NOG = OC / 8;
+    uint4* dst = reinterpret_cast<uint4*>(wimg);
+    for (int i = threadIdx.x; i < NOG * 8 * rc; i += blockDim.x) {
+        const int kk = i & 7, og = (i >> 3) % NOG, rr = i / (8 * NOG);
+        const float* t = tile + kk * KS + og * 8 * RP + rr;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(t[0], t[RP]), p1 = __floats2bfloat162_rn(t[2 * RP], t[3 * RP]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(t[4 * RP], t[5 * RP]), p3 = __floats2bfloat162_rn(t[6 * RP], t[7 * RP]);
+        uint4 v;
+        v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
+        v.z = *reinterpret_cast<uint32_t*>(&p2); v.w = *reinterpret_cast<uint32_t*>(&p3);
+        dst[((int64_t)s * R + r0 + rr) * ((int64_t)P * CG * CG * 8) + ts_image_a_row(P, NL, l, rg * 8 + kk, og)] = v;
+    }
+}
+
 // Image A for channel counts that are multiples of 4 only: one thread per 16-byte image row (strided reads; such layers are small).
 __global__ void __launch_bounds__(256) tc_wimage_generic_kernel(const float* __restrict__ lw, const float* __restrict__ logz,
                                                                uint4* __restrict__ wimg, int S, int c, int OC, int R, int P, int NL) {
@@ -1239,7 +1277,15 @@ extern "C" int spn_sum_tc_prepare(const float* lw, int nsd, int c, int oc, int R
     const int RP = R | 1;
     const int KS = oc * RP + ((9 - (oc * RP) % 32) + 32) % 32;
     const size_t smem = (size_t)8 * KS * sizeof(float);
-    if (c % 8 == 0 && oc % 8 == 0 && smem <= 200 * 1024) {
+    if (c % 8 == 0 && oc % 8 == 0 && R % 4 == 0 && smem > 64 * 1024) {
+        if (P != c || P != oc) {
+            cudaError_t e = cudaMemsetAsync(wimg, 0, (size_t)img_bytes, st);
+            if (e != cudaSuccess) return spn_cuda_status(e);
+        }
+        const int RPc = 17, KSc = oc * RPc + ((9 - (oc * RPc) % 32) + 32) % 32;
+        dim3 grid(nsd * (K / 8), (R + 15) / 16);
+        tc_wimage_rchunk_kernel<<<grid, 256, (size_t)8 * KSc * sizeof(float), st>>>(lw, logz, (uint8_t*)wimg, c, oc, R, P, ts_nl(P));
+    } else if (c % 8 == 0 && oc % 8 == 0 && smem <= 200 * 1024) {
         if (P != c || P != oc) {
             cudaError_t e = cudaMemsetAsync(wimg, 0, (size_t)img_bytes, st);
             if (e != cudaSuccess) return spn_cuda_status(e);

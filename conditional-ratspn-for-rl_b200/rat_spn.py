@@ -236,7 +236,7 @@ class RatSpn(nn.Module):
         if self._tensor_core_path_ok(x, caching):
             return self._forward_tensor_core(x, layer_index, perm32, detach_params)
         if self._tensor_core_sets_path_ok(x, caching, layer_index):
-            return self._forward_tensor_core_sets(x, perm32, detach_params)
+            return self._forward_tensor_core_sets(x, layer_index, perm32, detach_params)
         h = self._leaf(x, detach_params=detach_params, perm32=perm32)
         for li in range(1, min(layer_index, self.max_layer_index - 1) + 1):
             layer = self._inner_layers[li - 1]
@@ -278,7 +278,7 @@ class RatSpn(nn.Module):
         K * n samples per conditional, a wide conditional circuit a whole batch: every inner Sum layer is then one dense
         contraction per weight set and runs on the tcgen05 kernels batched over the sets."""
         cfg = self.config
-        if cfg.is_ratspn or not self.use_tensor_cores or caching or cfg.D < 2 or layer_index != self.max_layer_index:
+        if cfg.is_ratspn or not self.use_tensor_cores or caching or cfg.D < 2 or layer_index < 2:
             return False
         w = x.shape[-4]
         rows_per_set = x.numel() // (w * x.shape[-3] * x.shape[-2] * x.shape[-1])
@@ -289,16 +289,22 @@ class RatSpn(nn.Module):
                 return False
         return ops.tc_supported(cfg.I, cfg.S, cfg.R) and (cfg.D == 2 or ops.tc_supported(cfg.S, cfg.S, cfg.R))
 
-    def _forward_tensor_core_sets(self, x, perm32, detach_params):
-        """Leaf and root on the per-conditional fp32 kernels (reference layout), the inner Sum layers on the tensor-core
-        kernels with the activations in the internal layout [scope, repetition, set-major rows, channel]."""
+    def _forward_tensor_core_sets(self, x, layer_index, perm32, detach_params):
+        """Leaf and root on the per-conditional fp32 kernels (reference layout), the inner Sum layers up to ``layer_index``
+        on the tensor-core kernels with the activations in the internal layout [scope, repetition, set-major rows,
+        channel].  (``layer_index`` below the root: the recursive entropy estimate scores the samples of every node of
+        a layer under the circuit below it, rat_spn.py:625-750.)"""
         batch_shape, w = x.shape[:-4], x.shape[-4]
-        h = self._leaf(x, detach_params=detach_params, perm32=perm32)               # [*batch, w, d0, I, R]
-        d0, I, R = h.shape[-3:]
-        h = h.reshape(-1, w, d0, I, R).permute(2, 4, 1, 0, 3)                       # [d0, R, w, rows, I]
-        rows = h.shape[3]
-        h = h.reshape(d0, R, w * rows, I)
-        for li in range(2, self.max_layer_index, 2):
+        if w == 1 and x.shape[-1] == 1 and x.shape[-2] == 1:   # a single conditional: the leaf kernel writes the internal layout (as for a RatSpn)
+            h = self._leaf(x, detach_params=detach_params, perm32=perm32, layout="drbc")    # [d0, R, rows, I]
+            d0, R, rows, I = h.shape
+        else:
+            h = self._leaf(x, detach_params=detach_params, perm32=perm32)           # [*batch, w, d0, I, R]
+            d0, I, R = h.shape[-3:]
+            h = h.reshape(-1, w, d0, I, R).permute(2, 4, 1, 0, 3)                   # [d0, R, w, rows, I]
+            rows = h.shape[3]
+            h = h.reshape(d0, R, w * rows, I)
+        for li in range(2, min(layer_index, self.max_layer_index - 1) + 1, 2):
             layer = self._inner_layers[li - 1]
             if layer._raw_weights:   # fused weight normalisation: the raw head outputs go in
                 wt = layer.weight_param.detach() if detach_params else layer.weight_param
@@ -306,8 +312,18 @@ class RatSpn(nn.Module):
             else:
                 h = ops.sum_forward_tc(h, layer._weights_for(detach_params), False, None)
         d, c = h.shape[0], h.shape[3]
+        if layer_index == self.max_layer_index and ops.root_shared_supported(c, self.config.C, R):
+            # root on the internal layout, one weight set at a time (few sets with many rows each in this regime)
+            lw_root = self.root._weights_for(detach_params)
+            outs = [ops.root_forward_shared(h[:, :, i * rows:(i + 1) * rows], lw_root[i:i + 1]) for i in range(w)]
+            out = outs[0] if w == 1 else th.stack(outs, dim=1)                      # [rows, (w,) C]
+            return out.reshape(*batch_shape, w, 1, self.config.C, 1)
         h = h.reshape(d, R, w, rows, c).permute(3, 2, 0, 4, 1).reshape(*batch_shape, w, d, c, R)
-        return ops.sum_forward(h, self.root._weights_for(detach_params), "xroot")
+        if layer_index == self.max_layer_index:
+            return ops.sum_forward(h, self.root._weights_for(detach_params), "xroot")
+        if layer_index % 2 == 1:   # the pass ends on a CrossProduct: materialise it
+            h = self._inner_layers[layer_index - 1](h)
+        return h
 
     def _forward_tensor_core(self, x, layer_index, perm32, detach_params):
         """Same evaluation with activations in the internal [scope, repetition, row, channel] layout and every inner

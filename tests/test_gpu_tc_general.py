@@ -190,3 +190,36 @@ def test_cspn_with_many_rows_per_conditional_takes_the_tensor_core_path(fuse):
     assert set(g_t) == set(g_e)
     for k in g_e:
         check(g_t[k], g_e[k].cpu(), k, tol=2e-2, mean_tol=2e-3)
+
+
+def test_cspn_recursive_entropy_with_gradients_takes_the_tensor_core_path():
+    """rat_spn.py:625-750 on a CSPN: every node's samples (K nodes x n samples per conditional = 320 rows per weight set) are
+    scored under the circuit below the layer -- dense per-conditional contractions, on the tensor-core kernels batched over
+    the weight sets.  Entropy value and its gradients w.r.t. the gating network against the exact fp32 kernels, same noise."""
+    import ratspn_b200 as rb
+    torch.manual_seed(9)
+    np.random.seed(9)
+    cfg = rb.CspnConfig()
+    cfg.F_cond = (6,)
+    cfg.F, cfg.R, cfg.D, cfg.I, cfg.S, cfg.C = 32, 2, 3, 16, 16, 1
+    cfg.dropout = 0.0
+    cfg.leaf_base_class = rb.RatNormal
+    cfg.leaf_base_kwargs = {"min_sigma": 0.05, "max_sigma": 1.0}
+    cfg.tanh_squash = False
+    cfg.feat_layers, cfg.sum_param_layers, cfg.dist_param_layers = [8], [8], [8]
+    cfg.cond_layers_inner_act = torch.nn.LeakyReLU
+    m = rb.CSPN(cfg).to(DEV)
+    cond = torch.randn(2, 6, device=DEV)
+    res = []
+    for tc in (True, False):
+        m.use_tensor_cores = tc
+        m.zero_grad(set_to_none=True)
+        torch.manual_seed(21)
+        H, _ = m.recursive_entropy_approx(condition=cond, sample_size=20)
+        H.sum().backward()
+        res.append((H.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+    (H_t, g_t), (H_e, g_e) = res
+    assert float((H_t - H_e).abs().max()) <= 2e-3 * float(H_e.abs().max()) + 1e-3, (H_t, H_e)
+    assert set(g_t) == set(g_e)
+    for k in g_e:
+        check(g_t[k], g_e[k].cpu(), k, tol=3e-2, mean_tol=3e-3)

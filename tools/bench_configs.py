@@ -265,14 +265,72 @@ def cfg5_narrow_train_raw(w=512):
     return res
 
 
+def cfg5_wide(rows=2048, w=1):
+    """BASELINE config 5 as named: wide conditional circuit R=64, S=I=64, D=6, F=1024; batch 16384 = 8 conditionals x 2048
+    rows sharded over 8 GPUs, i.e. ONE conditional with 2048 rows per GPU: every inner Sum layer is a dense
+    per-conditional contraction (4.3e12 flop forward) and runs on the tcgen05 kernels (P = 64, streamed weight images).
+    The weights are injected directly (a gating head of this width would be Linear(h, 5e8))."""
+    torch.manual_seed(0); np.random.seed(0)
+    cfg = rb.CspnConfig()
+    cfg.F_cond = (4,)
+    cfg.F, cfg.R, cfg.D, cfg.I, cfg.S, cfg.C = 1024, 64, 6, 64, 64, 1
+    cfg.dropout = 0.0
+    cfg.leaf_base_class = rb.RatNormal
+    cfg.leaf_base_kwargs = {"min_sigma": 0.001, "max_sigma": 1.0}
+    cfg.tanh_squash = False
+    cfg.feat_layers, cfg.sum_param_layers, cfg.dist_param_layers = [4], [4], [4]
+    m = rb.RatSpn.__new__(rb.CSPN)
+    rb.RatSpn.__init__(m, cfg)
+    m.replace_layer_params()
+    m = m.to(DEV)
+    params, flops = [], 0
+    for layer in list(m._inner_layers) + [m.root]:
+        if isinstance(layer, rb.Sum):
+            shape = (w, layer.in_features, layer.in_channels, layer.out_channels, layer.num_repetitions)
+            layer.weight_param = torch.log_softmax(torch.randn(shape, device=DEV), dim=2).requires_grad_(True)
+            params.append(layer.weight_param)
+            if layer is not m.root:
+                flops += 2 * rows * w * layer.weight_param[0].numel()
+        else:
+            layer.num_conditionals = w
+    base = m._leaf.base_leaf
+    base.mean_param = torch.randn(w, 1024, 64, 64, device=DEV).requires_grad_(True)
+    base.std_param = (torch.rand(w, 1024, 64, 64, device=DEV) * 0.9 + 0.05).requires_grad_(True)
+    params += [base.mean_param, base.std_param]
+    x = torch.randn(rows, w, 1024, 1, 1, device=DEV)
+    assert m._tensor_core_sets_path_ok(x, False, m.max_layer_index)
+    with torch.no_grad():
+        ms_f, l_f = timed(lambda: rb.RatSpn.forward(m, x), reps=5)
+
+    def step():
+        for p in params:
+            p.grad = None
+        (-rb.RatSpn.forward(m, x).mean()).backward()
+    ms_t, l_t = timed(step, reps=3)
+    m.use_tensor_cores = False
+    with torch.no_grad():
+        ms_e, _ = timed(lambda: rb.RatSpn.forward(m, x), reps=1, warmup=1)
+    peak = 1672.2
+    return {"config": f"cfg5-wide CSPN R=64 S=I=64 D=6 F=1024, {w} conditional(s) x {rows} rows per GPU (tcgen05 path, bf16 operands)",
+            "forward": {"ms": ms_f, "rows_per_s": rows * w / ms_f * 1e3, "sum_layer_flops": flops,
+                        "achieved_tflops": flops / ms_f / 1e9, "frac_of_bf16_peak": flops / ms_f / 1e9 / peak, "abi_calls": l_f},
+            "forward_backward": {"ms": ms_t, "rows_per_s": rows * w / ms_t * 1e3, "sum_layer_flops": 3 * flops,
+                                 "achieved_tflops": 3 * flops / ms_t / 1e9, "frac_of_bf16_peak": 3 * flops / ms_t / 1e9 / peak,
+                                 "abi_calls": l_t},
+            "forward_exact_fp32_kernels_ms": ms_e}
+
+
 CONFIGS = (("cfg1", cfg1), ("cfg3", cfg3), ("cfg4", cfg4), ("cfg5_narrow", cfg5_narrow),
-           ("cfg5_narrow_train", cfg5_narrow_train), ("cfg5_narrow_train_raw", cfg5_narrow_train_raw))
+           ("cfg5_narrow_train", cfg5_narrow_train), ("cfg5_narrow_train_raw", cfg5_narrow_train_raw), ("cfg5_wide", cfg5_wide))
 
 
 def main():
     out_path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "configs.json")
     res = {"device": torch.cuda.get_device_name(0), "lib": _abi.version()}
+    only = set(sys.argv[2:])   # optional: names of the configs to run
     for name, fn in CONFIGS:
+        if only and name not in only:
+            continue
         t0 = time.time()
         try:
             res[name] = fn()
