@@ -37,6 +37,31 @@ struct LeafTiledArgs {
 
 __host__ __device__ inline int leaf_ldx(int B) { return (B + 3) / 4 * 4; }
 
+// Packed fp32 arithmetic (two lanes of a 64-bit register pair per instruction, sm_100): the scalar sub / mul / fma chain of
+// the leaf kernels reads three distinct registers per instruction and is limited by register-file bandwidth (1.6 clk per
+// instruction measured, profiles/r02_pipe_bench.txt); the packed forms issue 2 FMAs per 2 clk with half the issue slots.
+__device__ __forceinline__ uint64_t lf_pack(float lo, float hi) {
+    uint64_t v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+__device__ __forceinline__ void lf_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t lf_add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t lf_mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t lf_fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 __global__ void __launch_bounds__(256) leaf_transpose_kernel(const float* __restrict__ x, int64_t sx_b, int64_t sx_f, int B,
                                                             int ldx, int F, float* __restrict__ xT, int* __restrict__ nanflag) {
     __shared__ float tile[32][33];
@@ -62,8 +87,8 @@ __global__ void __launch_bounds__(1024) leaf_tiled_fwd_kernel(LeafTiledArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int I4 = (int)(blockDim.x >> 5) * 4;
     float* xs = sm;                       // [2][FC][FROWS]
-    float* pm = sm + 2 * FC * FROWS;      // [FC][I4] mu
-    float* pa = pm + FC * I4;             // [FC][I4] 1 / (2 sigma^2)
+    float* pm = sm + 2 * FC * FROWS;      // [FC][I4] -mu
+    float* pa = pm + FC * I4;             // [FC][I4] -1 / (2 sigma^2)
     float* pk = pa + FC * I4;             // [FC][I4] log sigma + log sqrt(2 pi)
     float* ks = pk + FC * I4;             // [I4]     sum of pk over the chunk
     const int s = blockIdx.z, r = blockIdx.y;
@@ -91,11 +116,9 @@ __global__ void __launch_bounds__(1024) leaf_tiled_fwd_kernel(LeafTiledArgs a) {
         spn_cp_async_commit();
     };
 
-    float acc[4][4];
+    uint64_t acc2[4][2];   // [row u][channel pair]: (acc[u][2 vp], acc[u][2 vp + 1])
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+    for (int u = 0; u < 4; ++u) acc2[u][0] = acc2[u][1] = 0ull;
 
     if (nstages > 0) issue(0);
     for (int k = 0; k < nstages; ++k) {
@@ -113,7 +136,7 @@ __global__ void __launch_bounds__(1024) leaf_tiled_fwd_kernel(LeafTiledArgs a) {
                     av = 1.f / (2.f * sg * sg);
                     kv = logf(sg) + SPN_LOG_SQRT_2PI;
                 }
-                pm[j * I4 + pi] = m; pa[j * I4 + pi] = av; pk[j * I4 + pi] = kv;
+                pm[j * I4 + pi] = -m; pa[j * I4 + pi] = -av; pk[j * I4 + pi] = kv;   // negated: d = x + (-mu), acc += (d * -a) * d
             }
             __syncthreads();
             if (threadIdx.x < I4) {
@@ -134,22 +157,24 @@ __global__ void __launch_bounds__(1024) leaf_tiled_fwd_kernel(LeafTiledArgs a) {
                 const float4 m4 = *reinterpret_cast<const float4*>(pm + j * I4 + 4 * cg);
                 const float4 a4 = *reinterpret_cast<const float4*>(pa + j * I4 + 4 * cg);
                 const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
-                const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
-                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+                const uint64_t nm2[2] = {lf_pack(m4.x, m4.y), lf_pack(m4.z, m4.w)};
+                const uint64_t na2[2] = {lf_pack(a4.x, a4.y), lf_pack(a4.z, a4.w)};
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < 4; ++u) {
+                    const uint64_t x2 = lf_pack(xv[u], xv[u]);
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const float d = xv[u] - mv[v];
-                        acc[u][v] = fmaf(-(d * av[v]), d, acc[u][v]);
+                    for (int vp = 0; vp < 2; ++vp) {
+                        const uint64_t d2 = lf_add2(x2, nm2[vp]);                        // x - mu
+                        acc2[u][vp] = lf_fma2(lf_mul2(d2, na2[vp]), d2, acc2[u][vp]);   // -= (x - mu)^2 / (2 sigma^2)
                     }
+                }
             }
             const float4 k4 = *reinterpret_cast<const float4*>(ks + 4 * cg);
-            const float kv[4] = {k4.x, k4.y, k4.z, k4.w};
+            const uint64_t nk2[2] = {lf_pack(-k4.x, -k4.y), lf_pack(-k4.z, -k4.w)};
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int v = 0; v < 4; ++v) acc[u][v] -= kv[v];
+                for (int vp = 0; vp < 2; ++vp) acc2[u][vp] = lf_add2(acc2[u][vp], nk2[vp]);
         } else {
             // slow path: NaN -> contributes nothing; tanh change-of-variables correction per (row, feature)
             for (int j = 0; j < cnt; ++j) {
@@ -158,18 +183,21 @@ __global__ void __launch_bounds__(1024) leaf_tiled_fwd_kernel(LeafTiledArgs a) {
                 const float4 a4 = *reinterpret_cast<const float4*>(pa + j * I4 + 4 * cg);
                 const float4 k4 = *reinterpret_cast<const float4*>(pk + j * I4 + 4 * cg);
                 const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
-                const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
-                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+                const float nmv[4] = {m4.x, m4.y, m4.z, m4.w};   // -mu
+                const float nav[4] = {a4.x, a4.y, a4.z, a4.w};   // -1 / (2 sigma^2)
                 const float kv[4] = {k4.x, k4.y, k4.z, k4.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (isnan(xv[u])) continue;
                     const float corr = a.tanh_corr ? spn_tanh_correction(xv[u]) : 0.f;
+                    float t[4];
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
-                        const float d = xv[u] - mv[v];
-                        acc[u][v] += -(d * d) * av[v] - kv[v] - corr;
+                        const float d = xv[u] + nmv[v];
+                        t[v] = (d * d) * nav[v] - kv[v] - corr;
                     }
+                    acc2[u][0] = lf_add2(acc2[u][0], lf_pack(t[0], t[1]));
+                    acc2[u][1] = lf_add2(acc2[u][1], lf_pack(t[2], t[3]));
                 }
             }
         }
@@ -179,17 +207,19 @@ __global__ void __launch_bounds__(1024) leaf_tiled_fwd_kernel(LeafTiledArgs a) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int64_t b = (int64_t)b0 + 4 * rg + u;
+                float acc[4];
+                lf_unpack(acc2[u][0], acc[0], acc[1]);
+                lf_unpack(acc2[u][1], acc[2], acc[3]);
                 if (b < a.B) {
                     if (a.vec_io) {
-                        *reinterpret_cast<float4*>(obase + b * a.so_b + 4 * cg) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+                        *reinterpret_cast<float4*>(obase + b * a.so_b + 4 * cg) = make_float4(acc[0], acc[1], acc[2], acc[3]);
                     } else {
 #pragma unroll
                         for (int v = 0; v < 4; ++v)
-                            if (4 * cg + v < a.I) obase[b * a.so_b + (int64_t)(4 * cg + v) * a.so_c] = acc[u][v];
+                            if (4 * cg + v < a.I) obase[b * a.so_b + (int64_t)(4 * cg + v) * a.so_c] = acc[v];
                     }
                 }
-#pragma unroll
-                for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+                acc2[u][0] = acc2[u][1] = 0ull;
             }
         }
         __syncthreads();  // stage buffers / parameters may be overwritten from here on
@@ -229,13 +259,17 @@ __global__ void __launch_bounds__(256, 3) leaf_tiled_bwd_kernel(LeafTiledArgs a)
             const int f = f_begin + min(4 * fg + u, cnt - 1), i = min(4 * ig + v, a.I - 1);
             mv[u][v] = a.mu[(int64_t)f * a.sp_f + (int64_t)i * a.sp_i + (int64_t)r * a.sp_r];
         }
-    float a1[4][4], a2[4][4], a0[4];
+    // packed accumulators over channel pairs (see lf_fma2): a1 = sum g d, a2 = sum g d^2, a0 = sum g
+    uint64_t nm2[4][2], a1p[4][2], a2p[4][2], a0p[2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        a0[u] = 0.f;
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) { a1[u][v] = 0.f; a2[u][v] = 0.f; }
-    }
+        for (int vp = 0; vp < 2; ++vp) {
+            nm2[u][vp] = lf_pack(-mv[u][2 * vp], -mv[u][2 * vp + 1]);
+            a1p[u][vp] = 0ull;
+            a2p[u][vp] = 0ull;
+        }
+    a0p[0] = a0p[1] = 0ull;
     const int64_t rows_per = (((int64_t)a.B + a.nsplit - 1) / a.nsplit + BROWS - 1) / BROWS * BROWS;
     const int64_t row_begin = (int64_t)blockIdx.z * rows_per;
     const int64_t row_end = min((int64_t)a.B, row_begin + rows_per);
@@ -290,40 +324,44 @@ __global__ void __launch_bounds__(256, 3) leaf_tiled_bwd_kernel(LeafTiledArgs a)
             for (int row = grp; row < nrow; row += ngroups) {
                 const float4 g4 = *reinterpret_cast<const float4*>(gb + row * I4 + 4 * ig);
                 const float4 x4 = *reinterpret_cast<const float4*>(xb + row * F4 + 4 * fg);
-                const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+                const uint64_t g2[2] = {lf_pack(g4.x, g4.y), lf_pack(g4.z, g4.w)};
                 const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+                a0p[0] = lf_add2(a0p[0], g2[0]);
+                a0p[1] = lf_add2(a0p[1], g2[1]);
 #pragma unroll
-                for (int v = 0; v < 4; ++v) a0[v] += gv[v];
+                for (int u = 0; u < 4; ++u) {
+                    const uint64_t x2 = lf_pack(xv[u], xv[u]);
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const float d = xv[u] - mv[u][v];
-                        const float tt = gv[v] * d;
-                        a1[u][v] += tt;
-                        a2[u][v] = fmaf(tt, d, a2[u][v]);
+                    for (int vp = 0; vp < 2; ++vp) {
+                        const uint64_t d2 = lf_add2(x2, nm2[u][vp]);    // x - mu
+                        const uint64_t t2 = lf_mul2(g2[vp], d2);
+                        a1p[u][vp] = lf_add2(a1p[u][vp], t2);
+                        a2p[u][vp] = lf_fma2(t2, d2, a2p[u][vp]);
                     }
+                }
             }
         } else {
             for (int row = grp; row < nrow; row += ngroups) {
                 const float4 g4 = *reinterpret_cast<const float4*>(gb + row * I4 + 4 * ig);
                 const float4 x4 = *reinterpret_cast<const float4*>(xb + row * F4 + 4 * fg);
                 const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+                const uint64_t g2[2] = {lf_pack(g4.x, g4.y), lf_pack(g4.z, g4.w)};
                 const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-                for (int v = 0; v < 4; ++v) a0[v] += gv[v];
+                a0p[0] = lf_add2(a0p[0], g2[0]);
+                a0p[1] = lf_add2(a0p[1], g2[1]);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (isnan(xv[u])) {
 #pragma unroll
                         for (int v = 0; v < 4; ++v) atomicAdd(crs + (4 * fg + u) * I4 + 4 * ig + v, gv[v]);  // row does not count for feature u
                     } else {
+                        const uint64_t x2 = lf_pack(xv[u], xv[u]);
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            const float d = xv[u] - mv[u][v];
-                            const float tt = gv[v] * d;
-                            a1[u][v] += tt;
-                            a2[u][v] = fmaf(tt, d, a2[u][v]);
+                        for (int vp = 0; vp < 2; ++vp) {
+                            const uint64_t d2 = lf_add2(x2, nm2[u][vp]);
+                            const uint64_t t2 = lf_mul2(g2[vp], d2);
+                            a1p[u][vp] = lf_add2(a1p[u][vp], t2);
+                            a2p[u][vp] = lf_fma2(t2, d2, a2p[u][vp]);
                         }
                     }
                 }
@@ -338,12 +376,12 @@ __global__ void __launch_bounds__(256, 3) leaf_tiled_bwd_kernel(LeafTiledArgs a)
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                my[u * 4 + v] = a1[u][v];
-                my[16 + u * 4 + v] = a2[u][v];
+            for (int vp = 0; vp < 2; ++vp) {
+                lf_unpack(a1p[u][vp], my[u * 4 + 2 * vp], my[u * 4 + 2 * vp + 1]);
+                lf_unpack(a2p[u][vp], my[16 + u * 4 + 2 * vp], my[16 + u * 4 + 2 * vp + 1]);
             }
-#pragma unroll
-        for (int v = 0; v < 4; ++v) my[32 + v] = a0[v];
+        lf_unpack(a0p[0], my[32], my[33]);
+        lf_unpack(a0p[1], my[34], my[35]);
     }
     __syncthreads();
     for (int e = threadIdx.x; e < ntile * 16; e += blockDim.x) {
