@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(256) leaf_transpose_kernel(const float* __rest
 }
 
 // grid (row-tile groups, R, d0); block 32 * ceil(I / 4) threads: lane = row group (4 rows), warp = channel group (4 ch).
-__global__ void __launch_bounds__(1024) leaf_tiled_fwd_kernel(LeafTiledArgs a) {
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) leaf_tiled_fwd_kernel(LeafTiledArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int I4 = (int)(blockDim.x >> 5) * 4;
     float* xs = sm;                       // [2][FC][FROWS]
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(1024) leaf_tiled_fwd_kernel(LeafTiledArgs a) {
         int has_nan = a.nanflag[b0 / NANROWS];
         if (b0 + NANROWS < a.B) has_nan |= a.nanflag[b0 / NANROWS + 1];
         if (!has_nan && !a.tanh_corr) {
-#pragma unroll 2
+#pragma unroll 4
             for (int j = 0; j < cnt; ++j) {
                 const float4 x4 = *reinterpret_cast<const float4*>(xb + j * FROWS + 4 * rg);
                 const float4 m4 = *reinterpret_cast<const float4*>(pm + j * I4 + 4 * cg);
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(256, 3) leaf_tiled_bwd_kernel(LeafTiledArgs a)
         if (b0 + NANROWS < a.B) has_nan |= a.nanflag[b0 / NANROWS + 1];
         if (!worker) {
         } else if (!has_nan) {
-#pragma unroll 2
+#pragma unroll 4
             for (int row = grp; row < nrow; row += ngroups) {
                 const float4 g4 = *reinterpret_cast<const float4*>(gb + row * I4 + 4 * ig);
                 const float4 x4 = *reinterpret_cast<const float4*>(xb + row * F4 + 4 * fg);
@@ -445,13 +446,15 @@ extern "C" int spn_leaf_tiled_fwd(const float* xT, const int32_t* perm, const fl
     a.vec_io = (so_c == 1 && I % 4 == 0 && so_b % 4 == 0 && so_d % 4 == 0 && so_r % 4 == 0 && aligned16(out)) ? 1 : 0;
     const int ncg = (I + 3) / 4, I4 = ncg * 4;
     const int smem = (2 * FC * FROWS + 3 * FC * I4 + I4) * (int)sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(leaf_tiled_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    // up to 16 channel groups (I <= 64): blocks of <= 512 threads may use 128 registers (deeper unrolling of the feature loop)
+    auto kernel = 32 * ncg <= 512 ? leaf_tiled_fwd_kernel<512> : leaf_tiled_fwd_kernel<1024>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return spn_cuda_status(e);
     const int ntiles = (B + FROWS - 1) / FROWS;
     int gx = (16 * 148 + R * d0 - 1) / (R * d0);
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
-    leaf_tiled_fwd_kernel<<<dim3(gx, R, d0), 32 * ncg, smem, (cudaStream_t)stream>>>(a);
+    kernel<<<dim3(gx, R, d0), 32 * ncg, smem, (cudaStream_t)stream>>>(a);
     return spn_launch_status();
 }
 

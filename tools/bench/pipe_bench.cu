@@ -36,6 +36,33 @@ __global__ void fbench(float* out, long long* clk, int iters) {
         } else if (KIND == 3) {   // fma with distinct registers: d = v[i] * v[j] + v[k]
 #pragma unroll
             for (int i = 0; i < 32; ++i) asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(v[i]) : "f"(v[(i + 7) & 31]), "f"(v[(i + 13) & 31]));
+        } else if (KIND == 6) {   // fma.f32x2 with three DISTINCT register pairs: acc[i] = v[j] * v[k] + acc[i] (dX epilogue pattern)
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                const int j = (i + 6) & 31, k = (i + 14) & 31;
+                asm volatile(
+                    "{\n\t.reg .b64 x, y, z;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\tmov.b64 z, {%4, %5};\n\t"
+                    "fma.rn.f32x2 x, y, z, x;\n\tmov.b64 {%0, %1}, x;\n\t}"
+                    : "+f"(v[i]), "+f"(v[i + 1]) : "f"(v[j]), "f"(v[j + 1]), "f"(v[k]), "f"(v[k + 1]));
+            }
+        } else if (KIND == 7) {   // fma.f32x2 with a broadcast scalar and two distinct pairs: acc[i] = a * v[k] + acc[i] (forward epilogue)
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                const int k = (i + 14) & 31;
+                asm volatile(
+                    "{\n\t.reg .b64 x, y, z;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %2};\n\tmov.b64 z, {%3, %4};\n\t"
+                    "fma.rn.f32x2 x, y, z, x;\n\tmov.b64 {%0, %1}, x;\n\t}"
+                    : "+f"(v[i]), "+f"(v[i + 1]) : "f"(a), "f"(v[k]), "f"(v[k + 1]));
+            }
+        } else if (KIND == 8) {   // add.f32x2, distinct pairs
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                const int k = (i + 14) & 31;
+                asm volatile(
+                    "{\n\t.reg .b64 x, z;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 z, {%2, %3};\n\t"
+                    "add.rn.f32x2 x, x, z;\n\tmov.b64 {%0, %1}, x;\n\t}"
+                    : "+f"(v[i]), "+f"(v[i + 1]) : "f"(v[k]), "f"(v[k + 1]));
+            }
         } else if (KIND == 4) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(v[i]) : "f"(a));
@@ -160,6 +187,9 @@ int main() {
     frun<3>("fma.f32 (3 distinct regs)", o, c, 32);
     frun<1>("fma.f32x2", o, c, 16);
     frun<2>("mul.f32x2", o, c, 16);
+    frun<6>("fma.f32x2 (3 distinct pairs)", o, c, 16);
+    frun<7>("fma.f32x2 (bcast, 2 pairs)", o, c, 16);
+    frun<8>("add.f32x2 (2 distinct pairs)", o, c, 16);
     frun<4>("mul.f32", o, c, 32);
     frun<5>("ex2.approx.f32", o, c, 32);
     trun<32, false, false>("tcgen05.ld same addr", (uint32_t*)o, c);
