@@ -33,6 +33,10 @@ SIGNATURES = {
     "spn_leaf_tiled_supported": [_I, _I, _I],
     "spn_leaf_tiled_fwd": [_P, _P, _P, _P, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L, _L, _L, _P],
     "spn_leaf_tiled_bwd_params": [_P, _P, _L, _L, _L, _L, _P, _P, _P, _L, _L, _L, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "spn_leaf_tc_supported": [_I, _I, _I, _I],
+    "spn_leaf_tc_image_bytes": [_I, _I, _I, _I],
+    "spn_leaf_tc_fwd": [_P, _P, _P, _P, _L, _L, _L, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "spn_leaf_tc_bwd_params": [_P, _P, _P, _P, _P, _L, _L, _L, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "spn_sum_fwd": [_I, _P, _L, _L, _L, _L, _I, _I, _P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _L,
                     _L, _L, _P],
     "spn_sum_bwd_w": [_I, _P, _L, _L, _L, _L, _I, _I, _P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P,
@@ -75,7 +79,7 @@ SIGNATURES = {
                             _I, _P, _I, _P, _P, _P, _P, _P],
 }
 
-_RETURNS_INT64 = {"spn_leaf_workspace_floats", "spn_sum_tc_image_bytes", "spn_sum_tc_hand_bytes", "spn_sum_tc_fhand_bytes",
+_RETURNS_INT64 = {"spn_leaf_workspace_floats", "spn_leaf_tc_image_bytes", "spn_sum_tc_image_bytes", "spn_sum_tc_hand_bytes", "spn_sum_tc_fhand_bytes",
                   "spn_sum_tc_dw_workspace_floats"}
 
 _lib = None

@@ -40,6 +40,8 @@ def needs_build(out=OUT):
 
 def extra_flags():
     extra = ["-DSPN_TC_PROFILE"] if os.environ.get("SPN_TC_PROFILE") else []
+    if os.environ.get("SPN_LEAF_TC_PROF"):
+        extra.append("-DSPN_LEAF_TC_PROF")
     for name in ("SPN_TC_DEBUG_MODE", "SPN_MBAR_HINT_NS"):
         if os.environ.get(name):
             extra.append(f"-D{name}={os.environ[name]}")

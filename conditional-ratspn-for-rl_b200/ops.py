@@ -37,6 +37,15 @@ def _pow2_ceil(d: int) -> int:
 # --------------------------------------------------------------------------------------------------------------
 # Leaf: permutation gather + Gaussian log-density + tanh correction + NaN marginalisation + product over `card`
 # --------------------------------------------------------------------------------------------------------------
+# Leaf on the tensor cores (leaf_tc.cu: tf32 split operands) wherever the tensor-core path asks for the internal layout and
+# the shape is supported; False keeps the exact fp32 kernels of leaf_tiled.cu (tests A/B the two).
+LEAF_TENSOR_CORES = True
+
+
+def leaf_tc_supported(I, R, card, d0):
+    return bool(_abi.lib().spn_leaf_tc_supported(I, R, card, d0))
+
+
 class LeafFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, mu, sigma, perm32, card, tanh_corr, layout="ref"):
@@ -65,9 +74,17 @@ class LeafFn(torch.autograd.Function):
             sp, i_fast = (R * I, 1, I), 1
         st = stream_ptr(x.device)
         xT = None
+        # tensor-core leaf: internal layout only, no tanh correction, 128-row tiles worth filling
+        use_tc = (tiled and layout != "ref" and LEAF_TENSOR_CORES and not tanh_corr and B >= 128
+                  and leaf_tc_supported(I, R, card, d0))
         if tiled:
             xT = torch.empty(_abi.lib().spn_leaf_workspace_floats(B, F), device=x.device, dtype=torch.float32)
             call("spn_leaf_transpose", ptr(x), sx[0], sx[1], B, F, ptr(xT), st)
+        if use_tc:
+            img = torch.empty(_abi.lib().spn_leaf_tc_image_bytes(I, R, card, d0), device=x.device, dtype=torch.uint8)
+            call("spn_leaf_tc_fwd", ptr(xT), ptr(perm32), ptr(mu), ptr(sigma), *sp, B, F, I, R, card, d0, ptr(img),
+                 ptr(out), st)
+        elif tiled:
             call("spn_leaf_tiled_fwd", ptr(xT), ptr(perm32), ptr(mu), ptr(sigma), *sp, B, F, I, R, card, d0,
                  int(tanh_corr), ptr(out), *so, st)
         elif shared:
@@ -78,13 +95,13 @@ class LeafFn(torch.autograd.Function):
                  int(tanh_corr), ptr(out), *so, st)
         empty = torch.empty(0, device=x.device)
         ctx.save_for_backward(x, mu, sigma, perm32 if perm32 is not None else empty, xT if tiled else empty)
-        ctx.meta = (sx, so, Wsets, w, B, F, I, R, card, d0, int(tanh_corr), perm32 is not None, sp, i_fast, tiled)
+        ctx.meta = (sx, so, Wsets, w, B, F, I, R, card, d0, int(tanh_corr), perm32 is not None, sp, i_fast, tiled, use_tc)
         return out
 
     @staticmethod
     def backward(ctx, g):
         x, mu, sigma, perm32, xT = ctx.saved_tensors
-        sx, so, Wsets, w, B, F, I, R, card, d0, tanh_corr, has_perm, sp, i_fast, tiled = ctx.meta
+        sx, so, Wsets, w, B, F, I, R, card, d0, tanh_corr, has_perm, sp, i_fast, tiled, use_tc = ctx.meta
         perm32 = perm32 if has_perm else None
         g = _f32c(g)
         dx = dmu = dsigma = None
@@ -92,7 +109,10 @@ class LeafFn(torch.autograd.Function):
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             dmu = torch.empty_like(mu)
             dsigma = torch.empty_like(sigma)
-            if tiled:
+            if use_tc:   # g is contiguous [d0][R][B][I] (_f32c above)
+                call("spn_leaf_tc_bwd_params", ptr(xT), ptr(g), ptr(perm32), ptr(mu), ptr(sigma), *sp, B, F, I, R, card, d0,
+                     ptr(dmu), ptr(dsigma), st)
+            elif tiled:
                 call("spn_leaf_tiled_bwd_params", ptr(xT), ptr(g), *so, ptr(perm32), ptr(mu), ptr(sigma), *sp, B, F, I, R,
                      card, d0, ptr(dmu), ptr(dsigma), st)
             elif Wsets == 1:

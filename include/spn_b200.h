@@ -92,6 +92,22 @@ int spn_leaf_tiled_bwd_params(const float* xT, const float* g, int64_t sg_b, int
                               int64_t sp_r, int B, int F, int I, int R, int card, int d0, float* dmu, float* dsigma,
                               void* stream);
 
+/* Tensor-core variants (tcgen05 kind::tf32, leaf_tc.cu) of the two calls above for the internal layout: the leaf + product
+ * over a scope as one GEMM per (scope, repetition) on operands split into two tf32 words each (x^2, x, valid against
+ * -1/(2 sigma^2), mu/sigma^2, the constant term), fp32 accumulation; the parameter gradients as the transposed GEMM over
+ * the rows.  out / g are contiguous [d0][R][B][I]; xT as written by spn_leaf_transpose; NaN inputs are marginalised; no
+ * tanh correction (distributions.py:220 stays on the fp32 kernels).  `img`: caller-allocated scratch of
+ * spn_leaf_tc_image_bytes bytes, 128-byte aligned (the parameter operand image, rebuilt by every forward call).
+ * Supported: I a multiple of 8 up to 64, card <= 25, every scope non-empty.  Replaces distributions.py:199-246 +
+ * layers.py:276-312 on the shared-parameter path (rat_spn.py:155-170 for the permutation). */
+int spn_leaf_tc_supported(int I, int R, int card, int d0);
+int64_t spn_leaf_tc_image_bytes(int I, int R, int card, int d0);
+int spn_leaf_tc_fwd(const float* xT, const int32_t* perm, const float* mu, const float* sigma, int64_t sp_f, int64_t sp_i,
+                    int64_t sp_r, int B, int F, int I, int R, int card, int d0, void* img, float* out, void* stream);
+int spn_leaf_tc_bwd_params(const float* xT, const float* g, const int32_t* perm, const float* mu, const float* sigma,
+                           int64_t sp_f, int64_t sp_i, int64_t sp_r, int B, int F, int I, int R, int card, int d0,
+                           float* dmu, float* dsigma, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Sum layer, optionally fused with the CrossProduct layer below it (the c*c outer sum is never materialised).
  * Replaces layers.py:419-440 + :545-563 (CrossProduct.forward / split_shuffled_scopes), layers.py:110-128

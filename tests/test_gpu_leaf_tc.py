@@ -1,0 +1,116 @@
+"""GPU: leaf layer on the tensor cores (csrc/leaf_tc.cu, tcgen05 kind::tf32 on split operands) against the CPU oracle in
+fp64 and against the exact fp32 kernels (csrc/leaf_tiled.cu).
+
+Tolerances (stated, measured values are printed): the tf32 x 3 split carries ~21 mantissa bits through a quadratic form
+whose three terms cancel, so the forward is allowed 4e-6 of the largest |log-density| (+ 1e-4 absolute) where the exact
+kernels are held to 2e-6 (+ 1e-5); parameter gradients 1e-4 of the largest gradient entry (exact kernels: 2e-5)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _oracle_leaf(x, perm, mu, sigma, arch):
+    from oracle import spn_oracle as O
+    xp = O.apply_permutation(x.double(), perm)
+    return O.leaf_product(O.leaf_log_prob(xp, mu, sigma, arch), arch)
+
+
+@pytest.mark.parametrize("F,D,I,R,B,nan", [
+    (784, 5, 40, 4, 300, True),     # cfg 2 leaf shape (fewer repetitions): card 25, short last scope, ragged last tile
+    (784, 5, 40, 3, 384, False),    # whole tiles only
+    (100, 2, 32, 2, 130, False),    # N = 32
+    (64, 3, 16, 5, 1000, True),     # card 8: one operand stage per tile
+    (48, 2, 64, 2, 256, False),     # N = 64, card 12
+    (17, 3, 8, 3, 200, True),       # card 3, padded scopes (17 features over 8 regions -> 6 non-empty scopes)
+])
+def test_tensor_core_leaf_vs_oracle_and_exact_kernels(F, D, I, R, B, nan):
+    from oracle import spn_oracle as O
+    from ratspn_b200 import ops
+    g = torch.Generator().manual_seed(F * 7 + B)
+    arch = O.Arch(F=F, D=D, R=R, S=2, I=I, C=1, tanh_squash=False)
+    card, d0 = arch.card, arch.d0
+    assert ops.leaf_tc_supported(I, R, card, d0)
+    x = torch.randn(B, 1, F, 1, 1, generator=g)
+    if nan:
+        x[3, 0, ::3] = float("nan")
+        x[B - 1, 0, :] = float("nan")
+        x[17, 0, 5] = float("nan")
+    perm = torch.stack([torch.randperm(F, generator=g) for _ in range(R)], dim=-1)
+    mu = torch.randn(1, F, I, R, generator=g)
+    sigma = torch.rand(1, F, I, R, generator=g) * 0.9 + 0.05
+    go = torch.randn(B, 1, d0, I, R, generator=g)
+
+    mu_o, sg_o = mu.double().requires_grad_(True), sigma.double().requires_grad_(True)
+    ref = _oracle_leaf(x, perm, mu_o, sg_o, arch)                    # [B, 1, d0, I, R]
+    (ref * go.double()).sum().backward()
+
+    res = {}
+    for tc in (True, False):
+        ops.LEAF_TENSOR_CORES = tc
+        try:
+            mu_t, sg_t = mu.to(DEV).requires_grad_(True), sigma.to(DEV).requires_grad_(True)
+            out = ops.leaf_forward(x.to(DEV), mu_t, sg_t, perm.to(torch.int32).to(DEV), card, False, "drbc")
+            assert out.shape == (d0, R, B, I)
+            got = out.permute(2, 0, 3, 1).unsqueeze(1)                   # -> [B, 1, d0, I, R]
+            (got * go.to(DEV)).sum().backward()
+            torch.cuda.synchronize()
+            res[tc] = (got.detach().cpu().double(), mu_t.grad.cpu().double(), sg_t.grad.cpu().double())
+        finally:
+            ops.LEAF_TENSOR_CORES = True
+    scale = ref.abs().max().item()
+    errs = {}
+    for tc, (got, dmu, dsg) in res.items():
+        errs[tc] = ((got - ref).abs().max().item() / scale, (dmu - mu_o.grad).abs().max().item() / mu_o.grad.abs().max().item(),
+                    (dsg - sg_o.grad).abs().max().item() / sg_o.grad.abs().max().item())
+    print(f"leaf F={F} I={I} R={R} B={B}: rel. max errors (fwd, dmu, dsigma) tensor cores {errs[True]}, exact kernels {errs[False]}")
+    got, dmu, dsg = res[True]
+    assert (got - ref).abs().max().item() <= 4e-6 * scale + 1e-4
+    for name, a, b in (("dmu", dmu, mu_o.grad), ("dsigma", dsg, sg_o.grad)):
+        err = (a - b).abs().max().item()
+        assert err <= 1e-4 * b.abs().max().item() + 1e-6, f"{name}: {err} vs scale {b.abs().max().item()}"
+
+
+def test_tensor_core_leaf_marginalises_all_nan_rows():
+    from ratspn_b200 import ops
+    F, I, R, B, card = 64, 8, 2, 256, 8
+    x = torch.randn(B, 1, F, 1, 1, device=DEV)
+    x[5] = float("nan")
+    x[200:] = float("nan")
+    mu = torch.randn(1, F, I, R, device=DEV)
+    sigma = torch.rand(1, F, I, R, device=DEV) + 0.1
+    out = ops.leaf_forward(x, mu, sigma, None, card, False, "drbc")     # [d0, R, B, I]
+    assert torch.equal(out[:, :, 5], torch.zeros_like(out[:, :, 5]))
+    assert torch.equal(out[:, :, 200:], torch.zeros_like(out[:, :, 200:]))
+    assert torch.isfinite(out).all() and (out[:, :, :5] != 0).all()
+
+
+def test_model_log_likelihood_and_gradients_do_not_depend_on_the_leaf_path():
+    """RatSpn on the tensor-core path: the tf32-split leaf against the exact fp32 leaf, same Sum kernels."""
+    import ratspn_b200 as rb
+    from ratspn_b200 import ops
+    cfg = rb.RatSpnConfig()
+    cfg.F, cfg.D, cfg.R, cfg.S, cfg.I, cfg.C = 784, 5, 6, 40, 40, 1
+    cfg.dropout, cfg.leaf_base_class, cfg.leaf_base_kwargs, cfg.tanh_squash = 0.0, rb.RatNormal, {}, False
+    torch.manual_seed(3)
+    model = rb.RatSpn(cfg).to(DEV)
+    x = torch.rand(512, 1, 784, 1, 1, device=DEV)
+    res = {}
+    for tc in (True, False):
+        ops.LEAF_TENSOR_CORES = tc
+        try:
+            model.zero_grad(set_to_none=True)
+            ll = model(x)
+            ll.mean().backward()
+            res[tc] = (ll.detach().clone(), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None})
+        finally:
+            ops.LEAF_TENSOR_CORES = True
+    ll_t, ll_e = res[True][0], res[False][0]
+    rel = ((ll_t - ll_e).abs() / ll_e.abs()).max().item()
+    print(f"model LL: max rel. deviation tensor-core leaf vs exact leaf {rel:.2e}")
+    assert rel <= 1e-5
+    for n, ge in res[False][1].items():
+        gt = res[True][1][n]
+        err = (gt - ge).abs().max().item() / (ge.abs().max().item() + 1e-30)
+        assert err <= 2e-3, f"{n}: {err}"
