@@ -28,11 +28,13 @@ __device__ int g_leaf_tc_aborts = 0;
 
 // per-phase clocks of one CTA (block 0, lane 0 of one warp per role); experiment builds only (-DSPN_LEAF_TC_PROF)
 #ifdef SPN_LEAF_TC_PROF
+#define LT_DBG(bit) ((a.dbg & (bit)) != 0)   // spn_debug_leaf_tc_mode: 1 no MMA, 2 no x reads, 4 no A operand, 8 no bulk store, 16 no B operand
 __device__ long long g_leaf_tc_prof[64];
 #define LTP_DECL long long ltp_t = clock64(), ltp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define LTP_LAP(i) do { const long long ltp_n = clock64(); ltp_acc[i] += ltp_n - ltp_t; ltp_t = ltp_n; } while (0)
 #define LTP_FLUSH(base) do { if (blockIdx.x == 0 && lane == 0) for (int ltp_i = 0; ltp_i < 8; ++ltp_i) atomicAdd((unsigned long long*)&g_leaf_tc_prof[(base) + ltp_i], (unsigned long long)ltp_acc[ltp_i]); } while (0)
 #else
+#define LT_DBG(bit) false
 #define LTP_DECL
 #define LTP_LAP(i)
 #define LTP_FLUSH(base)
@@ -40,10 +42,8 @@ __device__ long long g_leaf_tc_prof[64];
 
 namespace {
 
-constexpr int LT_FS = 4;                 // features per forward operand stage
-constexpr int LT_STAGE = LT_FS * 4096;   // [feature][2 K halves][128 rows][4 tf32]
-constexpr int LT_NSTAGE = 4;
-constexpr int LT_XD = 3;                 // forward: depth of the x ring in tiles (prefetch distance LT_XD - 1)
+constexpr int LT_NSTAGE = 4;             // forward: A-operand stages in tensor memory (8 features = 64 columns each)
+constexpr int LT_XD = 6;                 // forward: depth of the x ring in tiles (prefetch distance LT_XD - 1)
 constexpr int LT_MAXCARD = 25;           // backward: 5 operand rows per feature, M = 128
 constexpr int LT_BROWS = 64;             // rows (K extent) per backward stage
 constexpr int LT_BSTAGES = 2;
@@ -56,7 +56,7 @@ struct LeafTcArgs {
     const float* g;         // backward: [d0][R][B][I]
     const float* mu; const float* sigma; int64_t sp_f, sp_i, sp_r;
     float* dmu; float* dsigma;
-    int B, ldx, F, I, R, card, d0, fs, nst, img_bytes, dbg;
+    int B, ldx, F, I, R, card, d0, nst, img_bytes, gring, dbg;
 };
 
 __device__ __forceinline__ uint32_t tf32_hi(float v) { return __float_as_uint(v) & 0xFFFFE000u; }
@@ -110,22 +110,35 @@ __global__ void __launch_bounds__(256) leaf_tc_image_kernel(LeafTcArgs a, int NP
 }
 
 // --------------------------------------------------------------------------------------------------------------------
-// Forward.  Work item = (scope, repetition); 128-row tiles.  10 warps:
-//   warps 0-3  epilogue: accumulator -> registers -> this warp's 32-row staging block in shared memory -> one TMA bulk store
-//              per warp and tile (32 rows are a contiguous run of 32 * I floats of the [d0][R][B][I] output);
-//   warps 4-7  operand producers: thread = row.  The x values of a tile (one per feature) are fetched LT_XD - 1 tiles ahead
-//              with cp.async into a ring whose column `row` only this thread touches (no barrier; the loads of two tiles are
-//              in flight per thread -- with loads issued right before their use the kernel ran at the memory latency under
-//              the 839 MB output stream, 2.3 ms instead of 0.5 ms); the split words of x^2 / x / valid go into the A stage
-//              as two 16-byte stores (core-matrix rows are 16 bytes apart: conflict free);
-//   warp 8     MMA issuer (one K = 8 step per feature, N = NP);   warp 9   TMA of the item's parameter image.
+// Forward.  Work item = (scope, repetition); 128-row tiles.  14 warps:
+//   warps 0-3   epilogue: accumulator -> registers -> this warp's 32-row staging block in shared memory -> one TMA bulk store
+//               per warp and tile (32 rows are a contiguous run of 32 * I floats of the [d0][R][B][I] output);
+//   warps 4-11  operand producers, two threads per row (warp % 4 = TMEM lane quadrant, (warp - 4) / 4 = feature half).  The A
+//               operand never touches shared memory: the 8 split words of a feature (x2h x2h x2l xh xh xl v v) are ONE
+//               tcgen05.st of 8 columns into the row's TMEM lane, and the MMA reads A from tensor memory (the shared-memory
+//               variant moved 200 KB per tile through shared memory and ran at that bandwidth);
+//   warp 12     MMA issuer (one K = 8 step per feature, N = NP);
+//   warp 13     TMA: the item's parameter image, and the x values of every tile (one 512-byte row segment of xT per feature)
+//               LT_XD - 1 tiles ahead into a ring (with loads issued right before their use the kernel ran at the memory
+//               latency under the 839 MB output stream, 2.3 ms; per-thread cp.async cost 60 clk per feature and warp).
+// Tensor memory: columns [0, 128) two accumulators, [128, 128 + 64 LT_NSTAGE) the A ring (8 features x 8 columns a stage).
 // --------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_ts_tf32_uniform(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                    uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+
 template <int NP>
-__global__ void __launch_bounds__(320, 1) leaf_tc_fwd_kernel(LeafTcArgs a) {
+__global__ void __launch_bounds__(448, 1) leaf_tc_fwd_kernel(LeafTcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int img_stride = (a.img_bytes + 127) & ~127;
-    uint8_t* As = smem;                                                        // [LT_NSTAGE][LT_STAGE]
-    uint8_t* Ws = As + LT_NSTAGE * LT_STAGE;                                   // [2][img_stride]
+    uint8_t* Ws = smem;                                                        // [2][img_stride]
     float* Os = reinterpret_cast<float*>(Ws + 2 * img_stride);                 // [4 warps][2][32][I]
     float* Xs = Os + 2 * 128 * a.I;                                            // [LT_XD][card][128]
     uint64_t* s_full = reinterpret_cast<uint64_t*>(Xs + LT_XD * a.card * 128); // [LT_NSTAGE] producers -> MMA
@@ -134,13 +147,17 @@ __global__ void __launch_bounds__(320, 1) leaf_tc_fwd_kernel(LeafTcArgs a) {
     uint64_t* acc_empty = acc_full + 2;                                        // [2]
     uint64_t* w_full = acc_empty + 2;                                          // [2]
     uint64_t* w_empty = w_full + 2;                                            // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + 2);
+    uint64_t* x_full = w_empty + 2;                                            // [LT_XD] TMA -> producers
+    uint64_t* x_empty = x_full + LT_XD;                                        // [LT_XD] producers -> TMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_empty + LT_XD);
     volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+    constexpr int W_MMA = 12, W_TMA = 13;
+    constexpr uint32_t A_COL0 = 128;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < LT_NSTAGE; ++i) {
-            mbar_init(s_full + i, 4);
+            mbar_init(s_full + i, 8);
             mbar_init(s_empty + i, 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -149,10 +166,14 @@ __global__ void __launch_bounds__(320, 1) leaf_tc_fwd_kernel(LeafTcArgs a) {
             mbar_init(w_full + i, 1);
             mbar_init(w_empty + i, 1);
         }
+        for (int i = 0; i < LT_XD; ++i) {
+            mbar_init(x_full + i, 1);
+            mbar_init(x_empty + i, 8);
+        }
         *abort_flag = 0;
         mbar_fence_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, 128);
+    if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -160,90 +181,69 @@ __global__ void __launch_bounds__(320, 1) leaf_tc_fwd_kernel(LeafTcArgs a) {
 
     const int nitems = a.d0 * a.R;
     const int ntiles = (a.B + 127) / 128;
-    const int fs = a.fs, nst = a.nst;
+    const int nst = a.nst;
     uint32_t n_stage = 0, n_tile = 0, n_item = 0;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 4 && warp < 12) {
         // ===================================================== operand producers =====================================================
-        const int row = (warp - 4) * 32 + lane;
-        const int my_items = (int)blockIdx.x < nitems ? (nitems - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-        const int total = my_items * ntiles;
+        const int quad = warp & 3, half = (warp - 4) >> 2;
+        const int row = quad * 32 + lane;
         const int xslot = a.card * 128;
-        int pf_k = -1, pf_src = 0, pf_cnt = 0;   // prefetch cursor: lane j holds the source feature of the j-th feature of its item
-        auto prefetch = [&](int n) {
-            if (n < total && !(a.dbg & 2)) {
-                const int k = n / ntiles, t = n - k * ntiles;
-                if (k != pf_k) {
-                    const int item = blockIdx.x + k * gridDim.x;
-                    const int s = item / a.R, r = item % a.R;
-                    const int f_begin = s * a.card;
-                    pf_cnt = min(a.card, a.F - f_begin);
-                    pf_src = 0;
-                    if (lane < pf_cnt) pf_src = a.perm ? a.perm[(int64_t)(f_begin + lane) * a.R + r] : f_begin + lane;
-                    pf_k = k;
-                }
-                const int b = t * 128 + row;
-                const bool inb = b < a.B;
-                const float* xp = a.xT + (inb ? b : 0);
-                float* dst = Xs + (n % LT_XD) * xslot + row;
-#pragma unroll 5
-                for (int jj = 0; jj < pf_cnt; ++jj) {
-                    const int src = __shfl_sync(0xffffffffu, pf_src, jj);
-                    spn_cp_async4(dst + jj * 128, xp + (int64_t)src * a.ldx, inb ? 4 : 0);   // rows past the batch: zero fill
-                }
-            }
-            spn_cp_async_commit();
-        };
-        for (int n = 0; n < LT_XD - 1; ++n) prefetch(n);
+        uint32_t n_x = 0;
         LTP_DECL;
-        for (int n = 0; n < total; ++n) {
-            const int k = n / ntiles, t = n - k * ntiles;
-            const int item = blockIdx.x + k * gridDim.x;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int cnt = min(a.card, a.F - (item / a.R) * a.card);
-            const bool inb = t * 128 + row < a.B;
-            LTP_LAP(0);
-            prefetch(n + LT_XD - 1);
-            LTP_LAP(1);   // prefetch issue
-            spn_cp_async_wait<LT_XD - 1>();   // this thread's values of tile n have landed (it reads only its own column)
-            LTP_LAP(2);   // cp.async wait
-            const float* xs = Xs + (n % LT_XD) * xslot + row;
-            for (int c = 0; c < nst; ++c, ++n_stage) {
-                const uint32_t slot = n_stage % LT_NSTAGE, use = n_stage / LT_NSTAGE;
-                const int nf = min(fs, cnt - c * fs);
-                float xv[LT_FS];
+            for (int t = 0; t < ntiles; ++t, ++n_x) {
+                const bool inb = t * 128 + row < a.B;
+                const uint32_t xsl = n_x % LT_XD;
+                LTP_LAP(0);
+                mbar_wait_sticky(x_full + xsl, (n_x / LT_XD) & 1, abort_flag);
+                LTP_LAP(1);   // wait for the x tile
+                const float* xs = Xs + xsl * xslot + row;
+                for (int c = 0; c < nst; ++c, ++n_stage) {
+                    const uint32_t slot = n_stage % LT_NSTAGE, use = n_stage / LT_NSTAGE;
+                    const int j0 = 8 * c + 4 * half;
+                    float xv[4];
 #pragma unroll
-                for (int jj = 0; jj < LT_FS; ++jj) xv[jj] = jj < nf ? xs[(c * fs + jj) * 128] : 0.f;
-                LTP_LAP(3);   // x from the ring
-                mbar_wait_sticky(s_empty + slot, (use & 1) ^ 1, abort_flag);
-                LTP_LAP(4);   // wait for the stage
-                uint8_t* st = As + slot * LT_STAGE + row * 16;
-#pragma unroll
-                for (int jj = 0; jj < LT_FS; ++jj) {
-                    if (jj < nf && !(a.dbg & 4)) {
-                        float x = xv[jj];
-                        const bool ok = inb && (x == x);
-                        x = ok ? x : 0.f;
-                        const uint32_t v = ok ? 0x3F800000u : 0u;
-                        uint32_t xh, xl, qh, ql;
-                        tf32_split(x, xh, xl);
-                        tf32_split(x * x, qh, ql);
-                        *reinterpret_cast<uint4*>(st + jj * 4096) = make_uint4(qh, qh, ql, xh);
-                        *reinterpret_cast<uint4*>(st + jj * 4096 + 2048) = make_uint4(xh, xl, v, v);
+                    for (int e = 0; e < 4; ++e) xv[e] = (j0 + e < cnt && !LT_DBG(2)) ? xs[(j0 + e) * 128] : 0.f;
+                    if (c == nst - 1) {   // last read of this x tile: hand the ring slot back to the TMA warp
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(x_empty + xsl);
                     }
+                    LTP_LAP(2);   // x from the ring
+                    mbar_wait_sticky(s_empty + slot, (use & 1) ^ 1, abort_flag);
+                    fence_after_sync();
+                    LTP_LAP(3);   // wait for the stage
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + A_COL0 + slot * 64 + half * 32;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (j0 + e < cnt && !LT_DBG(4)) {
+                            float x = xv[e];
+                            const bool ok = inb && (x == x);
+                            x = ok ? x : 0.f;
+                            const uint32_t v = ok ? 0x3F800000u : 0u;
+                            uint32_t w[8];
+                            tf32_split(x * x, w[0], w[2]);
+                            tf32_split(x, w[3], w[5]);
+                            w[1] = w[0]; w[4] = w[3]; w[6] = v; w[7] = v;
+                            tmem_st8(taddr + e * 8, w);
+                        }
+                    }
+                    tmem_wait_st();
+                    LTP_LAP(4);   // split + tcgen05.st
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_full + slot);
+                    LTP_LAP(5);   // fence + arrive
                 }
-                LTP_LAP(5);   // split + stores
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(s_full + slot);
-                LTP_LAP(6);   // fence + arrive
             }
         }
-        spn_cp_async_wait<0>();
         if (warp == 4) LTP_FLUSH(0);
-    } else if (warp == 8) {
+    } else if (warp == W_MMA) {
         // ===================================================== MMA issuer =====================================================
         constexpr uint32_t idesc = instr_desc_tf32(128, NP);
-        const uint32_t as_addr = smem_u32(As), ws_addr = smem_u32(Ws);
+        const uint32_t ws_addr = smem_u32(Ws);
         LTP_DECL;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n_item) {
             const int s = item / a.R;
@@ -262,19 +262,18 @@ __global__ void __launch_bounds__(320, 1) leaf_tc_fwd_kernel(LeafTcArgs a) {
                 const uint32_t acc = tmem_base + ab * 64;
                 for (int c = 0; c < nst; ++c, ++n_stage) {
                     const uint32_t slot = n_stage % LT_NSTAGE, use = n_stage / LT_NSTAGE;
-                    const int nf = min(fs, cnt - c * fs);
+                    const int nf = min(8, cnt - c * 8);
                     mbar_wait_sticky(s_full + slot, use & 1, abort_flag);
                     LTP_LAP(3);   // wait for the operand stage
                     fence_after_sync();
-                    const uint32_t abase = as_addr + slot * LT_STAGE;
+                    const uint32_t abase = tmem_base + A_COL0 + slot * 64;
 #pragma unroll
-                    for (int jj = 0; jj < LT_FS; ++jj) {
+                    for (int jj = 0; jj < 8; ++jj) {
                         if (jj < nf) {
-                            // A [M = row][K = 8]: K halves 2048 B apart, 8-row groups 128 B apart
+                            // A [M = row][K = 8] in tensor memory: lane = row, 8 columns
                             // B [N = channel][K = 8]: K halves NP * 16 B apart, 8-channel groups 128 B apart
-                            const uint64_t adesc = smem_desc(abase + jj * 4096, 2048, 128);
-                            const uint64_t bdesc = smem_desc(wbase + (c * fs + jj) * (NP * 32), NP * 16, 128);
-                            if (!(a.dbg & 1)) mma_ss_tf32_uniform(acc, adesc, bdesc, idesc, (c | jj) ? 1u : 0u);
+                            const uint64_t bdesc = smem_desc(wbase + (c * 8 + jj) * (NP * 32), NP * 16, 128);
+                            if (!LT_DBG(1)) mma_ts_tf32_uniform(acc, abase + jj * 8, bdesc, idesc, (c | jj) ? 1u : 0u);
                         }
                     }
                     mma_commit_uniform(s_empty + slot);
@@ -285,10 +284,13 @@ __global__ void __launch_bounds__(320, 1) leaf_tc_fwd_kernel(LeafTcArgs a) {
             mma_commit_uniform(w_empty + ib);
         }
         LTP_FLUSH(8);
-    } else if (warp == 9) {
-        // ===================================================== parameter image TMA =====================================================
+    } else if (warp == W_TMA) {
+        // ===================================================== TMA: parameter images and x tiles =====================================================
+        uint32_t n_x = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n_item) {
             const uint32_t ib = n_item & 1;
+            const int s = item / a.R, r = item % a.R;
+            const int f_begin = s * a.card, cnt = min(a.card, a.F - f_begin);
             mbar_wait_sticky(w_empty + ib, ((n_item >> 1) & 1) ^ 1, abort_flag);
             if (lane == 0) {
                 mbar_arrive_expect_tx(w_full + ib, a.img_bytes);
@@ -298,6 +300,18 @@ __global__ void __launch_bounds__(320, 1) leaf_tc_fwd_kernel(LeafTcArgs a) {
                     bulk_g2s(Ws + ib * img_stride + off, src + off, min(CH, a.img_bytes - off), w_full + ib);
             }
             __syncwarp();
+            int64_t mysrc = 0;   // lane j: offset of the xT row of the scope's j-th feature
+            if (lane < cnt) mysrc = (int64_t)(a.perm ? a.perm[(int64_t)(f_begin + lane) * a.R + r] : f_begin + lane) * a.ldx;
+            for (int t = 0; t < ntiles; ++t, ++n_x) {
+                const uint32_t xsl = n_x % LT_XD;
+                const int rows4 = min(128, a.ldx - t * 128);   // whole 16-byte groups (xT rows are zero padded to ldx)
+                mbar_wait_sticky(x_empty + xsl, ((n_x / LT_XD) & 1) ^ 1, abort_flag);
+                if (lane == 0) mbar_arrive_expect_tx(x_full + xsl, cnt * rows4 * 4);
+                __syncwarp();
+                // one bulk copy per feature, each issued by its own lane (a single-lane loop cost ~90 clk per copy)
+                if (lane < cnt) bulk_g2s(Xs + xsl * (a.card * 128) + lane * 128, a.xT + mysrc + t * 128, rows4 * 4, x_full + xsl);
+                __syncwarp();
+            }
         }
     } else {
         // ===================================================== epilogue =====================================================
@@ -335,7 +349,7 @@ __global__ void __launch_bounds__(320, 1) leaf_tc_fwd_kernel(LeafTcArgs a) {
                 if (lane == 0) {
                     const int r0 = t * 128 + warp * 32;
                     const int rows = min(32, a.B - r0);
-                    if (rows > 0 && !(a.dbg & 8))
+                    if (rows > 0 && !LT_DBG(8))
                         bulk_s2g(a.out + ((int64_t)item * a.B + r0) * I, os, (uint32_t)(rows * I * 4));
                     bulk_commit_group();
                 }
@@ -349,22 +363,24 @@ __global__ void __launch_bounds__(320, 1) leaf_tc_fwd_kernel(LeafTcArgs a) {
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (warp == 8) tmem_dealloc(tmem_base, 128);
+    if (warp == W_MMA) tmem_dealloc(tmem_base, 512);
     if (threadIdx.x == 0) tc_abort_trap(abort_flag, &g_leaf_tc_aborts);
 }
 
 // --------------------------------------------------------------------------------------------------------------------
 // Backward (parameter gradients).  Work item = (scope, repetition); the accumulator D[M = 5 card][N = 2 I] stays in tensor
-// memory over all rows of the batch (K), in stages of 64 rows.  14 warps:
+// memory over all rows of the batch (K), in stages of 64 rows.  22 warps:
 //   warps 0-3   epilogue (once per item): accumulator -> shared memory -> dmu / dsigma;
-//   warps 4-11  operand producers.  A [M = 5 jj + term][K = row] (terms x2h x2l xh xl valid): thread = (feature jj, K group of
+//   warps 4-19  operand producers.  A [M = 5 jj + term][K = row] (terms x2h x2l xh xl valid): thread = (feature jj, K group of
 //               4 rows): one 16-byte load from xT (one stage ahead), five 16-byte stores; the 8 lanes of a quarter warp hold
 //               8 consecutive features, whose operand rows 5 jj + term fall into 8 different 16-byte bank groups.
 //               B [N = channel (hi) | I + channel (lo)][K = row]: thread = (channel, K group) from the TMA-landed g tile;
-//   warp 12     MMA issuer (8 K = 8 steps per stage);   warp 13   TMA of the g tiles (contiguous 64 * I floats, ring of 6).
+//   warp 20     MMA issuer (8 K = 8 steps per stage);   warp 21   TMA of the g tiles (64 * I floats as four padded 16-row
+//               blocks, ring of up to 6 stages).
 // --------------------------------------------------------------------------------------------------------------------
 constexpr int LB_A_BYTES = 128 * LT_BROWS * 4;   // 32 KB: [16 row groups][16 K groups][8][4]
-constexpr int LB_GRING = 6;
+constexpr int LB_GRING = 6;   // at most; the launch picks the depth that fits (a.gring)
+__host__ __device__ constexpr int lb_gslot_floats(int I) { return 4 * (16 * I + 8); }   // four 16-row blocks, 32 bytes of padding each
 __host__ __device__ constexpr int lb_b_bytes(int I) { return 2 * I * LT_BROWS * 4; }
 
 // long wait (a whole work item): sleep between probes instead of spinning next to the producer warps
@@ -376,15 +392,16 @@ __device__ __forceinline__ void lt_wait_sleepy(uint64_t* bar, uint32_t parity, v
     *abort_flag = 1;
 }
 
-__global__ void __launch_bounds__(448, 1) leaf_tc_bwd_kernel(LeafTcArgs a) {
+__global__ void __launch_bounds__(704, 1) leaf_tc_bwd_kernel(LeafTcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int I = a.I, NG = I / 8;
     const int b_bytes = lb_b_bytes(I);
-    const int graw_bytes = LT_BROWS * I * 4;
+    const int graw_bytes = lb_gslot_floats(I) * 4;
+    const uint32_t gring = a.gring;
     uint8_t* As = smem;                                                   // [2][LB_A_BYTES]
     uint8_t* Bs = As + LT_BSTAGES * LB_A_BYTES;                           // [2][b_bytes]
     uint8_t* Gr = Bs + LT_BSTAGES * b_bytes;                              // [LB_GRING][graw_bytes]
-    float* red = reinterpret_cast<float*>(Gr + LB_GRING * graw_bytes);    // [128][I + 1]
+    float* red = reinterpret_cast<float*>(Gr + gring * graw_bytes);       // [128][I + 1]
     uint64_t* s_full = reinterpret_cast<uint64_t*>(red + 128 * (I + 1));   // 512 (I + 1) bytes: 8-byte aligned
     uint64_t* s_empty = s_full + 2;
     uint64_t* g_full = s_empty + 2;             // [LB_GRING]
@@ -395,23 +412,24 @@ __global__ void __launch_bounds__(448, 1) leaf_tc_bwd_kernel(LeafTcArgs a) {
     volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    constexpr int W_MMA = 20, W_TMA = 21;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(s_full + i, 8);
+            mbar_init(s_full + i, 16);
             mbar_init(s_empty + i, 1);
             mbar_init(acc_full + i, 1);
             mbar_init(acc_empty + i, 4);
         }
         for (int i = 0; i < LB_GRING; ++i) {
             mbar_init(g_full + i, 1);
-            mbar_init(g_empty + i, 8);
+            mbar_init(g_empty + i, 16);
         }
         *abort_flag = 0;
         mbar_fence_init();
     }
     // operand rows 125 .. 127 (and, for short scopes, the rows of absent features) are zero: the former are never written
     for (int i = threadIdx.x; i < LT_BSTAGES * LB_A_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(As)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (warp == 12) tmem_alloc(tmem_slot, 256);
+    if (warp == W_MMA) tmem_alloc(tmem_slot, 256);
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
@@ -422,18 +440,18 @@ __global__ void __launch_bounds__(448, 1) leaf_tc_bwd_kernel(LeafTcArgs a) {
     const int nstages = (a.B + LT_BROWS - 1) / LT_BROWS;
     uint32_t n_stage = 0, n_item = 0;
 
-    if (warp >= 4 && warp < 12) {
+    if (warp >= 4 && warp < 20) {
         // ===================================================== operand producers =====================================================
         const int pw = warp - 4;
         const int l8 = lane & 7, l4 = lane >> 3;
-        // A: this thread's feature and its two K groups per stage
+        // A: this thread's feature and its K group of a stage
         const int jj = (pw & 3) * 8 + l8;
-        const int qa0 = (pw >> 2) * 4 + l4, qa1 = qa0 + 8;
+        const int qa = (pw >> 2) * 4 + l4;
         uint32_t aoff[5];
 #pragma unroll
         for (int t = 0; t < 5; ++t) {
             const int m = 5 * jj + t;
-            aoff[t] = (m >> 3) * 2048 + (m & 7) * 16;
+            aoff[t] = (m >> 3) * 2048 + (m & 7) * 16 + qa * 128;
         }
         const bool arow = jj < LT_MAXCARD;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -442,50 +460,46 @@ __global__ void __launch_bounds__(448, 1) leaf_tc_bwd_kernel(LeafTcArgs a) {
             const bool have = jj < cnt;
             const float* xrow = a.xT;
             if (have) xrow += (int64_t)(a.perm ? a.perm[(int64_t)(f_begin + jj) * a.R + r] : f_begin + jj) * a.ldx;
-            auto xload = [&](int st, int q) {
-                const int bq = st * LT_BROWS + 4 * q;
-                return (have && st < nstages && bq < a.ldx && !(a.dbg & 2)) ? *reinterpret_cast<const float4*>(xrow + bq)
+            auto xload = [&](int st) {
+                const int bq = st * LT_BROWS + 4 * qa;
+                return (have && st < nstages && bq < a.ldx && !LT_DBG(2)) ? *reinterpret_cast<const float4*>(xrow + bq)
                                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
             };
-            float4 xn0 = xload(0, qa0), xn1 = xload(0, qa1);
+            float4 xn = xload(0);
             LTP_DECL;
             for (int st = 0; st < nstages; ++st, ++n_stage) {
-                const uint32_t slot = n_stage & 1, gslot = n_stage % LB_GRING;
+                const uint32_t slot = n_stage & 1, gslot = n_stage % gring;
                 const int nrow = min(LT_BROWS, a.B - st * LT_BROWS);
-                const float4 xc[2] = {xn0, xn1};
-                xn0 = xload(st + 1, qa0);   // one stage ahead
-                xn1 = xload(st + 1, qa1);
+                const float4 xc = xn;
+                xn = xload(st + 1);   // one stage ahead
                 LTP_LAP(0);
                 mbar_wait_sticky(s_empty + slot, ((n_stage >> 1) & 1) ^ 1, abort_flag);
                 LTP_LAP(1);   // wait for the operand stage
-                if (arow && !(a.dbg & 4)) {
+                if (arow && !LT_DBG(4)) {
                     uint8_t* ast = As + slot * LB_A_BYTES;
+                    const float xs[4] = {xc.x, xc.y, xc.z, xc.w};
+                    uint32_t w[5][4];
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const float xs[4] = {xc[k].x, xc[k].y, xc[k].z, xc[k].w};
-                        uint32_t w[5][4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const bool ok = have && xs[e] == xs[e];
-                            const float x = ok ? xs[e] : 0.f;
-                            tf32_split(x * x, w[0][e], w[1][e]);
-                            tf32_split(x, w[2][e], w[3][e]);
-                            w[4][e] = ok ? 0x3F800000u : 0u;
-                        }
-                        uint8_t* dst = ast + (k ? qa1 : qa0) * 128;
-#pragma unroll
-                        for (int t = 0; t < 5; ++t) *reinterpret_cast<uint4*>(dst + aoff[t]) = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
+                    for (int e = 0; e < 4; ++e) {
+                        const bool ok = have && xs[e] == xs[e];
+                        const float x = ok ? xs[e] : 0.f;
+                        tf32_split(x * x, w[0][e], w[1][e]);
+                        tf32_split(x, w[2][e], w[3][e]);
+                        w[4][e] = ok ? 0x3F800000u : 0u;
                     }
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) *reinterpret_cast<uint4*>(ast + aoff[t]) = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
                 }
                 LTP_LAP(2);   // A operand
                 // g tile -> B operand: thread = (channel, K group): 4 rows in, hi and lo words out (16-byte stores)
-                mbar_wait_sticky(g_full + gslot, (n_stage / LB_GRING) & 1, abort_flag);
+                mbar_wait_sticky(g_full + gslot, (n_stage / gring) & 1, abort_flag);
                 LTP_LAP(3);   // wait for the g tile
                 const float* gr = reinterpret_cast<const float*>(Gr + gslot * graw_bytes);
                 uint8_t* bst = Bs + slot * b_bytes;
-                for (int p = pw; p < NG * 4 && !(a.dbg & 16); p += 8) {
-                    const int ig = p >> 2, q = (p & 3) * 4 + l4;
-                    const float* gp = gr + (4 * q) * I + ig * 8 + l8;
+                for (int p = pw; p < NG * 4 && !LT_DBG(16); p += 16) {
+                    // K group q = 4 l4 + (p & 3): the quarter warps read different 16-row blocks, which the padding puts 8 banks apart
+                    const int ig = p >> 2, ql = p & 3, q = l4 * 4 + ql;
+                    const float* gp = gr + l4 * (16 * I + 8) + (4 * ql) * I + ig * 8 + l8;
                     uint32_t gh[4], gl[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) tf32_split(4 * q + u < nrow ? gp[u * I] : 0.f, gh[u], gl[u]);
@@ -504,7 +518,7 @@ __global__ void __launch_bounds__(448, 1) leaf_tc_bwd_kernel(LeafTcArgs a) {
             }
             if (warp == 4) LTP_FLUSH(24);
         }
-    } else if (warp == 12) {
+    } else if (warp == W_MMA) {
         // ===================================================== MMA issuer =====================================================
         const uint32_t idesc = instr_desc_tf32(128, 2 * I);
         const uint32_t as_addr = smem_u32(As), bs_addr = smem_u32(Bs);
@@ -524,7 +538,7 @@ __global__ void __launch_bounds__(448, 1) leaf_tc_bwd_kernel(LeafTcArgs a) {
                     // A [M][K = rows] and B [N][K = rows], K-major: K halves 128 B apart, 8-row groups 2048 B apart
                     const uint64_t adesc = smem_desc(as_addr + slot * LB_A_BYTES + 2 * kk * 128, 128, 2048);
                     const uint64_t bdesc = smem_desc(bs_addr + slot * b_bytes + 2 * kk * 128, 128, 2048);
-                    if (!(a.dbg & 1)) mma_ss_tf32_uniform(acc, adesc, bdesc, idesc, (st | kk) ? 1u : 0u);
+                    if (!LT_DBG(1)) mma_ss_tf32_uniform(acc, adesc, bdesc, idesc, (st | kk) ? 1u : 0u);
                 }
                 mma_commit_uniform(s_empty + slot);
                 LTP_LAP(2);   // MMA issue
@@ -532,18 +546,21 @@ __global__ void __launch_bounds__(448, 1) leaf_tc_bwd_kernel(LeafTcArgs a) {
             mma_commit_uniform(acc_full + ab);
             LTP_FLUSH(32);
         }
-    } else if (warp == 13) {
+    } else if (warp == W_TMA) {
         // ===================================================== g tile TMA =====================================================
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const float* gsrc = a.g + (int64_t)item * a.B * I;
             for (int st = 0; st < nstages; ++st, ++n_stage) {
-                const uint32_t gslot = n_stage % LB_GRING;
+                const uint32_t gslot = n_stage % gring;
                 const int b0 = st * LT_BROWS;
                 const int nrow = min(LT_BROWS, a.B - b0);
-                mbar_wait_sticky(g_empty + gslot, ((n_stage / LB_GRING) & 1) ^ 1, abort_flag);
+                mbar_wait_sticky(g_empty + gslot, ((n_stage / gring) & 1) ^ 1, abort_flag);
                 if (lane == 0) {
                     mbar_arrive_expect_tx(g_full + gslot, nrow * I * 4);
-                    bulk_g2s(Gr + gslot * graw_bytes, gsrc + (int64_t)b0 * I, nrow * I * 4, g_full + gslot);
+                    float* dst = reinterpret_cast<float*>(Gr + gslot * graw_bytes);
+                    for (int blk = 0; blk < 4 && 16 * blk < nrow; ++blk)   // four 16-row blocks, padded apart (bank spread of the B build)
+                        bulk_g2s(dst + blk * (16 * I + 8), gsrc + (int64_t)(b0 + 16 * blk) * I, min(16, nrow - 16 * blk) * I * 4,
+                                 g_full + gslot);
                 }
                 __syncwarp();
             }
@@ -592,17 +609,22 @@ __global__ void __launch_bounds__(448, 1) leaf_tc_bwd_kernel(LeafTcArgs a) {
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (warp == 12) tmem_dealloc(tmem_base, 256);
+    if (warp == W_MMA) tmem_dealloc(tmem_base, 256);
     if (threadIdx.x == 0) tc_abort_trap(abort_flag, &g_leaf_tc_aborts);
 }
 
 int lt_np(int I) { return (I + 15) / 16 * 16; }
 int lt_fwd_smem(int I, int card) {
     const int img_stride = (card * lt_np(I) * 32 + 127) & ~127;
-    return LT_NSTAGE * LT_STAGE + 2 * img_stride + 2 * 128 * I * 4 + LT_XD * card * 512 + 256;
+    return 2 * img_stride + 2 * 128 * I * 4 + LT_XD * card * 512 + 512;
 }
-int lt_bwd_smem(int I) {
-    return LT_BSTAGES * (LB_A_BYTES + lb_b_bytes(I)) + LB_GRING * LT_BROWS * I * 4 + 128 * (I + 1) * 4 + 8 + 256;
+int lt_bwd_smem(int I, int gring) {
+    return LT_BSTAGES * (LB_A_BYTES + lb_b_bytes(I)) + gring * lb_gslot_floats(I) * 4 + 128 * (I + 1) * 4 + 8 + 256;
+}
+int lt_gring(int I) {   // deepest g ring that fits
+    int g = LB_GRING;
+    while (g > 2 && lt_bwd_smem(I, g) > 232448) --g;
+    return g;
 }
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -611,7 +633,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 extern "C" int spn_leaf_tc_supported(int I, int R, int card, int d0) {
     if (I < 8 || I > 64 || I % 8 != 0 || card < 1 || card > LT_MAXCARD || R < 1 || d0 < 1) return 0;
     if ((int64_t)R * d0 > (1 << 24)) return 0;
-    return (lt_fwd_smem(I, card) <= 232448 && lt_bwd_smem(I) <= 232448) ? 1 : 0;
+    return (lt_fwd_smem(I, card) <= 232448 && lt_bwd_smem(I, lt_gring(I)) <= 232448) ? 1 : 0;
 }
 
 extern "C" int64_t spn_leaf_tc_image_bytes(int I, int R, int card, int d0) {
@@ -629,15 +651,16 @@ extern "C" int spn_debug_leaf_tc_prof(long long* out_host, int reset) {
 }
 #endif
 static int g_leaf_tc_dbg = 0;
+#ifdef SPN_LEAF_TC_PROF
 extern "C" int spn_debug_leaf_tc_mode(int mode) { g_leaf_tc_dbg = mode; return 0; }
+#endif
 
 static void lt_fill(LeafTcArgs& a, const float* xT, const int32_t* perm, const float* mu, const float* sigma, int64_t sp_f,
                     int64_t sp_i, int64_t sp_r, int B, int F, int I, int R, int card, int d0) {
     a.xT = xT; a.perm = perm; a.ldx = (B + 3) / 4 * 4;
     a.mu = mu; a.sigma = sigma; a.sp_f = sp_f; a.sp_i = sp_i; a.sp_r = sp_r;
     a.B = B; a.F = F; a.I = I; a.R = R; a.card = card; a.d0 = d0;
-    a.nst = (card + LT_FS - 1) / LT_FS;
-    a.fs = (card + a.nst - 1) / a.nst;
+    a.nst = (card + 7) / 8;
     a.img_bytes = card * lt_np(I) * 32;
     a.dbg = g_leaf_tc_dbg;
 }
@@ -649,7 +672,8 @@ extern "C" int spn_leaf_tc_fwd(const float* xT, const int32_t* perm, const float
                                void* stream) {
     if (!xT || !mu || !sigma || !img || !out || B < 0 || F <= 0 || (int64_t)card * d0 < F || (int64_t)card * (d0 - 1) >= F)
         return SPN_ERR_ARG;   // every scope holds at least one feature
-    if (!spn_leaf_tc_supported(I, R, card, d0) || !aligned16(xT) || !aligned16(out) || (reinterpret_cast<uintptr_t>(img) & 127))
+    if (!spn_leaf_tc_supported(I, R, card, d0) || !aligned16(xT) || !aligned16(out) || (reinterpret_cast<uintptr_t>(img) & 127) ||
+        (int64_t)F * ((B + 3) / 4 * 4) >= (1ll << 31))   // 32-bit row offsets into xT
         return SPN_ERR_UNSUPPORTED;
     if (B == 0) return SPN_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -673,7 +697,7 @@ extern "C" int spn_leaf_tc_fwd(const float* xT, const int32_t* perm, const float
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int nitems = d0 * R;
-    kernel<<<nitems < sms ? nitems : sms, 320, smem, st>>>(a);
+    kernel<<<nitems < sms ? nitems : sms, 448, smem, st>>>(a);
     return spn_launch_status();
 }
 
@@ -689,6 +713,7 @@ extern "C" int spn_leaf_tc_bwd_params(const float* xT, const float* g, const int
     LeafTcArgs a{};
     lt_fill(a, xT, perm, mu, sigma, sp_f, sp_i, sp_r, B, F, I, R, card, d0);
     a.g = g; a.dmu = dmu; a.dsigma = dsigma;
+    a.gring = lt_gring(I);
     static std::atomic<unsigned long long> configured{0};
     int dev = 0, sms = 148;
     if (!tc_configured_on_device(configured, &dev)) {
@@ -698,6 +723,6 @@ extern "C" int spn_leaf_tc_bwd_params(const float* xT, const float* g, const int
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int nitems = d0 * R;
-    leaf_tc_bwd_kernel<<<nitems < sms ? nitems : sms, 448, lt_bwd_smem(I), st>>>(a);
+    leaf_tc_bwd_kernel<<<nitems < sms ? nitems : sms, 704, lt_bwd_smem(I, a.gring), st>>>(a);
     return spn_launch_status();
 }

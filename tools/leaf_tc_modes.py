@@ -1,5 +1,7 @@
-"""Experiment: leaf_tc kernels with parts switched off (spn_debug_leaf_tc_mode bits: 1 no MMA, 2 no x loads, 4 no A-operand
-stores, 8 no bulk store (forward), 16 no B-operand build (backward)); results are garbage, only the times matter."""
+"""Experiment (needs the experiment build: SPN_LEAF_TC_PROF=1 SPN_LIB_OUT=build/variants/libspn_prof.so python
+conditional-ratspn-for-rl_b200/build.py, then SPN_LIB_PATH=build/variants/libspn_prof.so): leaf_tc kernels with parts switched
+off (spn_debug_leaf_tc_mode bits: 1 no MMA, 2 no x reads, 4 no A-operand writes, 8 no bulk store (forward), 16 no B-operand
+build (backward)); results are garbage, only the times matter."""
 import os
 import sys
 
