@@ -41,7 +41,7 @@ METRIC = "ratspn_fwd_bwd_samples_per_sec"
 UNIT = "samples/s"
 # arithmetic of the path: fp32 inputs / outputs / accumulators everywhere; the shared-weight Sum layers multiply bf16
 # operands on the tensor cores (tcgen05 kind::f16) -- inside the north star's 1e-4 relative log-likelihood tolerance
-DTYPE = "f32 io/accumulate, bf16 mma operands"
+DTYPE = "f32 io/accumulate; bf16 mma operands (Sum layers), tf32 x 2 split operands (leaf)"
 
 
 def workload_name(rows_per_gpu=BATCH_PER_GPU):
@@ -583,6 +583,35 @@ def main():
             t_bx = time_alone(lambda: ops.tc_sum_backward_x(h0, out1, g1, wimg, w1, fhand, hand))
             t_bw = time_alone(lambda: ops.tc_sum_backward_w(fhand, hand, h0, out1, g1, w1, logz))
             t_prep = time_alone(lambda: ops.tc_prepare(w1, True))
+        # leaf layer alone (HBM bound: the [d0][R][B][I] activation is written once by the forward, its gradient read
+        # once by the backward): tensor-core kernels (leaf_tc.cu) and, beside them, the exact fp32 kernels
+        leaf = {}
+        try:
+            mu_l, sg_l = (t_.detach().clone().requires_grad_(True) for t_ in model._leaf.base_leaf._params_for(True))
+            perm_l, card_l = model._perm32()[0], model._leaf.cardinality
+            act_bytes = h0.numel() * 4
+            gl = torch.randn_like(h0) / B
+            hbm = peaks.get("hbm_gbs", 0.0) or 0.0
+            for tc_on in (True, False):
+                ops.LEAF_TENSOR_CORES = tc_on
+                try:
+                    t_lf = time_alone(lambda: ops.leaf_forward(resident[0], mu_l.detach(), sg_l.detach(), perm_l, card_l, False, "drbc"))
+                    o_l = ops.leaf_forward(resident[0], mu_l, sg_l, perm_l, card_l, False, "drbc")
+                    def bwd_only():
+                        mu_l.grad = sg_l.grad = None
+                        o_l.backward(gl, retain_graph=True)
+                    t_lb = time_alone(bwd_only)
+                finally:
+                    ops.LEAF_TENSOR_CORES = True
+                leaf["tensor_cores" if tc_on else "exact_fp32"] = {
+                    "fwd_ms": t_lf, "bwd_ms": t_lb, "activation_bytes": act_bytes,
+                    "fwd_write_GBps": act_bytes / t_lf / 1e6, "bwd_read_GBps": act_bytes / t_lb / 1e6,
+                    "fwd_frac_of_hbm_peak": (act_bytes / t_lf / 1e6 / hbm) if hbm else None,
+                    "bwd_frac_of_hbm_peak": (act_bytes / t_lb / 1e6 / hbm) if hbm else None}
+            leaf["note"] = ("fwd = x transpose + parameter image + leaf kernel (spn_leaf_tc_fwd / spn_leaf_tiled_fwd); bwd = parameter "
+                            "gradients; algorithmic bytes = one pass over the [d0][R][B][I] fp32 activation (839 MB)")
+        except Exception as e:   # the roofline line must not die on the side measurement
+            leaf = {"error": repr(e)}
         total_fwd, per_layer = contraction_flops_fwd(B)
         fl = per_layer[0]
         peak = peaks.get("bf16_tflops", 1590.0)
@@ -612,6 +641,7 @@ def main():
                                  "note": "Sum-layer contractions only (fwd + bwd = 3x forward, SURVEY 8d) over the whole training "
                                          "step incl. leaf, root, operand images, all-reduce and Adam"}
         kernels["tc_prepare"] = {"call": "spn_sum_tc_prepare (logz + operand image)", "ms": t_prep}
+        kernels["leaf"] = leaf
         dom = max(("fwd", "dx", "dw"), key=lambda k: kernels[k]["ms"])
         roof = {"bound": "tensor", "kernel": f"{kernels[dom]['call']}, layer S_1 (d=16, K=1600, N=40, R=40), "
                                              f"{fl:.3e} algorithmic flop per call (2*N*d*c^2*S*R)",

@@ -56,6 +56,7 @@ struct LeafTcArgs {
     const float* g;         // backward: [d0][R][B][I]
     const float* mu; const float* sigma; int64_t sp_f, sp_i, sp_r;
     float* dmu; float* dsigma;
+    unsigned int* counter;   // backward: zeroed work counter of this launch (dynamic item scheduling)
     int B, ldx, F, I, R, card, d0, nst, img_bytes, gring, dbg;
 };
 
@@ -380,6 +381,7 @@ __global__ void __launch_bounds__(448, 1) leaf_tc_fwd_kernel(LeafTcArgs a) {
 // --------------------------------------------------------------------------------------------------------------------
 constexpr int LB_A_BYTES = 128 * LT_BROWS * 4;   // 32 KB: [16 row groups][16 K groups][8][4]
 constexpr int LB_GRING = 6;   // at most; the launch picks the depth that fits (a.gring)
+constexpr uint32_t LB_ITRING = 16;   // work-item ring of the backward
 __host__ __device__ constexpr int lb_gslot_floats(int I) { return 4 * (16 * I + 8); }   // four 16-row blocks, 32 bytes of padding each
 __host__ __device__ constexpr int lb_b_bytes(int I) { return 2 * I * LT_BROWS * 4; }
 
@@ -408,8 +410,10 @@ __global__ void __launch_bounds__(704, 1) leaf_tc_bwd_kernel(LeafTcArgs a) {
     uint64_t* g_empty = g_full + LB_GRING;      // [LB_GRING]
     uint64_t* acc_full = g_empty + LB_GRING;    // [2]
     uint64_t* acc_empty = acc_full + 2;         // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* it_full = acc_empty + 2;          // [LB_ITRING] work-item ring: fetched by the TMA warp, read by every warp
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(it_full + LB_ITRING);
     volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+    volatile int* s_item = abort_flag + 1;      // [LB_ITRING]
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     constexpr int W_MMA = 20, W_TMA = 21;
@@ -420,6 +424,7 @@ __global__ void __launch_bounds__(704, 1) leaf_tc_bwd_kernel(LeafTcArgs a) {
             mbar_init(acc_full + i, 1);
             mbar_init(acc_empty + i, 4);
         }
+        for (int i = 0; i < LB_ITRING; ++i) mbar_init(it_full + i, 1);
         for (int i = 0; i < LB_GRING; ++i) {
             mbar_init(g_full + i, 1);
             mbar_init(g_empty + i, 16);
@@ -439,6 +444,16 @@ __global__ void __launch_bounds__(704, 1) leaf_tc_bwd_kernel(LeafTcArgs a) {
     const int nitems = a.d0 * a.R;
     const int nstages = (a.B + LT_BROWS - 1) / LT_BROWS;
     uint32_t n_stage = 0, n_item = 0;
+    // Work items come from an atomic counter (the gradient all-reduce of the layer above runs next to this kernel at N > 1 and
+    // holds SMs: a static share would leave the late CTAs' items for a second wave).  The TMA warp fetches item k + 1 while it
+    // works on item k and publishes it through a ring of LB_ITRING slots.  A slot is never overwritten before its last reader:
+    // the MMA warp starts item e + 2 only after the epilogue released the accumulator of item e, the producers are at most two
+    // stages ahead of the MMA warp and the TMA warp at most LB_GRING stages ahead of the producers -- with >= 1 stage per item
+    // the fetcher is fewer than 12 items ahead of the slowest warp (a ring of 4 deadlocked at 4 stages per item).
+    auto item_at = [&](uint32_t k) -> int {
+        mbar_wait_sticky(it_full + (k % LB_ITRING), (k / LB_ITRING) & 1, abort_flag);
+        return s_item[k % LB_ITRING];
+    };
 
     if (warp >= 4 && warp < 20) {
         // ===================================================== operand producers =====================================================
@@ -454,7 +469,9 @@ __global__ void __launch_bounds__(704, 1) leaf_tc_bwd_kernel(LeafTcArgs a) {
             aoff[t] = (m >> 3) * 2048 + (m & 7) * 16 + qa * 128;
         }
         const bool arow = jj < LT_MAXCARD;
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        for (uint32_t k = 0;; ++k) {
+            const int item = item_at(k);
+            if (item >= nitems) break;
             const int s = item / a.R, r = item % a.R;
             const int f_begin = s * a.card, cnt = min(a.card, a.F - f_begin);
             const bool have = jj < cnt;
@@ -522,7 +539,8 @@ __global__ void __launch_bounds__(704, 1) leaf_tc_bwd_kernel(LeafTcArgs a) {
         // ===================================================== MMA issuer =====================================================
         const uint32_t idesc = instr_desc_tf32(128, 2 * I);
         const uint32_t as_addr = smem_u32(As), bs_addr = smem_u32(Bs);
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n_item) {
+        for (;; ++n_item) {
+            if (item_at(n_item) >= nitems) break;
             const uint32_t ab = n_item & 1;
             mbar_wait_sticky(acc_empty + ab, ((n_item >> 1) & 1) ^ 1, abort_flag);
             const uint32_t acc = tmem_base + ab * 128;
@@ -548,7 +566,19 @@ __global__ void __launch_bounds__(704, 1) leaf_tc_bwd_kernel(LeafTcArgs a) {
         }
     } else if (warp == W_TMA) {
         // ===================================================== g tile TMA =====================================================
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        if (lane == 0) {
+            s_item[0] = (int)blockIdx.x < nitems ? (int)blockIdx.x : nitems;
+            mbar_arrive(it_full);
+        }
+        __syncwarp();
+        for (uint32_t k = 0;; ++k) {
+            const int item = item_at(k);
+            if (lane == 0) {   // publish item k + 1 before the long work on item k
+                s_item[(k + 1) % LB_ITRING] = item < nitems ? (int)min((unsigned int)nitems, gridDim.x + atomicAdd(a.counter, 1u)) : nitems;
+                mbar_arrive(it_full + ((k + 1) % LB_ITRING));
+            }
+            __syncwarp();
+            if (item >= nitems) break;
             const float* gsrc = a.g + (int64_t)item * a.B * I;
             for (int st = 0; st < nstages; ++st, ++n_stage) {
                 const uint32_t gslot = n_stage % gring;
@@ -569,7 +599,9 @@ __global__ void __launch_bounds__(704, 1) leaf_tc_bwd_kernel(LeafTcArgs a) {
         // ===================================================== epilogue =====================================================
         const int m = warp * 32 + lane;
         const int ld = I + 1;
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n_item) {
+        for (;; ++n_item) {
+            const int item = item_at(n_item);
+            if (item >= nitems) break;
             const int s = item / a.R, r = item % a.R;
             const int f_begin = s * a.card, cnt = min(a.card, a.F - f_begin);
             const uint32_t ab = n_item & 1;
@@ -619,7 +651,7 @@ int lt_fwd_smem(int I, int card) {
     return 2 * img_stride + 2 * 128 * I * 4 + LT_XD * card * 512 + 512;
 }
 int lt_bwd_smem(int I, int gring) {
-    return LT_BSTAGES * (LB_A_BYTES + lb_b_bytes(I)) + gring * lb_gslot_floats(I) * 4 + 128 * (I + 1) * 4 + 8 + 256;
+    return LT_BSTAGES * (LB_A_BYTES + lb_b_bytes(I)) + gring * lb_gslot_floats(I) * 4 + 128 * (I + 1) * 4 + 8 + 512;
 }
 int lt_gring(int I) {   // deepest g ring that fits
     int g = LB_GRING;
@@ -723,6 +755,8 @@ extern "C" int spn_leaf_tc_bwd_params(const float* xT, const float* g, const int
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int nitems = d0 * R;
+    a.counter = tc_next_counter(st);
+    if (!a.counter) return SPN_ERR_ARG;
     leaf_tc_bwd_kernel<<<nitems < sms ? nitems : sms, 704, lt_bwd_smem(I, a.gring), st>>>(a);
     return spn_launch_status();
 }

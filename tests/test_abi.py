@@ -67,3 +67,15 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# oracle", ""), fn
+
+
+def test_tensor_core_leaf_shape_gate_is_a_host_function():
+    """spn_leaf_tc_supported / spn_leaf_tc_image_bytes run on the host (no kernel): the gate of ops.LeafFn's tensor-core branch."""
+    import ratspn_b200 as rb
+    lib = rb._abi.lib()
+    assert lib.spn_leaf_tc_supported(40, 40, 25, 32) == 1          # BASELINE config 2
+    assert lib.spn_leaf_tc_supported(64, 64, 16, 64) == 1          # config 5 as named
+    assert lib.spn_leaf_tc_supported(33, 2, 25, 4) == 0            # channels not a multiple of 8
+    assert lib.spn_leaf_tc_supported(40, 40, 26, 32) == 0          # more than 25 features per scope (5 operand rows each, M = 128)
+    assert lib.spn_leaf_tc_supported(72, 2, 8, 4) == 0             # more than 64 channels
+    assert lib.spn_leaf_tc_image_bytes(40, 40, 25, 32) == 32 * 40 * 25 * 48 * 32 + 256

@@ -50,7 +50,7 @@ for mode in [int(v) for v in sys.argv[1:]] or [0]:
         if fn is fwd:
             tiles = items0 * 32
             print(f"mode {mode} forward, block 0: {tiles} tiles; clocks per tile")
-            print("  producer: other %.0f | prefetch issue %.0f | cp.async wait %.0f | ring read %.0f | stage wait %.0f | split+stores %.0f | fence+arrive %.0f" % tuple(t / tiles for t in v[0:7]))
+            print("  producer: other %.0f | x tile wait %.0f | ring read %.0f | stage wait %.0f | split+tcgen05.st %.0f | fence+arrive %.0f" % tuple(t / tiles for t in v[0:6]))
             print("  mma:      other %.0f | image wait %.0f | acc wait %.0f | stage wait %.0f | issue+commit %.0f" % tuple(t / tiles for t in v[8:13]))
             print("  epilogue: other %.0f | acc wait %.0f | tcgen05.ld %.0f | release+staging wait %.0f | staging+store %.0f" % tuple(t / tiles for t in v[16:21]))
         else:
