@@ -233,7 +233,8 @@ class RatSpn(nn.Module):
             return self._forward_layerwise(x, layer_index, x_needs_permutation, detach_params)
 
         caching = self.root._is_input_cache_enabled
-        if self._tensor_core_path_ok(x, caching):
+        # (a pass that ends below the first Sum layer stays on the exact fp32 leaf kernels)
+        if layer_index >= 2 and self._tensor_core_path_ok(x, caching):
             return self._forward_tensor_core(x, layer_index, perm32, detach_params)
         if self._tensor_core_sets_path_ok(x, caching, layer_index):
             return self._forward_tensor_core_sets(x, layer_index, perm32, detach_params)
