@@ -13,6 +13,7 @@ import sys
 
 from . import _abi, ops  # noqa: F401
 from . import type_checks, utils, layers, distributions, rat_spn, cspn, diffsample, parallel, graphs  # noqa: F401
+from . import sb3_adapter  # noqa: F401
 from .graphs import GraphedCall  # noqa: F401
 from .cspn import CSPN, CspnConfig, print_cspn_params  # noqa: F401
 from .distributions import IndependentMultivariate, Leaf, RatNormal, truncated_normal_  # noqa: F401
